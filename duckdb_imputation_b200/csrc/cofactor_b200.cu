@@ -1,0 +1,800 @@
+// cofactor_b200.cu -- the C ABI of include/cofactor_b200.h over the sm_100a kernels.
+//
+// One cfb_ctx is one aggregate state ("SumState" of sum_state.h:14-28 shrunk to a handle):
+// a dense device-resident state (state_layout.h), a stream, the scratch of the Gram kernel
+// and a double-buffered pinned staging ring for host (DuckDB vector) input.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry
+// point returns CFB_ERR_NO_DEVICE.
+#include "../../include/cofactor_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "gram_launch.h"
+#include "scatter_kernels.cuh"
+#include "state_layout.h"
+
+using cfb::Layout;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_timing{0};
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(e_ == cudaErrorMemoryAllocation ? CFB_ERR_OOM : CFB_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                  #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+  } while (0)
+
+int device_count_quiet() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+struct DeviceInfo {
+  int sms = 0;
+  int smem_optin = 0;
+};
+DeviceInfo g_dev[64];
+std::once_flag g_dev_once[64];
+
+const DeviceInfo &dev_info(int d) {
+  std::call_once(g_dev_once[d], [d] {
+    cudaDeviceGetAttribute(&g_dev[d].sms, cudaDevAttrMultiProcessorCount, d);
+    cudaDeviceGetAttribute(&g_dev[d].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d);
+  });
+  return g_dev[d];
+}
+
+struct Stage {
+  char *h = nullptr;  // pinned: [col][tile_rows] x 4 B, numeric cols, cat cols, group slot
+  char *d = nullptr;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+};
+
+}  // namespace
+
+struct cfb_ctx {
+  int device = 0, kind = 0, n = 0, m = 0, G = 1;
+  bool user_domain = false;  // set through cfb_ctx_set_cat_domain: out-of-range keys are errors
+  Layout lay{};
+  Layout *d_lay = nullptr;
+  double *d_f64 = nullptr;
+  unsigned long long *d_u64 = nullptr;
+  int *d_err = nullptr;
+  int *d_minmax = nullptr;  // [2][kMaxCat]
+  cudaStream_t stream = nullptr;
+  cudaStream_t user_stream = nullptr;  // last caller-provided stream of cfb_triple_device
+  // Gram scratch
+  double *d_partials = nullptr;
+  unsigned int *d_ticket = nullptr;
+  int gram_grid = 0;
+  // timing of the most recent device scan
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  // staging ring for host input
+  Stage st[2];
+  size_t tile_rows = 0, fill = 0;
+  int cur = 0;
+  bool uses_group = false;
+  int st_lo[cfb::kMaxCat], st_hi[cfb::kMaxCat];  // min/max of the keys staged in the open tile
+};
+
+namespace {
+
+// ------------------------------------------------------------------------- layout
+void build_layout(Layout &L, int kind, int n, int m, int G, const int *lo, const int *hi) {
+  memset(&L, 0, sizeof(L));
+  L.kind = kind;
+  L.n = n;
+  L.m = m;
+  L.n_groups = G;
+  L.nq = kind == CFB_NB ? n : n * (n + 1) / 2;
+  L.has_domain = (lo != nullptr) || m == 0;
+  long long off = 0;
+  for (int c = 0; c < m; c++) {
+    L.lo[c] = lo ? lo[c] : 0;
+    L.dom[c] = lo ? (int)((long long)hi[c] - lo[c] + 1) : 0;
+    L.cat_off[c] = off;
+    off += L.dom[c];
+  }
+  L.cat_off[m] = off;
+  L.total_dom = off;
+  L.numcat_base = n + L.nq;
+  L.pair_base = 1 + off;
+  long long po = 0;
+  if (kind == CFB_TRIPLE)
+    for (int k = 0; k < m; k++)
+      for (int l = k + 1; l < m; l++) {
+        L.pair_off[k * m + l] = po;
+        po += (long long)L.dom[k] * L.dom[l];
+      }
+  L.F = L.numcat_base + (kind == CFB_TRIPLE ? (long long)n * off : 0);
+  L.U = L.pair_base + po;
+}
+
+constexpr long long kMaxStateBytes = 16ll << 30;
+
+int alloc_state(const Layout &L, double **f, unsigned long long **u, cudaStream_t s) {
+  const long long bf = L.F * L.n_groups * 8, bu = L.U * L.n_groups * 8;
+  if (bf + bu > kMaxStateBytes)
+    return fail(CFB_ERR_DOMAIN, "dense categorical state would need %lld bytes (limit %lld): domain too large",
+                bf + bu, kMaxStateBytes);
+  CU(cudaMalloc(f, std::max<long long>(bf, 8)));
+  CU(cudaMalloc(u, std::max<long long>(bu, 8)));
+  CU(cudaMemsetAsync(*f, 0, std::max<long long>(bf, 8), s));
+  CU(cudaMemsetAsync(*u, 0, std::max<long long>(bu, 8), s));
+  return CFB_OK;
+}
+
+int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, double *df, unsigned long long *du,
+                     const double *sf, const unsigned long long *su, cudaStream_t s) {
+  const long long tot = (sl.F + sl.U) * sl.n_groups;
+  const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
+  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+// Make the context's categorical domain cover [lo, hi] per column, re-laying out the dense
+// state if it has to grow (stream-ordered).
+int ensure_domain(cfb_ctx *c, const int *lo, const int *hi) {
+  if (c->m == 0) return CFB_OK;
+  int nlo[cfb::kMaxCat], nhi[cfb::kMaxCat];
+  bool grow = !c->lay.has_domain;
+  for (int k = 0; k < c->m; k++) {
+    if (c->lay.has_domain) {
+      const int clo = c->lay.lo[k], chi = (int)((long long)c->lay.lo[k] + c->lay.dom[k] - 1);
+      nlo[k] = std::min(clo, lo[k]);
+      nhi[k] = std::max(chi, hi[k]);
+      if (nlo[k] != clo || nhi[k] != chi) grow = true;
+    } else {
+      nlo[k] = lo[k];
+      nhi[k] = hi[k];
+    }
+    if ((long long)nhi[k] - nlo[k] + 1 > (1ll << 30))
+      return fail(CFB_ERR_DOMAIN, "categorical column %d spans [%d,%d]: too large for the dense path", k, nlo[k], nhi[k]);
+  }
+  if (!grow) return CFB_OK;
+  Layout nl;
+  build_layout(nl, c->kind, c->n, c->m, c->G, nlo, nhi);
+  double *nf = nullptr;
+  unsigned long long *nu = nullptr;
+  int rc = alloc_state(nl, &nf, &nu, c->stream);
+  if (rc) return rc;
+  Layout *d_nl = nullptr;
+  CU(cudaMalloc(&d_nl, sizeof(Layout)));
+  CU(cudaMemcpyAsync(d_nl, &nl, sizeof(Layout), cudaMemcpyHostToDevice, c->stream));
+  // carry the old contents over; an old state without a domain has only its numeric part
+  // and N, which the remap handles because its tables are empty
+  rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, c->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));  // &nl and the old arrays must outlive the copies
+  cudaFree(c->d_f64);
+  cudaFree(c->d_u64);
+  cudaFree(c->d_lay);
+  c->d_f64 = nf;
+  c->d_u64 = nu;
+  c->d_lay = d_nl;
+  c->lay = nl;
+  return CFB_OK;
+}
+
+// ------------------------------------------------------------------ Gram dispatch
+template <bool DIAG, int... Ns>
+constexpr std::array<cudaError_t (*)(const cfb::GramLaunchParams &), sizeof...(Ns)> gram_table(
+    std::integer_sequence<int, Ns...>) {
+  return {{cfb::gram_launch<Ns + 1, DIAG>...}};
+}
+const auto kGramTriple = gram_table<false>(std::make_integer_sequence<int, CFB_MAX_NUM>{});
+const auto kGramNb = gram_table<true>(std::make_integer_sequence<int, CFB_MAX_NUM>{});
+
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int launch_gram(cfb_ctx *c, const float *const *cols, unsigned long long rows, cudaStream_t s) {
+  cfb::GramLaunchParams p{};
+  p.cols = cols;
+  p.rows = rows;
+  p.smem_optin = dev_info(c->device).smem_optin;
+  p.max_grid = c->gram_grid;
+  p.stages = env_int("CFB_GRAM_STAGES", 0);
+  p.flush_tiles = env_int("CFB_GRAM_FLUSH_TILES", 0);
+  p.partials = c->d_partials;
+  p.state = c->d_f64;  // ungrouped: slot 0, [lin | quad] leads the f64 array
+  p.ticket = c->d_ticket;
+  p.stream = s;
+  p.device = c->device;
+  const cudaError_t e = (c->kind == CFB_NB ? kGramNb : kGramTriple)[c->n - 1](p);
+  g_launches++;
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "Gram kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+// -------------------------------------------------------------------- device scan
+int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, const int32_t *group,
+                unsigned long long rows, cudaStream_t s) {
+  if (rows == 0) return CFB_OK;
+  for (int k = 0; k < c->n; k++)
+    if (!num[k] || ((uintptr_t)num[k] & 15))
+      return fail(CFB_ERR_INVALID, "numeric column %d must be a 16-byte aligned device pointer", k);
+  for (int k = 0; k < c->m; k++)
+    if (!cat[k]) return fail(CFB_ERR_INVALID, "categorical column %d is NULL", k);
+  cfb::ScanCols sc{};
+  for (int k = 0; k < c->n; k++) sc.num[k] = num[k];
+  for (int k = 0; k < c->m; k++) sc.cat[k] = cat[k];
+  sc.group = group;
+  const bool grouped = group != nullptr;
+  if (c->timed) CU(cudaEventRecord(c->ev0, s));
+  if (!grouped) {
+    if (c->n > 0) {
+      int rc = launch_gram(c, num, rows, s);
+      if (rc) return rc;
+    }
+    cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
+    g_launches++;
+  }
+  if (grouped || c->m > 0) {
+    const int blocks = (int)std::min<unsigned long long>((rows + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
+    cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(sc, c->d_lay, rows, grouped ? 1 : 0, c->d_f64,
+                                                                 c->d_u64, c->d_err);
+    g_launches++;
+  }
+  CU(cudaGetLastError());
+  if (c->timed) CU(cudaEventRecord(c->ev1, s));
+  return CFB_OK;
+}
+
+int check_async_error(cfb_ctx *c) {
+  int e = 0;
+  CU(cudaMemcpyAsync(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (e) {
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    if (e == 1) return fail(CFB_ERR_DOMAIN, "a categorical key lies outside the declared domain");
+    return fail(CFB_ERR_INVALID, "a group slot lies outside [0, n_groups)");
+  }
+  return CFB_OK;
+}
+
+// ------------------------------------------------------------------------ staging
+size_t stage_cols(const cfb_ctx *c) { return (size_t)c->n + c->m + 1; }
+
+int ensure_staging(cfb_ctx *c) {
+  if (c->tile_rows) return CFB_OK;
+  size_t rows = (16u << 20) / (4 * stage_cols(c));
+  if (const char *e = getenv("CFB_STAGE_ROWS")) rows = (size_t)std::max(1ll, atoll(e));
+  rows = std::max<size_t>(1024, (rows + 1023) / 1024 * 1024);
+  const size_t bytes = rows * 4 * stage_cols(c);
+  for (int i = 0; i < 2; i++) {
+    CU(cudaHostAlloc((void **)&c->st[i].h, bytes, cudaHostAllocDefault));
+    CU(cudaMalloc((void **)&c->st[i].d, bytes));
+    CU(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming));
+  }
+  c->tile_rows = rows;
+  c->fill = 0;
+  for (int k = 0; k < c->m; k++) {
+    c->st_lo[k] = INT_MAX;
+    c->st_hi[k] = INT_MIN;
+  }
+  return CFB_OK;
+}
+
+// Ship the open tile to the device and reduce it there; the host moves on to the other tile.
+int flush_tile(cfb_ctx *c) {
+  if (!c->fill) return CFB_OK;
+  Stage &st = c->st[c->cur];
+  const size_t rows = c->fill, tr = c->tile_rows, ncol = stage_cols(c);
+  if (c->m > 0 && !c->user_domain) {
+    int rc = ensure_domain(c, c->st_lo, c->st_hi);
+    if (rc) return rc;
+  }
+  if (rows == tr) {
+    CU(cudaMemcpyAsync(st.d, st.h, tr * 4 * (ncol - (c->uses_group ? 0 : 1)), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    for (size_t k = 0; k < ncol; k++) {
+      if (k == ncol - 1 && !c->uses_group) break;
+      CU(cudaMemcpyAsync(st.d + k * tr * 4, st.h + k * tr * 4, rows * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  const float *num[CFB_MAX_NUM];
+  const int32_t *cat[cfb::kMaxCat];
+  for (int k = 0; k < c->n; k++) num[k] = (const float *)(st.d + (size_t)k * tr * 4);
+  for (int k = 0; k < c->m; k++) cat[k] = (const int32_t *)(st.d + (size_t)(c->n + k) * tr * 4);
+  const int32_t *grp = c->uses_group ? (const int32_t *)(st.d + (size_t)(c->n + c->m) * tr * 4) : nullptr;
+  int rc = scan_device(c, num, cat, grp, rows, c->stream);
+  if (rc) return rc;
+  CU(cudaEventRecord(st.done, c->stream));
+  st.in_flight = true;
+  c->cur ^= 1;
+  c->fill = 0;
+  for (int k = 0; k < c->m; k++) {
+    c->st_lo[k] = INT_MAX;
+    c->st_hi[k] = INT_MIN;
+  }
+  Stage &nx = c->st[c->cur];
+  if (nx.in_flight) {
+    CU(cudaEventSynchronize(nx.done));
+    nx.in_flight = false;
+  }
+  return CFB_OK;
+}
+
+template <class T>
+inline void gather(T *dst, const T *src, const uint32_t *sel, size_t first, size_t cnt) {
+  if (!sel)
+    memcpy(dst, src + first, cnt * sizeof(T));
+  else
+    for (size_t i = 0; i < cnt; i++) dst[i] = src[sel[first + i]];
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+int cfb_abi_version(void) { return CFB_ABI_VERSION; }
+int cfb_device_count(void) { return device_count_quiet(); }
+const char *cfb_last_error(void) { return g_err.c_str(); }
+uint64_t cfb_kernel_launches(void) { return g_launches.load(); }
+int cfb_set_timing(int enabled) {
+  g_timing = enabled ? 1 : 0;
+  return CFB_OK;
+}
+
+int cfb_ctx_create(int device, int kind, int n_num, int n_cat, int n_groups, cfb_ctx **out) {
+  if (!out) return fail(CFB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (kind != CFB_TRIPLE && kind != CFB_NB) return fail(CFB_ERR_INVALID, "unknown kind %d", kind);
+  if (n_num < 0 || n_num > CFB_MAX_NUM || n_cat < 0 || n_cat > CFB_MAX_CAT || n_groups < 1)
+    return fail(CFB_ERR_INVALID, "bad shape n_num=%d n_cat=%d n_groups=%d", n_num, n_cat, n_groups);
+  const int nd = device_count_quiet();
+  if (nd == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+  if (device < 0 || device >= nd) return fail(CFB_ERR_INVALID, "device %d out of range (0..%d)", device, nd - 1);
+  CU(cudaSetDevice(device));
+  cfb_ctx *c = new cfb_ctx();
+  c->device = device;
+  c->kind = kind;
+  c->n = n_num;
+  c->m = n_cat;
+  c->G = n_groups;
+  c->timed = g_timing.load() != 0;
+  auto bail = [&](int rc) {
+    cfb_ctx_destroy(c);
+    return rc;
+  };
+#define CUB(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return bail(fail(e_ == cudaErrorMemoryAllocation ? CFB_ERR_OOM : CFB_ERR_CUDA, "%s: %s", #call, \
+                       cudaGetErrorString(e_)));                                               \
+  } while (0)
+  CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  build_layout(c->lay, kind, n_num, n_cat, n_groups, nullptr, nullptr);
+  int rc = alloc_state(c->lay, &c->d_f64, &c->d_u64, c->stream);
+  if (rc) return bail(rc);
+  CUB(cudaMalloc(&c->d_lay, sizeof(Layout)));
+  CUB(cudaMemcpyAsync(c->d_lay, &c->lay, sizeof(Layout), cudaMemcpyHostToDevice, c->stream));
+  CUB(cudaMalloc(&c->d_err, sizeof(int)));
+  CUB(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  CUB(cudaMalloc(&c->d_minmax, 2 * cfb::kMaxCat * sizeof(int)));
+  c->gram_grid = dev_info(device).sms;
+  if (const char *e = getenv("CFB_GRAM_GRID")) c->gram_grid = std::max(1, atoi(e));
+  CUB(cudaMalloc(&c->d_partials, (size_t)c->gram_grid * (n_num + n_num * (n_num + 1) / 2 + 1) * sizeof(double)));
+  CUB(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
+  CUB(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int), c->stream));
+  CUB(cudaEventCreate(&c->ev0));
+  CUB(cudaEventCreate(&c->ev1));
+  CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+  *out = c;
+  return CFB_OK;
+}
+
+int cfb_ctx_destroy(cfb_ctx *c) {
+  if (!c) return CFB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto &s : c->st) {
+    if (s.h) cudaFreeHost(s.h);
+    if (s.d) cudaFree(s.d);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  cudaFree(c->d_f64);
+  cudaFree(c->d_u64);
+  cudaFree(c->d_lay);
+  cudaFree(c->d_err);
+  cudaFree(c->d_minmax);
+  cudaFree(c->d_partials);
+  cudaFree(c->d_ticket);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
+  delete c;
+  return CFB_OK;
+}
+
+int cfb_ctx_set_cat_domain(cfb_ctx *c, const int32_t *lo, const int32_t *hi) {
+  if (!c || !lo || !hi) return fail(CFB_ERR_INVALID, "NULL argument");
+  for (int k = 0; k < c->m; k++)
+    if (hi[k] < lo[k]) return fail(CFB_ERR_INVALID, "empty domain for categorical column %d", k);
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_domain(c, lo, hi);
+  if (rc) return rc;
+  c->user_domain = true;
+  return CFB_OK;
+}
+
+int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *const *num_sel,
+                   const int32_t *const *cat_cols, const uint32_t *const *cat_sel, const uint32_t *group_slot,
+                   size_t count) {
+  if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (count == 0) return CFB_OK;
+  if ((c->n && !num_cols) || (c->m && !cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  if (group_slot && !c->uses_group) {
+    if (c->fill) {  // rows staged so far had no slot column: they belong to slot 0
+      memset(c->st[c->cur].h + (size_t)(c->n + c->m) * c->tile_rows * 4, 0, c->fill * 4);
+    }
+    c->uses_group = true;
+  }
+  size_t done = 0;
+  while (done < count) {
+    const size_t take = std::min(count - done, c->tile_rows - c->fill);
+    char *base = c->st[c->cur].h;
+    const size_t tr = c->tile_rows;
+    for (int k = 0; k < c->n; k++)
+      gather((float *)(base + (size_t)k * tr * 4) + c->fill, num_cols[k], num_sel ? num_sel[k] : nullptr, done, take);
+    for (int k = 0; k < c->m; k++) {
+      int32_t *dst = (int32_t *)(base + (size_t)(c->n + k) * tr * 4) + c->fill;
+      gather(dst, cat_cols[k], cat_sel ? cat_sel[k] : nullptr, done, take);
+      if (!c->user_domain) {
+        int lo = c->st_lo[k], hi = c->st_hi[k];
+        for (size_t i = 0; i < take; i++) {
+          lo = std::min(lo, dst[i]);
+          hi = std::max(hi, dst[i]);
+        }
+        c->st_lo[k] = lo;
+        c->st_hi[k] = hi;
+      }
+    }
+    if (c->uses_group) {
+      uint32_t *dst = (uint32_t *)(base + (size_t)(c->n + c->m) * tr * 4) + c->fill;
+      if (group_slot)
+        memcpy(dst, group_slot + done, take * 4);
+      else
+        memset(dst, 0, take * 4);
+    }
+    c->fill += take;
+    done += take;
+    if (c->fill == c->tile_rows) {
+      rc = flush_tile(c);
+      if (rc) return rc;
+    }
+  }
+  return CFB_OK;
+}
+
+int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
+                      const int32_t *d_group_slot, size_t n_rows, void *stream) {
+  if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if ((c->n && !d_num_cols) || (c->m && !d_cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (stream) c->user_stream = s;
+  if (c->m > 0 && !c->user_domain && n_rows > 0) {
+    // no declared domain: one extra pass finds [min,max] of every categorical column
+    int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+    int rc = cfb_cat_minmax_device(c->device, d_cat_cols, c->m, n_rows, lo, hi, s);
+    if (rc) return rc;
+    rc = ensure_domain(c, lo, hi);
+    if (rc) return rc;
+  }
+  return scan_device(c, d_num_cols, d_cat_cols, d_group_slot, n_rows, s);
+}
+
+int cfb_ctx_sync(cfb_ctx *c) {
+  if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  int rc = flush_tile(c);
+  if (rc) return rc;
+  if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
+  return check_async_error(c);
+}
+
+double cfb_last_scan_ms(cfb_ctx *c) {
+  if (!c || !c->timed) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0;
+  }
+  return (double)ms;
+}
+
+int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
+  cfb_ctx *src = const_cast<cfb_ctx *>(src_c);
+  if (!dst || !src) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (dst == src) return fail(CFB_ERR_INVALID, "cannot combine a context with itself");
+  if (dst->kind != src->kind || dst->n != src->n || dst->m != src->m || dst->G != src->G)
+    return fail(CFB_ERR_INVALID, "combine: shapes differ");
+  int rc = cfb_ctx_sync(src);
+  if (rc) return rc;
+  CU(cudaSetDevice(dst->device));
+  rc = flush_tile(dst);
+  if (rc) return rc;
+  if (src->m > 0 && !src->lay.has_domain) {
+    // src never saw a categorical key: only N / lin / quad can be non-zero, handled below
+  } else if (src->m > 0) {
+    int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+    for (int k = 0; k < src->m; k++) {
+      lo[k] = src->lay.lo[k];
+      hi[k] = (int)((long long)src->lay.lo[k] + src->lay.dom[k] - 1);
+    }
+    rc = ensure_domain(dst, lo, hi);
+    if (rc) return rc;
+  }
+  const double *sf = src->d_f64;
+  const unsigned long long *su = src->d_u64;
+  const Layout *sl = src->d_lay;
+  double *tf = nullptr;
+  unsigned long long *tu = nullptr;
+  Layout *tl = nullptr;
+  if (src->device != dst->device) {
+    // stage the source state on dst's device (peer copy; the driver routes it over NVLink)
+    const size_t bf = std::max<long long>(8, src->lay.F * src->lay.n_groups * 8);
+    const size_t bu = std::max<long long>(8, src->lay.U * src->lay.n_groups * 8);
+    CU(cudaMalloc(&tf, bf));
+    CU(cudaMalloc(&tu, bu));
+    CU(cudaMalloc(&tl, sizeof(Layout)));
+    CU(cudaMemcpyPeerAsync(tf, dst->device, src->d_f64, src->device, bf, dst->stream));
+    CU(cudaMemcpyPeerAsync(tu, dst->device, src->d_u64, src->device, bu, dst->stream));
+    CU(cudaMemcpyAsync(tl, &src->lay, sizeof(Layout), cudaMemcpyHostToDevice, dst->stream));
+    sf = tf;
+    su = tu;
+    sl = tl;
+  }
+  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(dst->stream));
+  cudaFree(tf);
+  cudaFree(tu);
+  cudaFree(tl);
+  return CFB_OK;
+}
+
+int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
+  if (!c || !out) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (group < 0 || group >= c->G) return fail(CFB_ERR_INVALID, "group %d out of range", group);
+  memset(out, 0, sizeof(*out));
+  int rc = cfb_ctx_sync(c);
+  if (rc) return rc;
+  const Layout &L = c->lay;
+  std::vector<double> f(std::max<long long>(1, L.F));
+  std::vector<unsigned long long> u(std::max<long long>(1, L.U));
+  CU(cudaMemcpyAsync(f.data(), c->d_f64 + (long long)group * L.F, L.F * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(u.data(), c->d_u64 + (long long)group * L.U, L.U * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int n = c->n, m = c->m;
+  out->kind = c->kind;
+  out->n_num = n;
+  out->n_cat = m;
+  out->N = (int64_t)u[0];
+  out->n_quad = L.nq;
+  auto dupv = [](const auto &v) {
+    using T = typename std::decay<decltype(v)>::type::value_type;
+    T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+    if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+  };
+  out->lin = dupv(std::vector<double>(f.begin(), f.begin() + n));
+  out->quad = dupv(std::vector<double>(f.begin() + n, f.begin() + n + L.nq));
+  // keys that occurred, ascending per column: the iteration order of the reference's std::map
+  std::vector<int32_t> keys;
+  std::vector<int64_t> counts, offs(m + 1, 0), dense_t;
+  for (int k = 0; k < m; k++) {
+    for (int s = 0; s < L.dom[k]; s++) {
+      const unsigned long long cnt = u[1 + L.cat_off[k] + s];
+      if (cnt) {
+        keys.push_back((int32_t)((long long)L.lo[k] + s));
+        counts.push_back((int64_t)cnt);
+        dense_t.push_back(L.cat_off[k] + s);
+      }
+    }
+    offs[k + 1] = (int64_t)keys.size();
+  }
+  out->total_keys = (int64_t)keys.size();
+  out->cat_offsets = dupv(offs);
+  out->cat_keys = dupv(keys);
+  out->cat_counts = dupv(counts);
+  if (c->kind == CFB_TRIPLE) {
+    std::vector<double> nc((size_t)n * keys.size());
+    for (int i = 0; i < n; i++)
+      for (size_t t = 0; t < keys.size(); t++)
+        nc[(size_t)i * keys.size() + t] = f[L.numcat_base + (long long)i * L.total_dom + dense_t[t]];
+    out->numcat_sums = dupv(nc);
+    out->n_pair_lists = (int64_t)m * (m + 1) / 2;
+    std::vector<int64_t> po(out->n_pair_lists + 1, 0), pc;
+    std::vector<int32_t> k1, k2;
+    int p = 0;
+    for (int k = 0; k < m; k++)
+      for (int l = k; l < m; l++, p++) {
+        if (k == l) {
+          // (key,key,count): the diagonal pair table is the key count itself
+          for (int64_t t = offs[k]; t < offs[k + 1]; t++) {
+            k1.push_back(keys[t]);
+            k2.push_back(keys[t]);
+            pc.push_back(counts[t]);
+          }
+        } else {
+          const unsigned long long *tab = u.data() + L.pair_base + L.pair_off[k * m + l];
+          // only slots whose keys occurred can be non-zero: walk the occurred keys of k and l
+          for (int64_t a = offs[k]; a < offs[k + 1]; a++) {
+            const long long sk = dense_t[a] - L.cat_off[k];
+            for (int64_t b = offs[l]; b < offs[l + 1]; b++) {
+              const long long s2 = dense_t[b] - L.cat_off[l];
+              const unsigned long long cnt = tab[sk * L.dom[l] + s2];
+              if (cnt) {
+                k1.push_back(keys[a]);
+                k2.push_back(keys[b]);
+                pc.push_back((int64_t)cnt);
+              }
+            }
+          }
+        }
+        po[p + 1] = (int64_t)k1.size();
+      }
+    out->pair_offsets = dupv(po);
+    out->pair_key1 = dupv(k1);
+    out->pair_key2 = dupv(k2);
+    out->pair_counts = dupv(pc);
+  } else {
+    out->n_pair_lists = 0;
+    out->pair_offsets = dupv(std::vector<int64_t>(1, 0));
+  }
+  return CFB_OK;
+}
+
+void cfb_result_free(cfb_result *r) {
+  if (!r) return;
+  free(r->lin);
+  free(r->quad);
+  free(r->cat_offsets);
+  free(r->cat_keys);
+  free(r->cat_counts);
+  free(r->numcat_sums);
+  free(r->pair_offsets);
+  free(r->pair_key1);
+  free(r->pair_key2);
+  free(r->pair_counts);
+  memset(r, 0, sizeof(*r));
+}
+
+int cfb_ctx_partial_sizes(cfb_ctx *c, size_t *n_f64, size_t *n_u64) {
+  if (!c || !n_f64 || !n_u64) return fail(CFB_ERR_INVALID, "NULL argument");
+  *n_f64 = (size_t)(c->lay.F * c->lay.n_groups);
+  *n_u64 = (size_t)(c->lay.U * c->lay.n_groups);
+  return CFB_OK;
+}
+
+int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
+  if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  int rc = cfb_ctx_sync(c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (c->lay.F) CU(cudaMemcpyAsync(d_f64, c->d_f64, c->lay.F * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(d_u64, c->d_u64, c->lay.U * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  return CFB_OK;
+}
+
+int cfb_ctx_import_partial(cfb_ctx *c, const void *d_f64, const void *d_u64, void *stream) {
+  if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  int rc = cfb_ctx_sync(c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (c->lay.F) CU(cudaMemcpyAsync(c->d_f64, d_f64, c->lay.F * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->d_u64, d_u64, c->lay.U * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  return CFB_OK;
+}
+
+int cfb_cat_minmax_device(int device, const int32_t *const *d_cat_cols, int n_cat, size_t n_rows, int32_t *lo_out,
+                          int32_t *hi_out, void *stream) {
+  if (!d_cat_cols || !lo_out || !hi_out || n_cat < 0 || n_cat > CFB_MAX_CAT) return fail(CFB_ERR_INVALID, "bad argument");
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible");
+  if (n_cat == 0) return CFB_OK;
+  CU(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int h[2 * cfb::kMaxCat];
+  for (int k = 0; k < cfb::kMaxCat; k++) {
+    h[k] = INT_MAX;
+    h[cfb::kMaxCat + k] = INT_MIN;
+  }
+  int *d = nullptr;
+  CU(cudaMalloc(&d, sizeof(h)));
+  CU(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s));
+  cfb::ScanCols sc{};
+  for (int k = 0; k < n_cat; k++) sc.cat[k] = d_cat_cols[k];
+  if (n_rows) {
+    const int bx = (int)std::min<size_t>((n_rows + 255) / 256, (size_t)std::max(1, dev_info(device).sms * 8 / n_cat));
+    cfb::cat_minmax_kernel<<<dim3(std::max(bx, 1), n_cat), 256, 0, s>>>(sc, n_rows, d, d + cfb::kMaxCat);
+    g_launches++;
+  }
+  CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  cudaFree(d);
+  for (int k = 0; k < n_cat; k++) {
+    if (h[k] > h[cfb::kMaxCat + k]) h[k] = h[cfb::kMaxCat + k] = 0;  // no rows
+    lo_out[k] = h[k];
+    hi_out[k] = h[cfb::kMaxCat + k];
+  }
+  return CFB_OK;
+}
+
+// ------------------------------------------------------- synthetic data (tests, bench)
+int cfb_gen_uniform_f32(int device, float *d_out, size_t n, uint64_t seed, uint64_t first, void *stream) {
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible");
+  CU(cudaSetDevice(device));
+  if (!n) return CFB_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)dev_info(device).sms * 16);
+  cfb::gen_uniform_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, n, seed, first);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+int cfb_gen_int32(int device, int32_t *d_out, size_t n, uint64_t seed, uint64_t first, int32_t lo, uint32_t range,
+                  void *stream) {
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible");
+  if (range == 0) return fail(CFB_ERR_INVALID, "range must be > 0");
+  CU(cudaSetDevice(device));
+  if (!n) return CFB_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)dev_info(device).sms * 16);
+  cfb::gen_int_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, n, seed, first, lo, range);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// scatter_kernels.cuh -- kernel family K3 (categorical aggregates) and the grouped path.
+//
+// Replaces the per-row std::map updates of Triple::SumNoLift (sum_no_lift.cpp:158-214) and
+// Triple::sum_to_nb_agg (sum_to_nb_agg.cpp:124-145): per categorical column the key count
+// (lin_cat) and the per-key numeric sums (quad_num_cat), per column pair the (key1,key2)
+// counts (quad_cat) -- and, when rows are routed to GROUP BY slots, also N / lin / quad of
+// each slot (the states[sdata.sel->get_index(j)] indirection of the reference).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "state_layout.h"
+
+namespace cfb {
+
+struct ScanCols {
+  const float *num[32];
+  const int32_t *cat[32];
+  const int32_t *group;  // per-row slot or nullptr
+};
+
+__device__ __forceinline__ void add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+
+// ---------------------------------------------------------------------------------------
+// Generic scan: one thread per row, every update an atomic on the dense context state.
+// Used for GROUP BY scans and as the categorical kernel for domains too large for the
+// shared-memory privatised kernel below.  do_numeric = also accumulate N / lin / quad.
+__global__ void __launch_bounds__(256)
+    generic_scan_kernel(const ScanCols cols, const Layout *__restrict__ lay_g, unsigned long long n_rows,
+                        int do_numeric, double *__restrict__ f64, unsigned long long *__restrict__ u64,
+                        int *__restrict__ err) {
+  __shared__ Layout lay;
+  {
+    const int *src = reinterpret_cast<const int *>(lay_g);
+    int *dst = reinterpret_cast<int *>(&lay);
+    for (int i = threadIdx.x; i < (int)(sizeof(Layout) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int n = lay.n, m = lay.m;
+  const bool triple = lay.kind == 0;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+       r += (unsigned long long)gridDim.x * blockDim.x) {
+    int g = cols.group ? cols.group[r] : 0;
+    if (g < 0 || g >= lay.n_groups) {
+      atomicExch(err, 2);
+      continue;
+    }
+    double *F = f64 + (long long)g * lay.F;
+    unsigned long long *U = u64 + (long long)g * lay.U;
+    float x[32];
+    for (int k = 0; k < n; k++) x[k] = cols.num[k][r];
+    if (do_numeric) {
+      add_u64(U, 1ull);
+      for (int k = 0; k < n; k++) atomicAdd(F + k, (double)x[k]);
+      if (triple) {
+        int p = n;
+        for (int i = 0; i < n; i++)
+          for (int j = i; j < n; j++, p++) atomicAdd(F + p, (double)x[i] * (double)x[j]);
+      } else {
+        for (int i = 0; i < n; i++) atomicAdd(F + n + i, (double)x[i] * (double)x[i]);
+      }
+    }
+    int s[32];
+    bool ok = true;
+    for (int c = 0; c < m; c++) {
+      const long long d = (long long)cols.cat[c][r] - (long long)lay.lo[c];
+      if (d < 0 || d >= lay.dom[c]) ok = false;
+      s[c] = (int)d;
+    }
+    if (!ok) {
+      atomicExch(err, 1);
+      continue;
+    }
+    for (int c = 0; c < m; c++) {
+      const long long t = lay.cat_off[c] + s[c];
+      add_u64(U + 1 + t, 1ull);
+      if (triple)
+        for (int i = 0; i < n; i++) atomicAdd(F + lay.numcat_base + (long long)i * lay.total_dom + t, (double)x[i]);
+    }
+    if (triple)
+      for (int k = 0; k < m; k++)
+        for (int l = k + 1; l < m; l++)
+          add_u64(U + lay.pair_base + lay.pair_off[k * m + l] + (long long)s[k] * lay.dom[l] + s[l], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// N += rows for an ungrouped scan (the count needs no pass over the data).
+__global__ void add_rows_kernel(unsigned long long *u64, unsigned long long rows) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) u64[0] += rows;
+}
+
+// ---------------------------------------------------------------------------------------
+// Observed [min,max] of categorical columns (blockIdx.y = column).
+__global__ void __launch_bounds__(256)
+    cat_minmax_kernel(const ScanCols cols, unsigned long long n_rows, int *__restrict__ lo, int *__restrict__ hi) {
+  const int32_t *col = cols.cat[blockIdx.y];
+  int mn = INT32_MAX, mx = INT32_MIN;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+       r += (unsigned long long)gridDim.x * blockDim.x) {
+    const int v = col[r];
+    mn = min(mn, v);
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMin(lo + blockIdx.y, mn);
+    atomicMax(hi + blockIdx.y, mx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dst += src where both are dense states with the same (kind, n, m, n_groups) and src's
+// categorical domain lies inside dst's.  Used by combine (sum_state.cpp:23-112), by domain
+// growth and by import/export of partials.  One thread per src element.
+__global__ void __launch_bounds__(256)
+    remap_add_kernel(const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g, double *__restrict__ df,
+                     unsigned long long *__restrict__ du, const double *__restrict__ sf,
+                     const unsigned long long *__restrict__ su) {
+  __shared__ Layout dl, sl;
+  {
+    const int *a = reinterpret_cast<const int *>(dl_g), *b = reinterpret_cast<const int *>(sl_g);
+    int *da = reinterpret_cast<int *>(&dl), *db = reinterpret_cast<int *>(&sl);
+    for (int i = threadIdx.x; i < (int)(sizeof(Layout) / sizeof(int)); i += blockDim.x) {
+      da[i] = a[i];
+      db[i] = b[i];
+    }
+  }
+  __syncthreads();
+  const int n = sl.n, m = sl.m;
+  const long long totF = sl.F * sl.n_groups, totU = sl.U * sl.n_groups;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < totF + totU;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e < totF) {
+      const long long g = e / sl.F, o = e % sl.F;
+      const double v = sf[e];
+      if (v == 0.0) continue;
+      long long d;
+      if (o < sl.numcat_base) {
+        d = o;
+      } else {
+        const long long q = o - sl.numcat_base, i = q / sl.total_dom, t = q % sl.total_dom;
+        int c = 0;
+        while (c + 1 < m && t >= sl.cat_off[c + 1]) c++;
+        const long long slot = t - sl.cat_off[c] + (sl.lo[c] - dl.lo[c]);
+        d = dl.numcat_base + i * dl.total_dom + dl.cat_off[c] + slot;
+      }
+      df[g * dl.F + d] += v;
+    } else {
+      const long long e2 = e - totF, g = e2 / sl.U, o = e2 % sl.U;
+      const unsigned long long v = su[e2];
+      if (v == 0ull) continue;
+      long long d;
+      if (o == 0) {
+        d = 0;
+      } else if (o < sl.pair_base) {
+        const long long t = o - 1;
+        int c = 0;
+        while (c + 1 < m && t >= sl.cat_off[c + 1]) c++;
+        d = 1 + dl.cat_off[c] + (t - sl.cat_off[c]) + (sl.lo[c] - dl.lo[c]);
+      } else {
+        const long long q = o - sl.pair_base;
+        int k = 0, l = 1;
+        // find the pair table that contains q (tables are laid out in (k<l) row-major order)
+        for (int a = 0; a < m; a++)
+          for (int b = a + 1; b < m; b++)
+            if (q >= sl.pair_off[a * m + b]) {
+              k = a;
+              l = b;
+            }
+        const long long w = q - sl.pair_off[k * m + l];
+        const long long sk = w / sl.dom[l] + (sl.lo[k] - dl.lo[k]), s2 = w % sl.dom[l] + (sl.lo[l] - dl.lo[l]);
+        d = dl.pair_base + dl.pair_off[k * m + l] + sk * dl.dom[l] + s2;
+      }
+      du[g * dl.U + d] += v;
+    }
+  }
+  (void)n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic columns for tests and bench (counter-based, so the host can regenerate any
+// slice bit-for-bit: see duckdb_imputation_b200/synth.py).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void gen_uniform_kernel(float *out, unsigned long long n, unsigned long long seed, unsigned long long first) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t h = mix64(seed * 0xD1342543DE82EF95ull + first + i);
+    out[i] = (float)(h >> 40) * (1.0f / 16777216.0f);
+  }
+}
+
+__global__ void gen_int_kernel(int32_t *out, unsigned long long n, unsigned long long seed, unsigned long long first,
+                               int lo, unsigned int range) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t h = mix64(seed * 0xD1342543DE82EF95ull + first + i);
+    out[i] = lo + (int)((h >> 33) % range);
+  }
+}
+
+}  // namespace cfb

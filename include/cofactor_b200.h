@@ -1,0 +1,200 @@
+/*
+ * cofactor_b200.h -- C ABI of the B200-native cofactor / triple aggregate.
+ *
+ * This is the drop-in boundary for the ONE hot path of eddbase/duckdb-imputation:
+ * the ring ("triple") sum aggregates sum_to_triple_x_y, sum_to_nb_agg_x_y,
+ * sum_triple, sum_nb_agg (and the to_cofactor lift that feeds sum_triple).
+ * The reference has no FFI of its own -- the only callers are the DuckDB
+ * aggregate callbacks -- so every entry point below cites the reference
+ * callback (file:line under /root/reference/duckdb_extension/src) whose work it
+ * replaces.  The DuckDB-side glue that binds them lives in
+ * duckdb_imputation_b200/csrc/duckdb_glue.cpp and is described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, POD arguments, no torch / DuckDB / CUDA types in any signature
+ *     (streams and device pointers travel as void*);
+ *   - every function returns CFB_OK (0) or a negative cfb_status; the message
+ *     for the calling thread's last failure is cfb_last_error();
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with CFB_ERR_NO_DEVICE;
+ *   - a cfb_ctx is the aggregate state ("SumState" shrinks to {cfb_ctx*}); it is
+ *     re-entrant per context: distinct threads may drive distinct contexts
+ *     concurrently, one thread at a time per context.
+ */
+#ifndef COFACTOR_B200_H
+#define COFACTOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFB_ABI_VERSION 1
+
+typedef enum cfb_status {
+  CFB_OK = 0,
+  CFB_ERR_INVALID = -1,   /* bad argument / shape mismatch                    */
+  CFB_ERR_NO_DEVICE = -2, /* no CUDA device or driver; never falls back to CPU */
+  CFB_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed              */
+  CFB_ERR_OOM = -4,       /* host or device allocation failed                  */
+  CFB_ERR_DOMAIN = -5,    /* categorical domain too large for the dense path   */
+  CFB_ERR_STATE = -6      /* call sequence violation (e.g. append after free)  */
+} cfb_status;
+
+/* Which ring the context accumulates.
+ * CFB_TRIPLE  : N, lin_agg, quad_agg (packed upper triangle), lin_cat,
+ *               quad_num_cat, quad_cat      -- Triple::SumNoLift, sum_no_lift.cpp:53-216
+ * CFB_NB      : N, lin_agg, quad_agg (diagonal only), lin_cat
+ *                                            -- Triple::sum_to_nb_agg, sum_to_nb_agg.cpp:39-146 */
+typedef enum cfb_kind { CFB_TRIPLE = 0, CFB_NB = 1 } cfb_kind;
+
+#define CFB_MAX_NUM 32 /* FLOAT columns per aggregate (reference grid: 0..19, README: 20) */
+#define CFB_MAX_CAT 32 /* INTEGER columns per aggregate                                   */
+
+typedef struct cfb_ctx cfb_ctx;
+
+/* ------------------------------------------------------------------ runtime */
+
+/* ABI version of the loaded library (== CFB_ABI_VERSION of the header it was built from). */
+int cfb_abi_version(void);
+
+/* Number of visible CUDA devices (0 when there is no driver/GPU). Never fails. */
+int cfb_device_count(void);
+
+/* Message of the calling thread's most recent failing call ("" if none). */
+const char *cfb_last_error(void);
+
+/* -------------------------------------------------------- aggregate context */
+
+/* Replaces StateFunction::Initialize (sum_state.h:33-45) plus the lazy shape
+ * allocation inside update (sum_no_lift.cpp:96-116 / sum_to_nb_agg.cpp:75-95).
+ * n_groups >= 1: the context holds n_groups independent states (GROUP BY slots);
+ * rows are routed by a per-row slot id in cfb_ctx_append / cfb_triple_device.  */
+int cfb_ctx_create(int device, int kind, int n_num, int n_cat, int n_groups, cfb_ctx **out);
+
+/* Replaces StateFunction::Destroy (sum_state.h:48-52).  NULL is accepted. */
+int cfb_ctx_destroy(cfb_ctx *ctx);
+
+/* Optional: declare the value range [lo[k], hi[k]] of categorical column k
+ * (e.g. from DuckDB column statistics) so the dense key->slot tables can be laid
+ * out without a min/max pre-pass.  Keys outside a declared range are an error
+ * (CFB_ERR_DOMAIN) reported by the next synchronising call.                    */
+int cfb_ctx_set_cat_domain(cfb_ctx *ctx, const int32_t *lo, const int32_t *hi);
+
+/* Replaces the per-chunk body of Triple::SumNoLift (sum_no_lift.cpp:83-214) and
+ * Triple::sum_to_nb_agg (sum_to_nb_agg.cpp:61-145) for HOST (DuckDB) vectors.
+ *   num_cols[i] / cat_cols[k] : base pointers of the unified-format column data
+ *   num_sel[i]  / cat_sel[k]  : that column's selection vector (NULL = identity);
+ *                               row r of the chunk reads data[sel ? sel[r] : r]
+ *                               (UnifiedVectorFormat, sum_no_lift.cpp:120)
+ *   group_slot                : per-row state slot in [0, n_groups) or NULL (slot 0)
+ *                               -- the states[sdata.sel->get_index(j)] indirection
+ *   count                     : rows in this chunk (any size; DuckDB sends <= 2048)
+ * Rows are gathered into pinned columnar staging; a full staging tile is shipped
+ * with cudaMemcpyAsync and reduced on the device while the next tile fills.
+ * Validity masks are not consulted (the reference never reads them).           */
+int cfb_ctx_append(cfb_ctx *ctx, const float *const *num_cols, const uint32_t *const *num_sel,
+                   const int32_t *const *cat_cols, const uint32_t *const *cat_sel,
+                   const uint32_t *group_slot, size_t count);
+
+/* Same reduction for DEVICE-resident columnar (SoA) input: the device-resident
+ * measurement path and the multi-GPU range partition.  Column pointers are
+ * device pointers (16-byte aligned); d_group_slot is a device int32 array of
+ * per-row slots or NULL.  `stream` is a cudaStream_t (NULL = the context's own
+ * stream).  Asynchronous: results are visible after cfb_ctx_sync/finalize.     */
+int cfb_triple_device(cfb_ctx *ctx, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
+                      const int32_t *d_group_slot, size_t n_rows, void *stream);
+
+/* Drain the context's streams; surfaces asynchronous kernel errors. */
+int cfb_ctx_sync(cfb_ctx *ctx);
+
+/* Replaces Triple::SumStateCombine (sum_state.cpp:10-114): dst += src, group by
+ * group.  Shapes must match (an empty dst adopts src's categorical domains).
+ * src stays valid and destroyable.  Works across devices (peer or staged copy). */
+int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src);
+
+/* ------------------------------------------------------------------- result */
+
+/* Flat canonical result of ONE state (group).  Mirrors the STRUCT written by
+ * Triple::SumStateFinalize (sum_state.cpp:116-464):
+ *   N            <- state->count                      (:132-135)
+ *   lin[i]       <- lin_agg                            (:162-171)
+ *   quad[p]      <- quadratic_agg, p = packed upper-triangle index
+ *                   i*n - i*(i+1)/2 + j (i<=j) for CFB_TRIPLE, p = i for CFB_NB (:177-199)
+ *   cat_*        <- per categorical column k, keys ascending (std::map order):
+ *                   cat_keys / cat_counts are the concatenation over k of the
+ *                   lin_cat lists; cat_offsets[k]..cat_offsets[k+1] is column k (:372-395)
+ *   numcat_sums  <- quad_num_cat: entry [i * total_keys + t] is SUM x_i over rows whose
+ *                   column-k key is cat_keys[t]  (sub-list index num*m+cat, :383-404)
+ *   pair_*       <- quad_cat: m(m+1)/2 lists in (k<=l) row-major order, diagonal
+ *                   included, entries ascending by (key1,key2)        (:440-461)
+ * Counts are exact integers; sums are fp64 (the glue narrows both to FLOAT, the
+ * STRUCT's declared type).  All arrays are owned by the result; free with
+ * cfb_result_free.                                                            */
+typedef struct cfb_result {
+  int32_t kind, n_num, n_cat;
+  int64_t N;
+  int64_t n_quad;        /* n(n+1)/2 (triple) or n (nb)                         */
+  double *lin;           /* [n_num]                                             */
+  double *quad;          /* [n_quad]                                            */
+  int64_t total_keys;    /* sum over k of distinct keys                         */
+  int64_t *cat_offsets;  /* [n_cat + 1]                                         */
+  int32_t *cat_keys;     /* [total_keys]                                        */
+  int64_t *cat_counts;   /* [total_keys]                                        */
+  double *numcat_sums;   /* [n_num * total_keys]   (NULL for CFB_NB)            */
+  int64_t n_pair_lists;  /* n_cat(n_cat+1)/2       (0 for CFB_NB)               */
+  int64_t *pair_offsets; /* [n_pair_lists + 1]                                  */
+  int32_t *pair_key1;    /* [pair_offsets[n_pair_lists]]                        */
+  int32_t *pair_key2;
+  int64_t *pair_counts;
+} cfb_result;
+
+/* Replaces Triple::SumStateFinalize for one group slot: synchronises, reads the
+ * device partials back and emits the canonical result.                        */
+int cfb_ctx_finalize(cfb_ctx *ctx, int group, cfb_result *out);
+void cfb_result_free(cfb_result *res);
+
+/* ------------------------------------------------- multi-GPU partial exchange */
+
+/* Dense partial layout for the NCCL reduce of SURVEY 8(e): the caller
+ * (one process per GPU) all-reduces / reduces two device buffers with SUM:
+ *   f64 part: [group][lin | quad | numcat dense]      (cfb_ctx_partial_sizes)
+ *   u64 part: [group][N | cat counts dense | pair counts dense]
+ * export copies the context's device state into caller-provided device buffers,
+ * import REPLACES the context's state with the buffers' contents.  Categorical
+ * domains must have been agreed with cfb_ctx_set_cat_domain on every rank.    */
+int cfb_ctx_partial_sizes(cfb_ctx *ctx, size_t *n_f64, size_t *n_u64);
+int cfb_ctx_export_partial(cfb_ctx *ctx, void *d_f64, void *d_u64, void *stream);
+int cfb_ctx_import_partial(cfb_ctx *ctx, const void *d_f64, const void *d_u64, void *stream);
+
+/* Observed [min,max] of each categorical column over device-resident input
+ * (device pre-pass; used to agree domains across ranks before the scan).      */
+int cfb_cat_minmax_device(int device, const int32_t *const *d_cat_cols, int n_cat, size_t n_rows,
+                          int32_t *lo_out, int32_t *hi_out, void *stream);
+
+/* ------------------------------------------------------ synthetic inputs (tests, bench) */
+
+/* Counter-based generators for device-resident synthetic columns: element i of the
+ * stream is a pure function of (seed, first + i), so the host can regenerate any slice
+ * bit-for-bit (duckdb_imputation_b200/synth.py) to feed the CPU oracle.
+ *   uniform: float in [0,1) with 24 random bits;  int32: lo + (hash % range).        */
+int cfb_gen_uniform_f32(int device, float *d_out, size_t n, uint64_t seed, uint64_t first, void *stream);
+int cfb_gen_int32(int device, int32_t *d_out, size_t n, uint64_t seed, uint64_t first, int32_t lo,
+                  uint32_t range, void *stream);
+
+/* ------------------------------------------------------------- introspection */
+
+/* Number of CUDA kernels this library has launched since load (bench.py's
+ * gpu_launches claim), and time of the most recent cfb_triple_device scan kernel
+ * in milliseconds measured with CUDA events on its launching stream (bench only:
+ * enabled by cfb_set_timing(1)).                                               */
+uint64_t cfb_kernel_launches(void);
+int cfb_set_timing(int enabled);
+double cfb_last_scan_ms(cfb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COFACTOR_B200_H */

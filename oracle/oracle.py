@@ -1,0 +1,105 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from duckdb_imputation_b200._native import Result, ptr_array
+from duckdb_imputation_b200.struct_result import arrays_to_struct, result_arrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+TRIPLE, NB = 0, 1
+EXACT, FAITHFUL = 0, 1
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        l = C.CDLL(LIB_PATH)
+        P = C.c_void_p
+        l.orc_aggregate.restype = C.c_int
+        l.orc_aggregate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
+                                    C.c_size_t, C.c_int, C.POINTER(Result)]
+        l.orc_sum_of_lifted.restype = C.c_int
+        l.orc_sum_of_lifted.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int,
+                                        C.c_size_t, C.POINTER(Result)]
+        l.orc_result_add.restype = C.c_int
+        l.orc_result_add.argtypes = [C.POINTER(Result)] * 3
+        l.orc_result_free.restype = None
+        l.orc_result_free.argtypes = [C.POINTER(Result)]
+        l.orc_last_seconds.restype = C.c_double
+        _lib = l
+    return _lib
+
+
+def _cols(cols, dt):
+    keep = [np.ascontiguousarray(c, dtype=dt) for c in cols]
+    return keep, ptr_array([k.ctypes.data for k in keep])
+
+
+def aggregate_arrays(kind, num_cols, cat_cols, group=None, n_groups=1, sel=None, mode=EXACT, threads=1):
+    """-> list (one per group) of numpy-form results (see struct_result.result_arrays)."""
+    kn, pn = _cols(num_cols, np.float32)
+    kc, pc = _cols(cat_cols, np.int32)
+    g = None if group is None else np.ascontiguousarray(group, np.int32)
+    s = None if sel is None else np.ascontiguousarray(sel, np.uint32)
+    rows = len(s) if s is not None else (len(kn[0]) if kn else (len(kc[0]) if kc else 0))
+    out = (Result * n_groups)()
+    rc = lib().orc_aggregate(kind, mode, len(kn), len(kc), pn, pc, None if g is None else g.ctypes.data, n_groups,
+                             None if s is None else s.ctypes.data, rows, threads, out)
+    if rc:
+        raise ValueError("orc_aggregate: bad arguments")
+    try:
+        return [result_arrays(out[i]) for i in range(n_groups)]
+    finally:
+        for i in range(n_groups):
+            lib().orc_result_free(C.byref(out[i]))
+
+
+def aggregate(kind, num_cols, cat_cols, group_by=None, where=None, mode=EXACT, threads=1, narrow=True):
+    """SQL-shaped front end: returns a STRUCT dict, or a list of them in ascending group-key order."""
+    sel = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
+    if group_by is None:
+        return arrays_to_struct(aggregate_arrays(kind, num_cols, cat_cols, sel=sel, mode=mode, threads=threads)[0], narrow)
+    gb = np.asarray(group_by)
+    used = gb[sel] if sel is not None else gb
+    labels = np.unique(used)
+    slots = np.searchsorted(labels, gb).clip(0, max(0, len(labels) - 1)).astype(np.int32)
+    res = aggregate_arrays(kind, num_cols, cat_cols, group=slots, n_groups=max(1, len(labels)), sel=sel, mode=mode,
+                           threads=threads)
+    return [arrays_to_struct(r, narrow) for r in res]
+
+
+def sum_of_lifted(kind, num_cols, cat_cols, group=None, n_groups=1):
+    kn, pn = _cols(num_cols, np.float32)
+    kc, pc = _cols(cat_cols, np.int32)
+    g = None if group is None else np.ascontiguousarray(group, np.int32)
+    rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
+    out = (Result * n_groups)()
+    rc = lib().orc_sum_of_lifted(kind, len(kn), len(kc), pn, pc, None if g is None else g.ctypes.data, n_groups, rows, out)
+    if rc:
+        raise ValueError("orc_sum_of_lifted: bad arguments")
+    try:
+        return [arrays_to_struct(result_arrays(out[i])) for i in range(n_groups)]
+    finally:
+        for i in range(n_groups):
+            lib().orc_result_free(C.byref(out[i]))
+
+
+def last_seconds() -> float:
+    return float(lib().orc_last_seconds())

@@ -1,0 +1,46 @@
+"""Just enough SQL to replay the reference's test statements against a backend.
+
+    SELECT <fn>(<cols>) from test [where gb = K] [GROUP BY gb [HAVING gb = K]]
+
+`backend(kind, num_cols, cat_cols, group_by=None, where=None)` returns one STRUCT dict or a
+list of them in ascending group order -- the signature shared by oracle.aggregate and
+duckdb_imputation_b200.aggregates.
+"""
+import re
+
+import numpy as np
+
+
+def table(fixture):
+    cols = {}
+    rows = fixture["rows"]
+    for i, (name, ty) in enumerate(zip(fixture["columns"], fixture["types"])):
+        dt = np.float32 if ty == "FLOAT" else np.int32
+        cols[name] = np.array([r[i] for r in rows], dtype=dt)
+    return cols, dict(zip(fixture["columns"], fixture["types"]))
+
+
+def parse(sql):
+    m = re.match(r"SELECT (\w+)\((.*?)\) from test\s*(.*)$", sql.strip().rstrip(";"), re.I)
+    fn, args, tail = m.group(1), [a.strip() for a in m.group(2).split(",")], m.group(3)
+    where = re.search(r"where gb = (\d+)", tail, re.I)
+    having = re.search(r"HAVING gb = (\d+)", tail, re.I)
+    return {"fn": fn, "args": args, "group": bool(re.search(r"GROUP BY gb", tail, re.I)),
+            "where": int(where.group(1)) if where else None, "having": int(having.group(1)) if having else None}
+
+
+def run_sum(sql, fixture, backend):
+    """Execute a sum_to_triple_x_y / sum_to_nb_agg_x_y statement -> list of result STRUCTs."""
+    q = parse(sql)
+    cols, types = table(fixture)
+    kind = 0 if q["fn"].startswith("sum_to_triple") else 1
+    num = [cols[a] for a in q["args"] if types[a] == "FLOAT"]
+    cat = [cols[a] for a in q["args"] if types[a] != "FLOAT"]
+    where = None if q["where"] is None else (cols["gb"] == q["where"])
+    if not q["group"]:
+        return [backend(kind, num, cat, where=where)]
+    res = backend(kind, num, cat, group_by=cols["gb"], where=where)
+    labels = np.unique(cols["gb"] if where is None else cols["gb"][where])
+    if q["having"] is not None:
+        return [r for r, l in zip(res, labels) if l == q["having"]]
+    return res
