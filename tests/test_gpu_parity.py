@@ -1,0 +1,226 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: N / keys / counts bit-exact; sums <= 1e-5 relative to the fp64 oracle (tests/parity.py);
+exact equality with the reference's golden STRUCTs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from duckdb_imputation_b200 import CFB_NB, CFB_TRIPLE, CofactorContext, CofactorError, sum_to_nb_agg, sum_to_triple
+from duckdb_imputation_b200 import _native as nat
+from duckdb_imputation_b200 import synth
+from oracle import oracle
+from tests import sqlmini
+from tests.parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _backend(kind, num, cat, group_by=None, where=None):
+    f = sum_to_triple if kind == CFB_TRIPLE else sum_to_nb_agg
+    return f(num, cat, group_by=group_by, where=where)
+
+
+def test_reference_goldens_through_the_c_abi(goldens):
+    cases = [c for c in goldens["cases"] if c["file"] in ("test_sum.py", "test_nb_sum.py")]
+    assert len(cases) == 8
+    for c in cases:
+        got = sqlmini.run_sum(c["sql"], goldens["fixtures"][c["file"]], _backend)
+        assert got[c["index"]] == c["expected"], (c["file"], c["test"], c["index"])
+
+
+def _table(rng, rows, n, m, dom=100, lo=0, dist="uniform"):
+    if dist == "normal":
+        num = [rng.standard_normal(rows).astype(np.float32) for _ in range(n)]
+    else:
+        num = [rng.random(rows).astype(np.float32) for _ in range(n)]
+    cat = [rng.integers(lo, lo + dom, rows).astype(np.int32) for _ in range(m)]
+    return num, cat
+
+
+def _gpu_host(kind, num, cat, group=None, n_groups=1, chunk=2048, sel=None):
+    """Feed host columns through cfb_ctx_append the way the DuckDB glue does."""
+    rows = len(sel) if sel is not None else (len(num[0]) if num else len(cat[0]))
+    with CofactorContext(kind, len(num), len(cat), n_groups) as ctx:
+        for lo in range(0, rows, chunk):
+            hi = min(rows, lo + chunk)
+            g = None if group is None else group[lo:hi]
+            if sel is None:
+                ctx.append([c[lo:hi] for c in num], [c[lo:hi] for c in cat], group=g, count=hi - lo)
+            else:
+                s = sel[lo:hi]
+                ctx.append(num, cat, group=g, num_sel=[s] * len(num), cat_sel=[s] * len(cat), count=hi - lo)
+        return [ctx.finalize_arrays(g) for g in range(n_groups)]
+
+
+SHAPES = [
+    (CFB_TRIPLE, 5, 0), (CFB_TRIPLE, 20, 0), (CFB_TRIPLE, 10, 10), (CFB_TRIPLE, 3, 3), (CFB_TRIPLE, 0, 2),
+    (CFB_TRIPLE, 1, 0), (CFB_TRIPLE, 11, 1), (CFB_TRIPLE, 17, 0), (CFB_TRIPLE, 21, 2), (CFB_TRIPLE, 32, 0),
+    (CFB_NB, 12, 4), (CFB_NB, 4, 0), (CFB_NB, 32, 1), (CFB_NB, 0, 3),
+]
+
+
+@pytest.mark.parametrize("kind,n,m", SHAPES)
+def test_host_feed_matches_oracle(kind, n, m):
+    rng = np.random.default_rng(100 + 7 * n + m)
+    rows = 150_001
+    num, cat = _table(rng, rows, n, m, dom=100 if m <= 4 else 20, lo=-5)
+    got = _gpu_host(kind, num, cat, chunk=2048)[0]
+    ref = oracle.aggregate_arrays(kind, num, cat)[0]
+    assert_parity(got, ref, what=f"kind={kind} n={n} m={m}")
+
+
+@pytest.mark.parametrize("kind,n,m,G", [(CFB_NB, 12, 4, 10), (CFB_TRIPLE, 12, 0, 10), (CFB_TRIPLE, 4, 2, 3)])
+def test_group_by_matches_oracle(kind, n, m, G):
+    rng = np.random.default_rng(5)
+    rows = 60_000
+    num, cat = _table(rng, rows, n, m, dom=30)
+    group = rng.integers(0, G, rows).astype(np.uint32)
+    got = _gpu_host(kind, num, cat, group=group, n_groups=G)
+    ref = oracle.aggregate_arrays(kind, num, cat, group=group.astype(np.int32), n_groups=G)
+    for g in range(G):
+        assert_parity(got[g], ref[g], what=f"group {g}")
+
+
+def test_filtered_scan_through_selection_vectors():
+    rng = np.random.default_rng(6)
+    rows = 40_000
+    num, cat = _table(rng, rows, 6, 2, dom=12)
+    sel = np.nonzero(rng.random(rows) < 0.8)[0].astype(np.uint32)
+    got = _gpu_host(CFB_TRIPLE, num, cat, sel=sel)[0]
+    ref = oracle.aggregate_arrays(CFB_TRIPLE, num, cat, sel=sel)[0]
+    assert_parity(got, ref)
+
+
+def test_cancelling_sums_normal_data():
+    rng = np.random.default_rng(11)
+    rows = 300_000
+    num, cat = _table(rng, rows, 8, 0, dist="normal")
+    got = _gpu_host(CFB_TRIPLE, num, cat, chunk=65536)[0]
+    ref = oracle.aggregate_arrays(CFB_TRIPLE, num, cat)[0]
+    # off-diagonal sums of N(0,1) products cancel to ~sqrt(rows): floor on sum of |terms| ~ rows
+    assert_parity(got, ref, abs_scale=float(rows))
+
+
+def _device_cols(torch, rows, n, m, seed, dom=100, lo=0):
+    l = nat.lib()
+    dn = [torch.empty(rows, dtype=torch.float32, device="cuda") for _ in range(n)]
+    dc = [torch.empty(rows, dtype=torch.int32, device="cuda") for _ in range(m)]
+    for k, t in enumerate(dn):
+        nat.check(l.cfb_gen_uniform_f32(0, t.data_ptr(), rows, synth.column_seed(seed, k), 0, None))
+    for k, t in enumerate(dc):
+        nat.check(l.cfb_gen_int32(0, t.data_ptr(), rows, synth.column_seed(seed, 100 + k), 0, lo, dom, None))
+    torch.cuda.synchronize()
+    hn = [synth.uniform_f32(rows, synth.column_seed(seed, k)) for k in range(n)]
+    hc = [synth.int32(rows, synth.column_seed(seed, 100 + k), lo=lo, rng=dom) for k in range(m)]
+    return dn, dc, hn, hc
+
+
+@pytest.mark.parametrize("kind,n,m,rows", [
+    (CFB_TRIPLE, 5, 0, 1_000_000), (CFB_TRIPLE, 20, 0, 2_000_003), (CFB_TRIPLE, 10, 10, 500_001),
+    (CFB_NB, 12, 4, 700_002), (CFB_TRIPLE, 20, 0, 3), (CFB_TRIPLE, 7, 0, 513), (CFB_TRIPLE, 32, 0, 300_000),
+    (CFB_TRIPLE, 24, 0, 100_001), (CFB_TRIPLE, 13, 0, 65_536),
+])
+def test_device_resident_scan_matches_oracle(kind, n, m, rows):
+    torch = pytest.importorskip("torch")
+    dn, dc, hn, hc = _device_cols(torch, rows, n, m, seed=42)
+    # the device generator and its host twin must agree bit for bit
+    assert np.array_equal(dn[0].cpu().numpy(), hn[0])
+    if m:
+        assert np.array_equal(dc[0].cpu().numpy(), hc[0])
+    with CofactorContext(kind, n, m) as ctx:
+        ctx.scan_device(dn, dc, rows)
+        got = ctx.finalize_arrays()
+    ref = oracle.aggregate_arrays(kind, hn, hc)[0]
+    assert_parity(got, ref, what=f"device n={n} m={m} rows={rows}")
+
+
+def test_device_scan_is_deterministic_and_accumulates():
+    torch = pytest.importorskip("torch")
+    rows = 1_000_000
+    dn, dc, hn, hc = _device_cols(torch, rows, 20, 0, seed=3)
+    outs = []
+    for _ in range(2):
+        with CofactorContext(CFB_TRIPLE, 20, 0) as ctx:
+            ctx.scan_device(dn, dc, rows)
+            outs.append(ctx.finalize_arrays())
+    assert np.array_equal(outs[0]["quad"], outs[1]["quad"]) and np.array_equal(outs[0]["lin"], outs[1]["lin"])
+    with CofactorContext(CFB_TRIPLE, 20, 0) as ctx:  # two scans into one state == 2x
+        ctx.scan_device(dn, dc, rows)
+        ctx.scan_device(dn, dc, rows)
+        twice = ctx.finalize_arrays()
+    assert twice["N"] == 2 * rows
+    np.testing.assert_allclose(twice["quad"], 2 * outs[0]["quad"], rtol=1e-12)
+
+
+def test_device_group_by():
+    torch = pytest.importorskip("torch")
+    rows, G = 400_000, 10
+    dn, dc, hn, hc = _device_cols(torch, rows, 12, 4, seed=9)
+    dg = torch.empty(rows, dtype=torch.int32, device="cuda")
+    nat.check(nat.lib().cfb_gen_int32(0, dg.data_ptr(), rows, 777, 0, 0, G, None))
+    torch.cuda.synchronize()
+    hg = synth.int32(rows, 777, lo=0, rng=G)
+    for kind in (CFB_NB, CFB_TRIPLE):
+        with CofactorContext(kind, 12, 4, n_groups=G) as ctx:
+            ctx.scan_device(dn, dc, rows, d_group=dg)
+            got = [ctx.finalize_arrays(g) for g in range(G)]
+        ref = oracle.aggregate_arrays(kind, hn, hc, group=hg, n_groups=G)
+        for g in range(G):
+            assert_parity(got[g], ref[g], what=f"kind {kind} group {g}")
+
+
+def test_combine_equals_single_scan():
+    rng = np.random.default_rng(21)
+    rows = 50_000
+    num, cat = _table(rng, rows, 6, 3, dom=15, lo=-4)
+    h = 20_000
+    with CofactorContext(CFB_TRIPLE, 6, 3) as a, CofactorContext(CFB_TRIPLE, 6, 3) as b, \
+            CofactorContext(CFB_TRIPLE, 6, 3) as empty:
+        a.append([c[:h] for c in num], [c[:h] % 7 for c in cat])  # a sees a narrower key range than b
+        b.append([c[h:] for c in num], [c[h:] for c in cat])
+        a.combine(b)
+        a.combine(empty)
+        got = a.finalize_arrays()
+        b_alone = b.finalize_arrays()  # src stays valid (sum_state.h:48-52 destroys it later)
+    cat2 = [np.concatenate([c[:h] % 7, c[h:]]) for c in cat]
+    assert_parity(got, oracle.aggregate_arrays(CFB_TRIPLE, num, cat2)[0])
+    assert_parity(b_alone, oracle.aggregate_arrays(CFB_TRIPLE, [c[h:] for c in num], [c[h:] for c in cat])[0])
+
+
+def test_domain_grows_across_appends_and_negative_keys():
+    num = [np.array([1, 2, 3, 4], np.float32)]
+    with CofactorContext(CFB_TRIPLE, 1, 1) as ctx:
+        ctx.append([num[0][:2]], [np.array([5, 6], np.int32)])
+        ctx.sync()
+        ctx.append([num[0][2:]], [np.array([-1000, 70000], np.int32)])
+        got = ctx.finalize()
+    assert got["lin_cat"] == [[{"key": -1000, "value": 1.0}, {"key": 5, "value": 1.0}, {"key": 6, "value": 1.0},
+                               {"key": 70000, "value": 1.0}]]
+    assert [e["value"] for e in got["quad_num_cat"][0]] == [3.0, 1.0, 2.0, 4.0]
+
+
+def test_declared_domain_violation_is_an_error():
+    with CofactorContext(CFB_TRIPLE, 0, 1) as ctx:
+        ctx.set_cat_domain([0], [9])
+        ctx.append([], [np.array([1, 2, 10], np.int32)])
+        with pytest.raises(CofactorError) as e:
+            ctx.sync()
+        assert e.value.code == nat.CFB_ERR_DOMAIN
+
+
+def test_empty_input_and_tiny_inputs():
+    with CofactorContext(CFB_TRIPLE, 2, 1) as ctx:
+        got = ctx.finalize()
+    assert got == {"N": 0, "lin_agg": [0.0, 0.0], "quad_agg": [0.0, 0.0, 0.0], "lin_cat": [[]],
+                   "quad_num_cat": [[], []], "quad_cat": [[]]}
+    one = sum_to_triple([np.array([3.0], np.float32)], [np.array([4], np.int32)])
+    assert one == {"N": 1, "lin_agg": [3.0], "quad_agg": [9.0], "lin_cat": [[{"key": 4, "value": 1.0}]],
+                   "quad_num_cat": [[{"key": 4, "value": 3.0}]], "quad_cat": [[{"key1": 4, "key2": 4, "value": 1.0}]]}
+
+
+def test_kernels_actually_launch():
+    before = nat.lib().cfb_kernel_launches()
+    sum_to_triple([np.ones(10, np.float32)] * 3, [])
+    assert nat.lib().cfb_kernel_launches() > before
