@@ -25,7 +25,7 @@ cudaError_t gram_launch(const GramLaunchParams &p) {
   static std::once_flag once[64];
   cudaError_t attr_err = cudaSuccess;
   std::call_once(once[p.device & 63], [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_optin);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_optin - 1024);
   });
   if (attr_err != cudaSuccess) return attr_err;
   GramArgs a{};
