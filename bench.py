@@ -285,7 +285,7 @@ def main():
                 c.scan_device([t[h:] for t in cols], [], rows - h, stream=stream.cuda_stream)
                 halves = c.finalize_arrays()
             check["halves_vs_whole_rel"] = float(np.max(np.abs(halves["quad"] - last["quad"]) / np.abs(last["quad"])))
-            assert check["halves_vs_whole_rel"] < 1e-9 and halves["N"] == last["N"]
+            assert check["halves_vs_whole_rel"] < 1e-6 and halves["N"] == last["N"]
             # E[x]=1/2, E[x^2]=1/3, E[x y]=1/4 for U[0,1): a distribution-level sanity check at full size
             check["mean_lin"] = float(np.mean(last["lin"]) / last["N"])
     for c in ctxs:

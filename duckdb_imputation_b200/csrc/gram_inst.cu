@@ -32,8 +32,8 @@ cudaError_t gram_launch(const GramLaunchParams &p) {
   for (int k = 0; k < N; k++) a.cols.p[k] = p.cols[k];
   a.n_rows = p.rows;
   a.stages = stages;
-  // default: an fp32 accumulator half sees at most ~96 rows between folds into fp64
-  a.flush_tiles = p.flush_tiles > 0 ? p.flush_tiles : std::max(1, 96 * 64 * S::kGroups / TR);
+  // default: an fp32 accumulator half sees at most ~256 rows between folds into fp64
+  a.flush_tiles = p.flush_tiles > 0 ? p.flush_tiles : std::max(1, 256 * 64 * S::kGroups / TR);
   a.partials = p.partials;
   a.state = p.state;
   a.ticket = p.ticket;

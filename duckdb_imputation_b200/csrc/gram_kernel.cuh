@@ -43,6 +43,10 @@ __device__ __forceinline__ void fadd2(unsigned long long &d, unsigned long long 
 __device__ __forceinline__ unsigned long long lds64(const float *p) {
   return *reinterpret_cast<const unsigned long long *>(p);
 }
+struct __align__(16) U64x2 {
+  unsigned long long lo, hi;  // rows (r, r+1) and (r+2, r+3) of one column
+};
+__device__ __forceinline__ U64x2 lds128(const float *p) { return *reinterpret_cast<const U64x2 *>(p); }
 __device__ __forceinline__ float hsum2(unsigned long long v) {
   return __uint_as_float((unsigned)(v & 0xffffffffull)) + __uint_as_float((unsigned)(v >> 32));
 }
@@ -139,7 +143,7 @@ struct GramArgs {
 // rows per ring stage: narrow tables get longer tiles so a stage stays >= 8 KB
 template <int N>
 struct GramTile {
-  static constexpr int kRows = N <= 4 ? 2048 : (N <= 8 ? 1024 : 512);
+  static constexpr int kRows = N <= 4 ? 2048 : (N <= 10 ? 1024 : 512);  // multiple of 128 * kGroups
 };
 
 template <int N, bool DIAG>
@@ -205,40 +209,47 @@ __device__ __forceinline__ void gram_consume(const GramArgs &a, const float *rin
     const float *st = ring + (size_t)stage * (N * TR);
     ptx::mbar_wait(&full[stage], phase);
 #pragma unroll 1
-    for (int it = group; it < TR / 64; it += S::kGroups) {
-      const int row = it * 64 + lane * 2;
-      if (row >= valid) break;  // valid is a multiple of 4: a lane's two rows are both in or out
-      unsigned long long xi[RL::kI];
-      unsigned long long xj[RL::kSame ? 1 : RL::kJ];
+    for (int it = group; it < TR / 128; it += S::kGroups) {
+      const int row = it * 128 + lane * 4;
+      if (row >= valid) break;  // valid is a multiple of 4: a lane's four rows are all in or all out
+      U64x2 xi[RL::kI];
+      U64x2 xj[RL::kSame ? 1 : RL::kJ];
 #pragma unroll
-      for (int k = 0; k < RL::kI; k++) xi[k] = lds64(st + (RL::i0 + k) * TR + row);
+      for (int k = 0; k < RL::kI; k++) xi[k] = lds128(st + (RL::i0 + k) * TR + row);
       if constexpr (!RL::kSame) {
 #pragma unroll
-        for (int k = 0; k < RL::kJ; k++) xj[k] = lds64(st + (RL::j0 + k) * TR + row);
+        for (int k = 0; k < RL::kJ; k++) xj[k] = lds128(st + (RL::j0 + k) * TR + row);
       }
       static_for<0, RL::kI>([&](auto ai_) {
         static_for<0, RL::kJ>([&](auto bj_) {
           constexpr int ai = decltype(ai_)::value, bj = decltype(bj_)::value;
           if constexpr (RL::owns(ai, bj)) {
             constexpr int s = RL::slot(ai, bj);
-            if constexpr (RL::kSame)
-              ffma2(acc[s], xi[ai], xi[bj]);
-            else
-              ffma2(acc[s], xi[ai], xj[bj]);
+            if constexpr (RL::kSame) {
+              ffma2(acc[s], xi[ai].lo, xi[bj].lo);
+              ffma2(acc[s], xi[ai].hi, xi[bj].hi);
+            } else {
+              ffma2(acc[s], xi[ai].lo, xj[bj].lo);
+              ffma2(acc[s], xi[ai].hi, xj[bj].hi);
+            }
           }
         });
       });
       // column sums (lin_agg) this role owns: ranges are subsets of its loaded columns
       static_for<0, RL::kLinA>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
-        fadd2(acc[RL::kPairs + k], xi[RL::la0 - RL::i0 + k]);
+        fadd2(acc[RL::kPairs + k], xi[RL::la0 - RL::i0 + k].lo);
+        fadd2(acc[RL::kPairs + k], xi[RL::la0 - RL::i0 + k].hi);
       });
       static_for<0, RL::kLinB>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
-        if constexpr (RL::kSame)
-          fadd2(acc[RL::kPairs + RL::kLinA + k], xi[RL::lb0 - RL::i0 + k]);
-        else
-          fadd2(acc[RL::kPairs + RL::kLinA + k], xj[RL::lb0 - RL::j0 + k]);
+        if constexpr (RL::kSame) {
+          fadd2(acc[RL::kPairs + RL::kLinA + k], xi[RL::lb0 - RL::i0 + k].lo);
+          fadd2(acc[RL::kPairs + RL::kLinA + k], xi[RL::lb0 - RL::i0 + k].hi);
+        } else {
+          fadd2(acc[RL::kPairs + RL::kLinA + k], xj[RL::lb0 - RL::j0 + k].lo);
+          fadd2(acc[RL::kPairs + RL::kLinA + k], xj[RL::lb0 - RL::j0 + k].hi);
+        }
       });
     }
     __syncwarp();
@@ -282,23 +293,24 @@ __global__ void __launch_bounds__(GramShape<N, DIAG>::kThreads, 1)
 
   if (warp == S::kConsumerWarps) {
     // ------------------------------------------------------------ producer warp
-    if (lane == 0) {
-      const uint64_t pol = ptx::policy_evict_first();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long row0 = tile * TR;
-        const uint32_t valid = (uint32_t)((rows4 - row0) < (unsigned long long)TR ? (rows4 - row0) : (unsigned long long)TR);
+    // Lane 0 waits for the stage to drain and arms its "full" barrier; then lane c issues the
+    // bulk copy of column c, so the N copies of a tile are issued in parallel (one thread can
+    // only issue a bulk copy every ~100 cycles: profiles/r01_stream_ceiling.txt).
+    int stage = 0;
+    uint32_t phase = 0;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const unsigned long long row0 = tile * TR;
+      const uint32_t valid = (uint32_t)((rows4 - row0) < (unsigned long long)TR ? (rows4 - row0) : (unsigned long long)TR);
+      if (lane == 0) {
         ptx::mbar_wait(&empty[stage], phase ^ 1u);
         ptx::mbar_arrive_expect_tx(&full[stage], valid * (uint32_t)sizeof(float) * N);
-        float *dst = ring + (size_t)stage * (N * TR);
-#pragma unroll 1
-        for (int c = 0; c < N; c++)
-          ptx::bulk_g2s(dst + c * TR, a.cols.p[c] + row0, valid * (uint32_t)sizeof(float), &full[stage], pol);
-        if (++stage == a.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      __syncwarp();
+      float *dst = ring + (size_t)stage * (N * TR);
+      if (lane < N) ptx::bulk_g2s_plain(dst + lane * TR, a.cols.p[lane] + row0, valid * (uint32_t)sizeof(float), &full[stage]);
+      if (++stage == a.stages) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else {

@@ -72,6 +72,15 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
       : "memory");
 }
 
+// Same without a cache hint (evict_first measured slightly slower for 2 KB chunks).
+__device__ __forceinline__ void bulk_g2s_plain(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
