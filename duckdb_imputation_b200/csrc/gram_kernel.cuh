@@ -63,7 +63,10 @@ struct GramShape {
   static constexpr int kRoles = DIAG ? 1 : (N <= 10 ? 1 : (N <= 20 ? 4 : 10));
   static constexpr int kGroups = kRoles == 1 ? 8 : (kRoles == 4 ? 2 : 1);
   static constexpr int kConsumerWarps = kRoles * kGroups;
-  static constexpr int kThreads = (kConsumerWarps + 1) * 32;
+  // 8 consumer warps = 2 warpgroups; the producer warp sits in a third warpgroup (3 idle warps)
+  // so that setmaxnreg can move its registers to the consumers.
+  static constexpr bool kRegSplit = kConsumerWarps == 8;
+  static constexpr int kThreads = kRegSplit ? 384 : (kConsumerWarps + 1) * 32;
   static constexpr int kOut = DIAG ? 2 * N : N + N * (N + 1) / 2;  // [lin | quad]
 
   static constexpr RoleGeom role(int r) {
@@ -291,7 +294,16 @@ __global__ void __launch_bounds__(GramShape<N, DIAG>::kThreads, 1)
   const unsigned long long rows4 = a.n_rows & ~3ull;
   const unsigned long long n_tiles = (rows4 + TR - 1) / TR;
 
-  if (warp == S::kConsumerWarps) {
+  // Register split (kRegSplit): 384 threads start with 168 registers each; the producer
+  // warpgroup shrinks to 24 and the two consumer warpgroups grow to 240
+  // (24*128 + 240*256 = 64512 <= 65536).  Each setmaxnreg sits inside its own branch so that
+  // the register budget of the code that follows is unambiguous to ptxas.
+  if (warp > S::kConsumerWarps) {
+    // idle warps of the producer warpgroup
+    if constexpr (S::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    return;
+  } else if (warp == S::kConsumerWarps) {
+    if constexpr (S::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     // ------------------------------------------------------------ producer warp
     // Lane 0 waits for the stage to drain and arms its "full" barrier; then lane c issues the
     // bulk copy of column c, so the N copies of a tile are issued in parallel (one thread can
@@ -313,8 +325,10 @@ __global__ void __launch_bounds__(GramShape<N, DIAG>::kThreads, 1)
         phase ^= 1u;
       }
     }
+    return;
   } else {
     // ----------------------------------------------------------- consumer warps
+    if constexpr (S::kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int role = warp % S::kRoles, group = warp / S::kRoles;
     double *tot = totals + group * S::kOut;
     if constexpr (S::kRoles == 1) {
@@ -341,26 +355,28 @@ __global__ void __launch_bounds__(GramShape<N, DIAG>::kThreads, 1)
       }
     }
   }
-  __syncthreads();
+  // Only the consumer warps get here (the producer warpgroup has exited).
+  constexpr int kTail = S::kConsumerWarps * 32;
+  ptx::named_bar_sync(1, kTail);
 
   // ------------------------------------------------- CTA partial -> global, last CTA folds
   double *mine = a.partials + (size_t)blockIdx.x * S::kOut;
-  for (int t = threadIdx.x; t < S::kOut; t += blockDim.x) {
+  for (int t = threadIdx.x; t < S::kOut; t += kTail) {
     double s = 0.0;
 #pragma unroll
     for (int gq = 0; gq < S::kGroups; gq++) s += totals[gq * S::kOut + t];
     mine[t] = s;
   }
   __threadfence();
-  __syncthreads();
+  ptx::named_bar_sync(1, kTail);
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(a.ticket, 1u);
     s_is_last = (prev == gridDim.x - 1) ? 1u : 0u;
   }
-  __syncthreads();
+  ptx::named_bar_sync(1, kTail);
   if (s_is_last) {
     __threadfence();
-    for (int t = threadIdx.x; t < S::kOut; t += blockDim.x) {
+    for (int t = threadIdx.x; t < S::kOut; t += kTail) {
       double s = 0.0;
       for (unsigned int b = 0; b < gridDim.x; b++) s += a.partials[(size_t)b * S::kOut + t];
       // the <= 3 rows that are not a multiple of 4 never enter the ring
