@@ -1,0 +1,223 @@
+// replay_host.cpp -- see replay_host.h.
+#include "replay_host.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+
+#include <duckdb.hpp>
+
+// Provided by the extension linked into this library (ours or the reference's).
+namespace duckdb_ring {
+void Load(duckdb::DatabaseInstance &db);
+const char *Implementation();
+}  // namespace duckdb_ring
+
+namespace {
+
+thread_local std::string g_error;
+duckdb::DatabaseInstance &Catalog() {
+  static duckdb::DatabaseInstance db;
+  static std::once_flag once;
+  std::call_once(once, [] { duckdb_ring::Load(db); });
+  return db;
+}
+
+void RenderValue(duckdb::Vector &v, idx_t row, std::ostringstream &os) {
+  using namespace duckdb;
+  const auto &t = v.GetType();
+  switch (t.id()) {
+    case LogicalTypeId::INTEGER:
+      os << FlatVector::GetData<int32_t>(v)[row];
+      break;
+    case LogicalTypeId::FLOAT: {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%.9g", (double)FlatVector::GetData<float>(v)[row]);
+      os << buf;
+      break;
+    }
+    case LogicalTypeId::LIST: {
+      const list_entry_t e = ListVector::GetData(v)[row];
+      Vector &child = ListVector::GetEntry(v);
+      os << "[";
+      for (idx_t i = 0; i < e.length; i++) {
+        if (i) os << ", ";
+        RenderValue(child, e.offset + i, os);
+      }
+      os << "]";
+      break;
+    }
+    case LogicalTypeId::STRUCT: {
+      auto &kids = StructVector::GetEntries(v);
+      os << "{";
+      for (size_t i = 0; i < kids.size(); i++) {
+        if (i) os << ", ";
+        os << "\"" << t.children()[i].first << "\": ";
+        RenderValue(*kids[i], row, os);
+      }
+      os << "}";
+      break;
+    }
+    default:
+      throw duckdb::InternalException("replay: cannot render this type");
+  }
+}
+
+struct ThreadLocalStates {
+  std::unique_ptr<duckdb::data_t[]> mem;  // n_groups * state_size, like hash-table row storage
+  std::vector<char> live;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *replay_last_error(void) { return g_error.c_str(); }
+const char *replay_implementation(void) { return duckdb_ring::Implementation(); }
+void replay_free(char *p) { free(p); }
+
+char *replay_list_functions(void) {
+  std::string s;
+  for (auto &kv : Catalog().aggregates) s += kv.first + "\n";
+  return strdup(s.c_str());
+}
+
+int replay_aggregate(const char *function, int n_num, int n_cat, const float *const *num,
+                     const int32_t *const *cat, const int32_t *group, int n_groups, const uint32_t *sel,
+                     size_t n_sel, size_t rows, int threads, char **json_out, double *seconds) {
+  using namespace duckdb;
+  try {
+    if (!function || !json_out || n_groups < 1) throw InvalidInputException("bad arguments");
+    *json_out = nullptr;
+    auto it = Catalog().aggregates.find(function);
+    if (it == Catalog().aggregates.end())
+      throw InvalidInputException(std::string("Catalog Error: aggregate function ") + function + " does not exist");
+    AggregateFunction fun = it->second;  // bind mutates its copy (return_type)
+    const int n_cols = n_num + n_cat;
+    if ((size_t)n_cols != fun.arguments.size() && fun.varargs.id() == LogicalTypeId::INVALID)
+      throw InvalidInputException("argument count does not match the function signature");
+    ClientContext context;
+    vector<unique_ptr<Expression>> args;
+    unique_ptr<FunctionData> bind_data;
+    if (fun.bind) bind_data = fun.bind(context, fun, args);
+    AggregateInputData aggr(bind_data.get());
+    const idx_t ssz = fun.state_size();
+
+    const size_t n_chunks = (rows + STANDARD_VECTOR_SIZE - 1) / STANDARD_VECTOR_SIZE;
+    int T = std::max(1, threads);
+    if ((size_t)T > std::max<size_t>(1, n_chunks)) T = (int)std::max<size_t>(1, n_chunks);
+    std::vector<ThreadLocalStates> tls(T);
+    for (auto &t : tls) {
+      t.mem.reset(new data_t[std::max<size_t>(1, ssz * n_groups)]);
+      t.live.assign(n_groups, 0);
+    }
+    std::string worker_error;
+    std::mutex err_mu;
+
+    const auto t0 = std::chrono::steady_clock::now();
+    auto worker = [&](int t) {
+      try {
+        ThreadLocalStates &loc = tls[t];
+        const size_t c_lo = n_chunks * t / T, c_hi = n_chunks * (t + 1) / T;
+        std::vector<data_ptr_t> ptrs(STANDARD_VECTOR_SIZE);
+        std::vector<sel_t> rel(STANDARD_VECTOR_SIZE);
+        // first selected row at or after this thread's range (sel is ascending)
+        size_t s_pos = sel ? (size_t)(std::lower_bound(sel, sel + n_sel, (uint32_t)(c_lo * STANDARD_VECTOR_SIZE)) - sel) : 0;
+        for (size_t c = c_lo; c < c_hi; c++) {
+          const size_t lo = c * STANDARD_VECTOR_SIZE, hi = std::min(rows, lo + STANDARD_VECTOR_SIZE);
+          idx_t count = hi - lo;
+          if (sel) {
+            count = 0;
+            while (s_pos < n_sel && sel[s_pos] < hi) rel[count++] = (sel_t)(sel[s_pos++] - lo);
+            if (!count) continue;
+          }
+          for (idx_t r = 0; r < count; r++) {
+            const size_t row = lo + (sel ? rel[r] : r);
+            const int g = group ? group[row] : 0;
+            if (g < 0 || g >= n_groups) throw InvalidInputException("group slot out of range");
+            data_ptr_t st = loc.mem.get() + (size_t)g * ssz;
+            if (!loc.live[g]) {
+              fun.initialize(st);
+              loc.live[g] = 1;
+            }
+            ptrs[r] = st;
+          }
+          // scan vectors over the table's column storage (+ the filter's selection on top)
+          std::vector<Vector> inputs;
+          inputs.reserve(n_cols);
+          for (int k = 0; k < n_num; k++) inputs.emplace_back(LogicalType::FLOAT, (data_ptr_t)(num[k] + lo));
+          for (int k = 0; k < n_cat; k++) inputs.emplace_back(LogicalType::INTEGER, (data_ptr_t)(cat[k] + lo));
+          if (sel)
+            for (auto &v : inputs) v.Slice(SelectionVector(rel.data()));
+          Vector state_vector(LogicalType::POINTER, (data_ptr_t)ptrs.data());
+          fun.update(inputs.data(), aggr, (idx_t)n_cols, state_vector, count);
+        }
+      } catch (std::exception &e) {
+        std::lock_guard<std::mutex> g(err_mu);
+        worker_error = e.what();
+      }
+    };
+    if (T == 1) {
+      worker(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < T; t++) pool.emplace_back(worker, t);
+      for (auto &th : pool) th.join();
+    }
+    if (!worker_error.empty()) throw Exception(worker_error);
+
+    // combine the thread-local states into thread 0's, group by group, then destroy sources
+    ThreadLocalStates &dst = tls[0];
+    for (int t = 1; t < T; t++) {
+      std::vector<data_ptr_t> src_p, dst_p;
+      for (int g = 0; g < n_groups; g++)
+        if (tls[t].live[g]) {
+          data_ptr_t d = dst.mem.get() + (size_t)g * ssz;
+          if (!dst.live[g]) {
+            fun.initialize(d);
+            dst.live[g] = 1;
+          }
+          src_p.push_back(tls[t].mem.get() + (size_t)g * ssz);
+          dst_p.push_back(d);
+        }
+      if (src_p.empty()) continue;
+      Vector sv(LogicalType::POINTER, (data_ptr_t)src_p.data()), dv(LogicalType::POINTER, (data_ptr_t)dst_p.data());
+      fun.combine(sv, dv, aggr, src_p.size());
+      if (fun.destructor) fun.destructor(sv, aggr, src_p.size());
+    }
+    std::vector<data_ptr_t> fin;
+    for (int g = 0; g < n_groups; g++)
+      if (dst.live[g]) fin.push_back(dst.mem.get() + (size_t)g * ssz);
+    std::ostringstream os;
+    os << "[";
+    double secs = 0;
+    if (!fin.empty()) {
+      Vector states(LogicalType::POINTER, (data_ptr_t)fin.data());
+      Vector result(fun.return_type, std::max<idx_t>(fin.size(), 1));
+      fun.finalize(states, aggr, result, fin.size(), 0);
+      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      for (size_t i = 0; i < fin.size(); i++) {
+        if (i) os << ", ";
+        RenderValue(result, i, os);
+      }
+      if (fun.destructor) fun.destructor(states, aggr, fin.size());
+    } else {
+      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    os << "]";
+    if (seconds) *seconds = secs;
+    *json_out = strdup(os.str().c_str());
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"

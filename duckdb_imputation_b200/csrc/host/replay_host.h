@@ -1,0 +1,45 @@
+/* replay_host.h -- C API of the hash-aggregate replay ("mini DuckDB operator").
+ *
+ * DuckDB itself is not available here, so this is the caller side of the drop-in boundary:
+ * it drives a registered duckdb::AggregateFunction with the exact protocol DuckDB 0.9.2's
+ * PhysicalHashAggregate uses for the ring aggregates: bind once; T worker
+ * threads, each with thread-local states (state_size bytes, initialize on first use), scanning
+ * contiguous morsels in chunks of <= 2048 rows and calling
+ *   update(inputs[], aggr_input_data, input_count, state_vector /-* one pointer per row *-/, count)
+ * then combine(source, target) of the thread-local states, destructor on the sources,
+ * finalize(states, result, count, 0) and destructor on the targets.
+ * The same file is linked (a) with our extension (ring_extension.cpp + triple_glue.cpp) and
+ * (b) with the reference's own sources (oracle/ref_extension.cpp) -- one driver, two
+ * implementations behind the same callback API.
+ */
+#ifndef CFB_REPLAY_HOST_H
+#define CFB_REPLAY_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Run  SELECT <function>(num..., cat...) FROM t [WHERE row in sel] [GROUP BY group]
+ *   function   registered name, e.g. "sum_to_triple_3_3"
+ *   group      per-row group slot in [0, n_groups) or NULL; results come back in slot order,
+ *              slots without rows are omitted
+ *   sel        ascending row ids that pass the filter, or NULL (n_sel ignored); filtered chunks
+ *              reach update() as DICTIONARY vectors (selection on top of the scan vectors)
+ *   json_out   malloc'd JSON array with one STRUCT per group (free with replay_free)
+ *   seconds    wall time of update + combine + finalize
+ * Returns 0, or -1 with the message in replay_last_error().                             */
+int replay_aggregate(const char *function, int n_num, int n_cat, const float *const *num,
+                     const int32_t *const *cat, const int32_t *group, int n_groups, const uint32_t *sel,
+                     size_t n_sel, size_t rows, int threads, char **json_out, double *seconds);
+void replay_free(char *p);
+const char *replay_last_error(void);
+/* Names of all registered aggregate functions, '\n'-separated (malloc'd). */
+char *replay_list_functions(void);
+/* Which implementation is behind this library: "b200" or "reference". */
+const char *replay_implementation(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,50 @@
+// ring_extension.cpp -- registration of the ring aggregates, B200 build.
+//
+// Mirrors load_ring / load_nb_ring of the reference (duckdb_imputation_extension.cpp:80-113,
+// :146-179): the same SQL names, argument types, constructor-argument order
+//   (name, arg_types, return_type, state_size, initialize, update, combine, finalize,
+//    simple_update = nullptr, bind, destructor, statistics = nullptr, window = nullptr),
+// varargs = ANY and SPECIAL null handling.  The reference's loops stop at 19 although its
+// README promises 20 (README.md:136); this build registers i, j in [0, 20] -- a superset that
+// includes the headline sum_to_triple_20_0.
+#include <string>
+
+#include "triple_glue.h"
+
+namespace duckdb_ring {
+
+const char *Implementation() { return "b200"; }
+
+void Load(duckdb::DatabaseInstance &instance) {
+  using namespace duckdb;
+  constexpr int kMaxCols = 20;
+  for (int i = 0; i <= kMaxCols; i++)
+    for (int j = 0; j <= kMaxCols; j++) {
+      if (i == 0 && j == 0) continue;
+      vector<LogicalType> args;
+      for (int k = 0; k < i; k++) args.push_back(LogicalType::FLOAT);
+      for (int k = 0; k < j; k++) args.push_back(LogicalType::INTEGER);
+      const std::string xy = std::to_string(i) + "_" + std::to_string(j);
+      AggregateFunction triple("sum_to_triple_" + xy, args, LogicalTypeId::STRUCT,
+                               AggregateFunction::StateSize<Triple::SumState>,
+                               AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>,
+                               Triple::SumNoLift, Triple::SumStateCombine, Triple::SumStateFinalize, nullptr,
+                               Triple::SumNoLiftBind,
+                               AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
+      triple.varargs = LogicalType::ANY;
+      triple.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+      ExtensionUtil::RegisterFunction(instance, triple);
+
+      AggregateFunction nb("sum_to_nb_agg_" + xy, args, LogicalTypeId::STRUCT,
+                           AggregateFunction::StateSize<Triple::SumState>,
+                           AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>,
+                           Triple::sum_to_nb_agg, Triple::SumStateCombine, Triple::SumStateFinalize, nullptr,
+                           Triple::sum_to_nb_agg_bind,
+                           AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
+      nb.varargs = LogicalType::ANY;
+      nb.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+      ExtensionUtil::RegisterFunction(instance, nb);
+    }
+}
+
+}  // namespace duckdb_ring

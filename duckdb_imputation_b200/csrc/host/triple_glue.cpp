@@ -1,0 +1,331 @@
+// triple_glue.cpp -- DuckDB aggregate callbacks -> C ABI (include/cofactor_b200.h).
+//
+//   update    Triple::SumNoLift / Triple::sum_to_nb_agg   (reference: sum_no_lift.cpp:53-216,
+//             sum_to_nb_agg.cpp:39-146): read the chunk through UnifiedVectorFormat, route
+//             rows to their states, hand column base pointers + selection vectors to
+//             cfb_ctx_append (pinned staging -> cudaMemcpyAsync -> kernels).
+//   combine   Triple::SumStateCombine (sum_state.cpp:10-114): adopt or cfb_ctx_combine.
+//   finalize  Triple::SumStateFinalize (sum_state.cpp:116-464): cfb_ctx_finalize, then write
+//             the nested STRUCT vector in the reference's layout.
+// Errors of the C ABI become duckdb::InternalException / InvalidInputException (never abort).
+#include "triple_glue.h"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../../include/cofactor_b200.h"
+
+namespace Triple {
+
+namespace {
+
+void Check(int rc) {
+  if (rc == CFB_OK) return;
+  const std::string msg = cfb_last_error();
+  if (rc == CFB_ERR_INVALID || rc == CFB_ERR_DOMAIN) throw duckdb::InvalidInputException(msg);
+  throw duckdb::InternalException(msg);
+}
+
+// States are spread over the visible devices (CFB_DEVICES=all, default: device 0 only): one
+// DuckDB worker thread keeps feeding the same state, so a state's device never changes.
+int PickDevice() {
+  static const int n_dev = [] {
+    const char *e = getenv("CFB_DEVICES");
+    if (!e || strcmp(e, "all") != 0) return 1;
+    return cfb_device_count() > 0 ? cfb_device_count() : 1;
+  }();
+  static std::atomic<unsigned> next{0};
+  return n_dev == 1 ? 0 : (int)(next.fetch_add(1) % (unsigned)n_dev);
+}
+
+duckdb::LogicalType KeyValueList() {
+  duckdb::child_list_t<duckdb::LogicalType> kv;
+  kv.emplace_back("key", duckdb::LogicalType::INTEGER);
+  kv.emplace_back("value", duckdb::LogicalType::FLOAT);
+  return duckdb::LogicalType::LIST(duckdb::LogicalType::LIST(duckdb::LogicalType::STRUCT(kv)));
+}
+
+// STRUCT(N, lin_agg, quad_agg, lin_cat[, quad_num_cat, quad_cat])  -- sum_no_lift.cpp:21-44,
+// sum_to_nb_agg.cpp:18-30
+duckdb::LogicalType ResultType(bool nb) {
+  duckdb::child_list_t<duckdb::LogicalType> f;
+  f.emplace_back("N", duckdb::LogicalType::INTEGER);
+  f.emplace_back("lin_agg", duckdb::LogicalType::LIST(duckdb::LogicalType::FLOAT));
+  f.emplace_back("quad_agg", duckdb::LogicalType::LIST(duckdb::LogicalType::FLOAT));
+  f.emplace_back("lin_cat", KeyValueList());
+  if (!nb) {
+    f.emplace_back("quad_num_cat", KeyValueList());
+    duckdb::child_list_t<duckdb::LogicalType> kkv;
+    kkv.emplace_back("key1", duckdb::LogicalType::INTEGER);
+    kkv.emplace_back("key2", duckdb::LogicalType::INTEGER);
+    kkv.emplace_back("value", duckdb::LogicalType::FLOAT);
+    f.emplace_back("quad_cat", duckdb::LogicalType::LIST(duckdb::LogicalType::LIST(duckdb::LogicalType::STRUCT(kkv))));
+  }
+  return duckdb::LogicalType::STRUCT(f);
+}
+
+void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state_vector, idx_t count) {
+  if (count == 0) return;
+  duckdb::UnifiedVectorFormat sdata;
+  state_vector.ToUnifiedFormat(count, sdata);
+  auto states = (SumState **)sdata.data;
+
+  // FLOAT (and DOUBLE, like the reference) columns are numeric, everything else categorical;
+  // numeric columns come first (README.md:126).
+  const float *num[CFB_MAX_NUM];
+  const uint32_t *num_sel[CFB_MAX_NUM];
+  const int32_t *cat[CFB_MAX_CAT];
+  const uint32_t *cat_sel[CFB_MAX_CAT];
+  duckdb::UnifiedVectorFormat fmt[CFB_MAX_NUM + CFB_MAX_CAT];
+  if (cols > CFB_MAX_NUM + CFB_MAX_CAT) throw duckdb::InvalidInputException("too many columns for a ring aggregate");
+  int n = 0, m = 0;
+  for (idx_t j = 0; j < cols; j++) {
+    inputs[j].ToUnifiedFormat(count, fmt[j]);
+    const auto &t = inputs[j].GetType();
+    if (t == duckdb::LogicalType::FLOAT || t == duckdb::LogicalType::DOUBLE) {
+      if (m) throw duckdb::InvalidInputException("numeric columns must precede categorical columns");
+      if (n == CFB_MAX_NUM) throw duckdb::InvalidInputException("too many numeric columns");
+      num[n] = duckdb::UnifiedVectorFormat::GetData<float>(fmt[j]);
+      num_sel[n++] = fmt[j].sel->sel;
+    } else {
+      if (m == CFB_MAX_CAT) throw duckdb::InvalidInputException("too many categorical columns");
+      cat[m] = duckdb::UnifiedVectorFormat::GetData<int32_t>(fmt[j]);
+      cat_sel[m++] = fmt[j].sel->sel;
+    }
+  }
+  auto ensure = [&](SumState *s) {
+    if (!s->ctx) Check(cfb_ctx_create(PickDevice(), kind, n, m, 1, &s->ctx));  // lazy shape, sum_no_lift.cpp:96-116
+  };
+
+  // Ungrouped aggregates (and single-group chunks) send every row to one state.
+  SumState *first = states[sdata.sel->get_index(0)];
+  bool uniform = true;
+  for (idx_t r = 1; r < count && uniform; r++) uniform = states[sdata.sel->get_index(r)] == first;
+  if (uniform) {
+    ensure(first);
+    Check(cfb_ctx_append(first->ctx, num, num_sel, cat, cat_sel, nullptr, count));
+    return;
+  }
+  // GROUP BY: bucket the chunk's rows by state and append each bucket through composed
+  // selection vectors (the states[sdata.sel->get_index(j)] indirection of the reference).
+  SumState *seen[STANDARD_VECTOR_SIZE];
+  uint32_t n_seen = 0;
+  std::vector<std::vector<uint32_t>> rows_of;
+  for (idx_t r = 0; r < count; r++) {
+    SumState *s = states[sdata.sel->get_index(r)];
+    uint32_t b = 0;
+    while (b < n_seen && seen[b] != s) b++;
+    if (b == n_seen) {
+      seen[n_seen++] = s;
+      rows_of.emplace_back();
+    }
+    rows_of[b].push_back((uint32_t)r);
+  }
+  std::vector<uint32_t> composed((size_t)(n + m) * count);
+  for (uint32_t b = 0; b < n_seen; b++) {
+    const auto &rows = rows_of[b];
+    const uint32_t *nsel[CFB_MAX_NUM], *csel[CFB_MAX_CAT];
+    for (int k = 0; k < n + m; k++) {
+      const uint32_t *src = k < n ? num_sel[k] : cat_sel[k - n];
+      uint32_t *dst = composed.data() + (size_t)k * count;
+      if (src)
+        for (size_t i = 0; i < rows.size(); i++) dst[i] = src[rows[i]];
+      else
+        memcpy(dst, rows.data(), rows.size() * sizeof(uint32_t));
+      if (k < n)
+        nsel[k] = dst;
+      else
+        csel[k - n] = dst;
+    }
+    ensure(seen[b]);
+    Check(cfb_ctx_append(seen[b]->ctx, num, nsel, cat, csel, nullptr, rows.size()));
+  }
+}
+
+}  // namespace
+
+template <class STATE>
+void StateFunction::Destroy(STATE &state, duckdb::AggregateInputData &) {
+  cfb_ctx_destroy(state.ctx);
+  state.ctx = nullptr;
+}
+template void StateFunction::Destroy<SumState>(SumState &, duckdb::AggregateInputData &);
+
+duckdb::unique_ptr<duckdb::FunctionData> SumNoLiftBind(duckdb::ClientContext &, duckdb::AggregateFunction &function,
+                                                       duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &) {
+  function.return_type = ResultType(false);
+  return duckdb::make_uniq<duckdb::VariableReturnBindData>(function.return_type);
+}
+
+duckdb::unique_ptr<duckdb::FunctionData> sum_to_nb_agg_bind(duckdb::ClientContext &, duckdb::AggregateFunction &function,
+                                                            duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &) {
+  function.return_type = ResultType(true);
+  return duckdb::make_uniq<duckdb::VariableReturnBindData>(function.return_type);
+}
+
+void SumNoLift(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::Vector &state_vector,
+               idx_t count) {
+  Update(CFB_TRIPLE, inputs, input_count, state_vector, count);
+}
+
+void sum_to_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &, duckdb::idx_t cols, duckdb::Vector &state_vector,
+                   duckdb::idx_t count) {
+  Update(CFB_NB, inputs, cols, state_vector, count);
+}
+
+void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::AggregateInputData &, idx_t count) {
+  duckdb::UnifiedVectorFormat sdata;
+  state.ToUnifiedFormat(count, sdata);
+  auto src = (SumState **)sdata.data;
+  auto dst = duckdb::FlatVector::GetData<SumState *>(combined);
+  for (idx_t i = 0; i < count; i++) {
+    SumState *s = src[sdata.sel->get_index(i)];
+    if (!s->ctx) continue;  // the source never saw a row
+    if (!dst[i]->ctx) {
+      // empty target adopts the source's device state (sum_state.cpp:26-60); the source stays
+      // destroyable: its destructor sees a null handle
+      dst[i]->ctx = s->ctx;
+      s->ctx = nullptr;
+    } else {
+      Check(cfb_ctx_combine(dst[i]->ctx, s->ctx));
+    }
+  }
+}
+
+void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &, duckdb::Vector &result, idx_t count,
+                      idx_t offset) {
+  using namespace duckdb;
+  if (offset != 0) throw InternalException("ring aggregate finalize expects offset 0");  // sum_state.cpp:120
+  if (count == 0) return;
+  UnifiedVectorFormat sdata;
+  state_vector.ToUnifiedFormat(count, sdata);
+  auto states = (SumState **)sdata.data;
+
+  // Pull every group's canonical result first: list children are sized once, then filled.
+  std::vector<cfb_result> res(count);
+  struct Guard {
+    std::vector<cfb_result> &r;
+    ~Guard() {
+      for (auto &x : r) cfb_result_free(&x);
+    }
+  } guard{res};
+  const bool nb = StructVector::GetEntries(result).size() == 4;
+  int n = 0, m = 0;
+  idx_t total_keys = 0, total_pairs = 0;
+  for (idx_t i = 0; i < count; i++) {
+    SumState *s = states[sdata.sel->get_index(i)];
+    memset(&res[i], 0, sizeof(cfb_result));
+    if (s->ctx) {
+      Check(cfb_ctx_finalize(s->ctx, 0, &res[i]));
+      n = res[i].n_num;
+      m = res[i].n_cat;
+    }
+    total_keys += (idx_t)res[i].total_keys;
+    if (res[i].pair_offsets) total_pairs += (idx_t)res[i].pair_offsets[res[i].n_pair_lists];
+  }
+  const idx_t nq = nb ? (idx_t)n : (idx_t)n * (n + 1) / 2;
+  const idx_t npl = (idx_t)m * (m + 1) / 2;
+
+  auto &kids = StructVector::GetEntries(result);
+  Vector &vN = *kids[0], &vLin = *kids[1], &vQuad = *kids[2], &vLinCat = *kids[3];
+  auto N = FlatVector::GetData<int32_t>(vN);
+
+  ListVector::Reserve(vLin, (idx_t)n * count);
+  ListVector::SetListSize(vLin, (idx_t)n * count);
+  ListVector::Reserve(vQuad, nq * count);
+  ListVector::SetListSize(vQuad, nq * count);
+  auto lin_e = ListVector::GetData(vLin);
+  auto quad_e = ListVector::GetData(vQuad);
+  auto lin_d = FlatVector::GetData<float>(ListVector::GetEntry(vLin));
+  auto quad_d = FlatVector::GetData<float>(ListVector::GetEntry(vQuad));
+
+  // lin_cat: LIST(LIST(STRUCT(key,value))): outer = m lists per group, inner = keys
+  ListVector::Reserve(vLinCat, (idx_t)m * count);
+  ListVector::SetListSize(vLinCat, (idx_t)m * count);
+  Vector &lc_inner = ListVector::GetEntry(vLinCat);
+  ListVector::Reserve(lc_inner, total_keys);
+  ListVector::SetListSize(lc_inner, total_keys);
+  auto lc_outer_e = ListVector::GetData(vLinCat);
+  auto lc_inner_e = ListVector::GetData(lc_inner);
+  auto &lc_kv = StructVector::GetEntries(ListVector::GetEntry(lc_inner));
+  auto lc_key = FlatVector::GetData<int32_t>(*lc_kv[0]);
+  auto lc_val = FlatVector::GetData<float>(*lc_kv[1]);
+
+  list_entry_t *nc_outer_e = nullptr, *nc_inner_e = nullptr, *cc_outer_e = nullptr, *cc_inner_e = nullptr;
+  int32_t *nc_key = nullptr, *cc_k1 = nullptr, *cc_k2 = nullptr;
+  float *nc_val = nullptr, *cc_val = nullptr;
+  if (!nb) {
+    Vector &vNumCat = *kids[4], &vCatCat = *kids[5];
+    ListVector::Reserve(vNumCat, (idx_t)n * m * count);
+    ListVector::SetListSize(vNumCat, (idx_t)n * m * count);
+    Vector &nc_inner = ListVector::GetEntry(vNumCat);
+    ListVector::Reserve(nc_inner, total_keys * n);
+    ListVector::SetListSize(nc_inner, total_keys * n);
+    nc_outer_e = ListVector::GetData(vNumCat);
+    nc_inner_e = ListVector::GetData(nc_inner);
+    auto &nc_kv = StructVector::GetEntries(ListVector::GetEntry(nc_inner));
+    nc_key = FlatVector::GetData<int32_t>(*nc_kv[0]);
+    nc_val = FlatVector::GetData<float>(*nc_kv[1]);
+    ListVector::Reserve(vCatCat, npl * count);
+    ListVector::SetListSize(vCatCat, npl * count);
+    Vector &cc_inner = ListVector::GetEntry(vCatCat);
+    ListVector::Reserve(cc_inner, total_pairs);
+    ListVector::SetListSize(cc_inner, total_pairs);
+    cc_outer_e = ListVector::GetData(vCatCat);
+    cc_inner_e = ListVector::GetData(cc_inner);
+    auto &cc_kkv = StructVector::GetEntries(ListVector::GetEntry(cc_inner));
+    cc_k1 = FlatVector::GetData<int32_t>(*cc_kkv[0]);
+    cc_k2 = FlatVector::GetData<int32_t>(*cc_kkv[1]);
+    cc_val = FlatVector::GetData<float>(*cc_kkv[2]);
+  }
+
+  idx_t key_pos = 0, nc_pos = 0, cc_pos = 0;
+  for (idx_t i = 0; i < count; i++) {
+    const cfb_result &r = res[i];
+    const bool live = r.lin != nullptr;
+    N[i] = (int32_t)r.N;  // INTEGER in the STRUCT (sum_no_lift.cpp:22)
+    lin_e[i] = {i * (idx_t)n, (idx_t)n};
+    quad_e[i] = {i * nq, nq};
+    for (int k = 0; k < n; k++) lin_d[i * n + k] = live ? (float)r.lin[k] : 0.f;
+    for (idx_t k = 0; k < nq; k++) quad_d[i * nq + k] = live ? (float)r.quad[k] : 0.f;
+    // lin_cat[c] = [{key, count}], keys ascending (sum_state.cpp:372-395)
+    lc_outer_e[i] = {i * (idx_t)m, (idx_t)m};
+    const idx_t group_key0 = key_pos;
+    for (int c = 0; c < m; c++) {
+      const idx_t lo = live ? (idx_t)r.cat_offsets[c] : 0, hi = live ? (idx_t)r.cat_offsets[c + 1] : 0;
+      lc_inner_e[i * m + c] = {key_pos, hi - lo};
+      for (idx_t t = lo; t < hi; t++, key_pos++) {
+        lc_key[key_pos] = r.cat_keys[t];
+        lc_val[key_pos] = (float)r.cat_counts[t];
+      }
+    }
+    (void)group_key0;
+    if (nb) continue;
+    // quad_num_cat: sub-list index num*m + cat (sum_state.cpp:383-404); value = sum x_num | key
+    nc_outer_e[i] = {i * (idx_t)n * m, (idx_t)n * m};
+    for (int k = 0; k < n; k++)
+      for (int c = 0; c < m; c++) {
+        const idx_t lo = live ? (idx_t)r.cat_offsets[c] : 0, hi = live ? (idx_t)r.cat_offsets[c + 1] : 0;
+        nc_inner_e[(i * n + k) * m + c] = {nc_pos, hi - lo};
+        for (idx_t t = lo; t < hi; t++, nc_pos++) {
+          nc_key[nc_pos] = r.cat_keys[t];
+          nc_val[nc_pos] = (float)r.numcat_sums[(idx_t)k * r.total_keys + t];
+        }
+      }
+    // quad_cat: m(m+1)/2 lists in (k<=l) order, entries ascending by (key1,key2) (sum_state.cpp:440-461)
+    cc_outer_e[i] = {i * npl, npl};
+    for (idx_t p = 0; p < npl; p++) {
+      const idx_t lo = live ? (idx_t)r.pair_offsets[p] : 0, hi = live ? (idx_t)r.pair_offsets[p + 1] : 0;
+      cc_inner_e[i * npl + p] = {cc_pos, hi - lo};
+      for (idx_t t = lo; t < hi; t++, cc_pos++) {
+        cc_k1[cc_pos] = r.pair_key1[t];
+        cc_k2[cc_pos] = r.pair_key2[t];
+        cc_val[cc_pos] = (float)r.pair_counts[t];
+      }
+    }
+  }
+}
+
+}  // namespace Triple

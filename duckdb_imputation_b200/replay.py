@@ -1,0 +1,98 @@
+"""ctypes front end of the hash-aggregate replay host (csrc/host/replay_host.h).
+
+`Replay(path)` wraps one library built around the replay host:
+  * duckdb_imputation_b200/lib/libduckdb_imputation_b200.so -- OUR extension (CUDA behind the
+    DuckDB aggregate callbacks);
+  * oracle/_ref/libref_replay.so -- the reference's own sources (test infrastructure; loaded
+    only through oracle/ref_replay.py).
+`query()` is the SQL-shaped entry the parity tests use:  SELECT fn(cols) FROM t [WHERE..] [GROUP BY gb].
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from ._native import ptr_array
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GLUE_LIB_PATH = os.path.join(_HERE, "lib", "libduckdb_imputation_b200.so")
+
+
+class ReplayError(RuntimeError):
+    pass
+
+
+class Replay:
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing (build it: __graft_entry__.build())")
+        l = C.CDLL(path, mode=C.RTLD_GLOBAL if path == GLUE_LIB_PATH else C.RTLD_LOCAL)
+        P = C.c_void_p
+        l.replay_aggregate.restype = C.c_int
+        l.replay_aggregate.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
+                                       C.c_size_t, C.c_size_t, C.c_int, C.POINTER(P), C.POINTER(C.c_double)]
+        l.replay_free.argtypes = [P]
+        l.replay_last_error.restype = C.c_char_p
+        l.replay_list_functions.restype = P
+        l.replay_implementation.restype = C.c_char_p
+        self.lib = l
+        self.last_seconds = 0.0
+
+    @property
+    def implementation(self) -> str:
+        return self.lib.replay_implementation().decode()
+
+    def functions(self):
+        p = self.lib.replay_list_functions()
+        try:
+            return C.string_at(p).decode().split()
+        finally:
+            self.lib.replay_free(p)
+
+    def aggregate(self, function: str, num_cols, cat_cols, group=None, n_groups=1, sel=None, threads=1):
+        """Raw call: group = int32 slots; sel = ascending uint32 row ids.  -> list of STRUCT dicts."""
+        kn = [np.ascontiguousarray(c, np.float32) for c in num_cols]
+        kc = [np.ascontiguousarray(c, np.int32) for c in cat_cols]
+        rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
+        g = None if group is None else np.ascontiguousarray(group, np.int32)
+        s = None if sel is None else np.ascontiguousarray(sel, np.uint32)
+        out = C.c_void_p()
+        secs = C.c_double()
+        rc = self.lib.replay_aggregate(function.encode(), len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
+                                       ptr_array([k.ctypes.data for k in kc]), None if g is None else g.ctypes.data,
+                                       n_groups, None if s is None else s.ctypes.data, 0 if s is None else len(s), rows,
+                                       threads, C.byref(out), C.byref(secs))
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            self.last_seconds = secs.value
+            return json.loads(C.string_at(out).decode())
+        finally:
+            self.lib.replay_free(out)
+
+    def query(self, kind, num_cols, cat_cols, group_by=None, where=None, threads=1):
+        """Same signature as oracle.aggregate / aggregates._aggregate (tests/sqlmini.py backend)."""
+        fn = ("sum_to_triple_%d_%d" if kind == 0 else "sum_to_nb_agg_%d_%d") % (len(num_cols), len(cat_cols))
+        sel = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
+        if group_by is None:
+            return self.aggregate(fn, num_cols, cat_cols, sel=sel, threads=threads)[0]
+        gb = np.asarray(group_by)
+        labels = np.unique(gb)
+        slots = np.searchsorted(labels, gb).astype(np.int32)
+        return self.aggregate(fn, num_cols, cat_cols, group=slots, n_groups=max(1, len(labels)), sel=sel, threads=threads)
+
+
+_glue = None
+
+
+def glue() -> Replay:
+    """Our extension behind the replay host (needs a CUDA device to run queries)."""
+    global _glue
+    if _glue is None:
+        from . import _native
+        _native.lib()  # libcofactor_b200.so first: the glue links against it
+        _glue = Replay(GLUE_LIB_PATH)
+    return _glue

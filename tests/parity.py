@@ -39,3 +39,27 @@ def max_rel_err(got: dict, ref: dict) -> float:
             if nz.any():
                 worst = max(worst, float(np.max(np.abs(g - r)[nz] / np.abs(r)[nz])))
     return worst
+
+
+def assert_struct_parity(got: dict, ref: dict, rtol: float = RTOL, abs_floor: float = 0.0, what=""):
+    """Same bar on two result STRUCT dicts (the Python form of the DuckDB value): N, every key and
+    every count exact; lin_agg / quad_agg / quad_num_cat values within rtol."""
+    assert list(got.keys()) == list(ref.keys()), f"{what}: fields {list(got.keys())} != {list(ref.keys())}"
+    assert got["N"] == ref["N"], what
+    assert got["lin_cat"] == ref["lin_cat"], f"{what}: lin_cat differs"
+    if "quad_cat" in ref:
+        assert got["quad_cat"] == ref["quad_cat"], f"{what}: quad_cat differs"
+
+    def close(a, b, where):
+        assert abs(a - b) <= rtol * abs(b) + abs_floor, f"{what}: {where}: {a} vs {b}"
+
+    for f in ("lin_agg", "quad_agg"):
+        assert len(got[f]) == len(ref[f]), f"{what}: {f} length"
+        for i, (a, b) in enumerate(zip(got[f], ref[f])):
+            close(a, b, f"{f}[{i}]")
+    if "quad_num_cat" in ref:
+        assert len(got["quad_num_cat"]) == len(ref["quad_num_cat"])
+        for li, (la, lb) in enumerate(zip(got["quad_num_cat"], ref["quad_num_cat"])):
+            assert [e["key"] for e in la] == [e["key"] for e in lb], f"{what}: quad_num_cat[{li}] keys"
+            for a, b in zip(la, lb):
+                close(a["value"], b["value"], f"quad_num_cat[{li}][{a['key']}]")

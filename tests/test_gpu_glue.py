@@ -1,0 +1,60 @@
+"""GPU suite: OUR extension behind the DuckDB aggregate callbacks (triple_glue.cpp), driven by the
+hash-aggregate replay host with DuckDB's protocol, against the reference goldens and the oracle."""
+import numpy as np
+import pytest
+
+from duckdb_imputation_b200 import replay
+from oracle import oracle
+from tests import sqlmini
+from tests.parity import assert_struct_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_registration_superset_of_the_reference():
+    fns = set(replay.glue().functions())
+    assert replay.glue().implementation == "b200"
+    for name in ("sum_to_triple_3_3", "sum_to_triple_19_19", "sum_to_triple_20_0", "sum_to_nb_agg_12_4", "sum_to_triple_20_10"):
+        assert name in fns
+    assert "sum_to_triple_0_0" not in fns and len(fns) == 2 * (21 * 21 - 1)
+
+
+def test_goldens_through_the_duckdb_callbacks(goldens):
+    g = replay.glue()
+    cases = [c for c in goldens["cases"] if c["file"] in ("test_sum.py", "test_nb_sum.py")]
+    for threads in (1, 3):
+        for c in cases:
+            got = sqlmini.run_sum(c["sql"], goldens["fixtures"][c["file"]],
+                                  lambda *a, **k: g.query(*a, threads=threads, **k))
+            assert got[c["index"]] == c["expected"], (c["file"], c["test"], c["index"], threads)
+
+
+@pytest.mark.parametrize("kind,n,m", [(0, 20, 0), (0, 10, 10), (1, 12, 4), (0, 5, 0), (0, 3, 3), (0, 0, 2)])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_callbacks_match_oracle(kind, n, m, threads):
+    rng = np.random.default_rng(17 * n + m + threads)
+    rows = 100_003
+    num = [rng.random(rows).astype(np.float32) for _ in range(n)]
+    cat = [rng.integers(-2, 25, rows).astype(np.int32) for _ in range(m)]
+    got = replay.glue().query(kind, num, cat, threads=threads)
+    assert_struct_parity(got, oracle.aggregate(kind, num, cat), what=f"{kind} {n} {m} T={threads}")
+
+
+def test_group_by_and_where_through_callbacks():
+    rng = np.random.default_rng(3)
+    rows = 80_000
+    num = [rng.random(rows).astype(np.float32) for _ in range(12)]
+    cat = [rng.integers(0, 30, rows).astype(np.int32) for _ in range(4)]
+    gb = rng.integers(0, 10, rows)
+    keep = rng.random(rows) < 0.8
+    for kind in (0, 1):
+        got = replay.glue().query(kind, num, cat, group_by=gb, where=keep, threads=4)
+        ref = oracle.aggregate(kind, num, cat, group_by=gb, where=keep)
+        assert len(got) == len(ref) == 10
+        for g, (a, b) in enumerate(zip(got, ref)):
+            assert_struct_parity(a, b, what=f"kind {kind} group {g}")
+
+
+def test_unknown_function_is_a_query_error():
+    with pytest.raises(replay.ReplayError, match="does not exist"):
+        replay.glue().aggregate("sum_to_triple_21_0", [np.zeros(4, np.float32)] * 21, [])
