@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=FULL_ROWS, help="rows per GPU (default: the 1 B of BASELINE.json)")
-    ap.add_argument("--e2e-rows", type=int, default=32_000_000)
+    ap.add_argument("--e2e-rows", type=int, default=64_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -291,25 +291,22 @@ def main():
     for c in ctxs:
         c.close()
 
-    # ---- end to end: host buffers -> C ABI (pinned staging + cudaMemcpyAsync + kernels) -> result on host
+    # ---- end to end: host (DuckDB-side) buffers -> the extension's aggregate callbacks under DuckDB's
+    # protocol (T threads x 2048-row chunks, update/combine/finalize) -> pinned staging ->
+    # cudaMemcpyAsync -> kernels -> result STRUCT back on the host.
     e2e = None
     if not args.no_e2e:
+        from duckdb_imputation_b200 import replay
         er = args.e2e_rows
+        threads = max(1, (os.cpu_count() or 1) // world)
         rng = np.random.default_rng(SEED + rank)
         host = [rng.random(er, dtype=np.float32) for _ in range(N_NUM)]
-        ptrs = nat.ptr_array([h.ctypes.data for h in host])
-        import ctypes as C
+        os.environ["CFB_DEVICE"] = str(local)
+        g = replay.glue()
 
         def e2e_step():
-            h = C.c_void_p()
-            nat.check(lib.cfb_ctx_create(local, CFB_TRIPLE, N_NUM, 0, 1, C.byref(h)))
-            nat.check(lib.cfb_ctx_append(h, ptrs, None, nat.ptr_array([]), None, None, er))
-            res = nat.Result()
-            nat.check(lib.cfb_ctx_finalize(h, 0, C.byref(res)))
-            n = res.N
-            lib.cfb_result_free(C.byref(res))
-            lib.cfb_ctx_destroy(h)
-            return n
+            res = g.aggregate(f"sum_to_triple_{N_NUM}_0", host, [], threads=threads)
+            return res[0]["N"]
 
         for _ in range(2):
             e2e_step()
@@ -325,9 +322,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * er * esteps / dt, "unit": "rows/s", "h2d_bytes_per_step": er * BYTES_PER_ROW,
-               "d2h_bytes_per_step": 8 * (1 + N_NUM + N_NUM * (N_NUM + 1) // 2),
-               "rows_per_step": er, "steps": esteps,
-               "path": "pageable host columns -> cfb_ctx_append (pinned double-buffered staging, cudaMemcpyAsync) -> cfb_ctx_finalize"}
+               "d2h_bytes_per_step": 8 * (1 + N_NUM + N_NUM * (N_NUM + 1) // 2) * threads,
+               "rows_per_step": er, "steps": esteps, "host_threads": threads,
+               "path": "pageable host columns -> DuckDB aggregate callbacks (replay host: %d threads, 2048-row chunks) -> "
+                       "cfb_ctx_append (pinned double-buffered staging, cudaMemcpyAsync) -> combine -> finalize" % threads}
         del host
 
     if rank != 0:

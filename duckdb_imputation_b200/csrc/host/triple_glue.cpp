@@ -28,9 +28,11 @@ void Check(int rc) {
   throw duckdb::InternalException(msg);
 }
 
-// States are spread over the visible devices (CFB_DEVICES=all, default: device 0 only): one
-// DuckDB worker thread keeps feeding the same state, so a state's device never changes.
+// Device of a new state: CFB_DEVICE=<k> pins every state to device k (one process per GPU);
+// CFB_DEVICES=all spreads states over the visible devices (one DuckDB worker thread keeps
+// feeding the same state, so a state's device never changes); default: device 0.
 int PickDevice() {
+  if (const char *one = getenv("CFB_DEVICE")) return atoi(one);
   static const int n_dev = [] {
     const char *e = getenv("CFB_DEVICES");
     if (!e || strcmp(e, "all") != 0) return 1;

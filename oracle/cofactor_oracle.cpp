@@ -303,6 +303,51 @@ int run_exact(const Input &in, int n_groups, size_t rows, orc_result *out) {
   return 0;
 }
 
+// With a filter the scan still walks the table in physical 2048-row chunks and every chunk
+// reaches update() with a selection on top (count = rows that pass): chunks and thread morsels
+// are cut in PHYSICAL rows, exactly as the replay host does.
+int run_faithful_filtered(const Input &in, int n_groups, size_t n_sel, size_t table_rows, int threads, orc_result *out) {
+  if (threads < 1) threads = 1;
+  if (n_sel && in.sel[n_sel - 1] >= table_rows) table_rows = (size_t)in.sel[n_sel - 1] + 1;
+  const size_t n_chunks = (table_rows + kChunk - 1) / kChunk;
+  if ((size_t)threads > std::max<size_t>(1, n_chunks)) threads = (int)std::max<size_t>(1, n_chunks);
+  std::vector<std::vector<RefState>> local(threads, std::vector<RefState>(n_groups));
+  int bad = 0;
+  auto worker = [&](int t) {
+    const size_t c_lo = n_chunks * t / threads, c_hi = n_chunks * (t + 1) / threads;
+    std::vector<RefState *> st(kChunk);
+    size_t pos = std::lower_bound(in.sel, in.sel + n_sel, (uint32_t)(c_lo * kChunk)) - in.sel;
+    for (size_t c = c_lo; c < c_hi; c++) {
+      const size_t hi = std::min(table_rows, (c + 1) * kChunk);
+      const size_t first = pos;
+      while (pos < n_sel && in.sel[pos] < hi) {
+        const int g = in.group ? in.group[in.sel[pos]] : 0;
+        if (g < 0 || g >= n_groups) {
+          bad = 1;
+          return;
+        }
+        st[pos - first] = &local[t][g];
+        pos++;
+      }
+      if (pos > first) ref_update_chunk(in, first, pos, st.data());  // rows index the selection
+    }
+  };
+  if (threads == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+    for (auto &th : pool) th.join();
+  }
+  if (bad) return -1;
+  for (int g = 0; g < n_groups; g++) {
+    RefState total;
+    for (int t = 0; t < threads; t++) ref_combine(total, local[t][g]);
+    emit_ref(total, in.kind, in.n, in.m, &out[g]);
+  }
+  return 0;
+}
+
 int run_faithful(const Input &in, int n_groups, size_t rows, int threads, orc_result *out) {
   if (threads < 1) threads = 1;
   const size_t n_chunks = (rows + kChunk - 1) / kChunk;
@@ -348,12 +393,13 @@ extern "C" {
 
 int orc_aggregate(int kind, int mode, int n_num, int n_cat, const float *const *num_cols,
                   const int32_t *const *cat_cols, const int32_t *group, int n_groups,
-                  const uint32_t *sel, size_t rows, int threads, orc_result *out) {
+                  const uint32_t *sel, size_t rows, size_t table_rows, int threads, orc_result *out) {
   if ((kind != ORC_TRIPLE && kind != ORC_NB) || n_num < 0 || n_cat < 0 || n_groups < 1 || !out) return -1;
   Input in{kind, n_num, n_cat, num_cols, cat_cols, group, sel};
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = (mode == ORC_EXACT) ? run_exact(in, n_groups, rows, out)
-                                     : run_faithful(in, n_groups, rows, threads, out);
+                 : sel              ? run_faithful_filtered(in, n_groups, rows, table_rows, threads, out)
+                                    : run_faithful(in, n_groups, rows, threads, out);
   g_last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return rc;
 }

@@ -51,13 +51,14 @@ enum {
 
 /* Aggregate `rows` rows of columnar input into n_groups results (out[g]).
  * group == NULL -> everything goes to group 0.  sel == NULL -> identity; else
- * the aggregate runs over rows sel[0..rows) of the columns (a filtered scan).
+ * the aggregate runs over rows sel[0..rows) (ascending) of the columns, a filtered scan of a
+ * table of table_rows physical rows (only used to cut ORC_FAITHFUL chunks and morsels).
  * Follows sum_no_lift.cpp:83-214 (ORC_TRIPLE) / sum_to_nb_agg.cpp:61-145
  * (ORC_NB), sum_state.cpp:23-112 (combine) and :132-461 (output order).
  * Returns 0, or -1 on bad arguments. */
 int orc_aggregate(int kind, int mode, int n_num, int n_cat, const float *const *num_cols,
                   const int32_t *const *cat_cols, const int32_t *group, int n_groups,
-                  const uint32_t *sel, size_t rows, int threads, orc_result *out);
+                  const uint32_t *sel, size_t rows, size_t table_rows, int threads, orc_result *out);
 
 /* sum_triple(to_cofactor(..)) / sum_nb_agg(to_nb_agg(..)): lift every row to a
  * singleton triple (lift.cpp:85-241, lift_to_nb_agg.cpp:13-136) and add the

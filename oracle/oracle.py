@@ -34,7 +34,7 @@ def lib():
         P = C.c_void_p
         l.orc_aggregate.restype = C.c_int
         l.orc_aggregate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
-                                    C.c_size_t, C.c_int, C.POINTER(Result)]
+                                    C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Result)]
         l.orc_sum_of_lifted.restype = C.c_int
         l.orc_sum_of_lifted.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int,
                                         C.c_size_t, C.POINTER(Result)]
@@ -58,10 +58,11 @@ def aggregate_arrays(kind, num_cols, cat_cols, group=None, n_groups=1, sel=None,
     kc, pc = _cols(cat_cols, np.int32)
     g = None if group is None else np.ascontiguousarray(group, np.int32)
     s = None if sel is None else np.ascontiguousarray(sel, np.uint32)
-    rows = len(s) if s is not None else (len(kn[0]) if kn else (len(kc[0]) if kc else 0))
+    table_rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
+    rows = len(s) if s is not None else table_rows
     out = (Result * n_groups)()
     rc = lib().orc_aggregate(kind, mode, len(kn), len(kc), pn, pc, None if g is None else g.ctypes.data, n_groups,
-                             None if s is None else s.ctypes.data, rows, threads, out)
+                             None if s is None else s.ctypes.data, rows, table_rows, threads, out)
     if rc:
         raise ValueError("orc_aggregate: bad arguments")
     try:

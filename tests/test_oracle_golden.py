@@ -90,7 +90,7 @@ def test_result_add_is_combine():
         kn = [np.ascontiguousarray(c) for c in nc]
         kc = [np.ascontiguousarray(c) for c in cc]
         rc = l.orc_aggregate(0, 0, len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
-                             ptr_array([k.ctypes.data for k in kc]), None, 1, None, len(kn[0]), 1, C.byref(out))
+                             ptr_array([k.ctypes.data for k in kc]), None, 1, None, len(kn[0]), len(kn[0]), 1, C.byref(out))
         assert rc == 0
         return out
 

@@ -36,7 +36,7 @@ def test_reference_registration_grid_stops_at_19():
     fns = set(ref_replay.ref().functions())
     assert "sum_to_triple_19_19" in fns and "sum_to_nb_agg_19_0" in fns
     assert "sum_to_triple_20_0" not in fns and "sum_to_triple_0_0" not in fns  # ext.cpp:80-85
-    assert len(fns) == 2 * 399
+    assert len(fns) == 2 * 399 + 1 and "ref_sum_to_triple_20_0" in fns  # + the bench-only extra
 
 
 @pytest.mark.parametrize("kind", [oracle.TRIPLE, oracle.NB])
