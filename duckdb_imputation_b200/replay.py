@@ -29,7 +29,9 @@ class Replay:
     def __init__(self, path: str):
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing (build it: __graft_entry__.build())")
-        l = C.CDLL(path, mode=C.RTLD_GLOBAL if path == GLUE_LIB_PATH else C.RTLD_LOCAL)
+        # RTLD_LOCAL (+ -Bsymbolic at link time): our extension and the reference build define the same
+        # Triple::* symbols and may be loaded side by side in one test or bench process
+        l = C.CDLL(path, mode=C.RTLD_LOCAL)
         P = C.c_void_p
         l.replay_aggregate.restype = C.c_int
         l.replay_aggregate.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
