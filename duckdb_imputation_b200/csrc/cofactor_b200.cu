@@ -79,9 +79,49 @@ const DeviceInfo &dev_info(int d) {
 struct Stage {
   char *h = nullptr;  // pinned: [col][tile_rows] x 4 B, numeric cols, cat cols, group slot
   char *d = nullptr;
+  size_t bytes = 0;
   cudaEvent_t done = nullptr;
   bool in_flight = false;
 };
+
+// Staging buffers (pinned host + device twin) are recycled across contexts: pinning memory costs
+// milliseconds, and a DuckDB query creates one state per worker thread (and per group).
+constexpr size_t kStageBytes = 16u << 20;
+struct StagePool {
+  std::mutex mu;
+  std::vector<Stage> free_list[64];
+  int acquire(int device, Stage *out) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto &fl = free_list[device & 63];
+      if (!fl.empty()) {
+        *out = fl.back();
+        fl.pop_back();
+        return CFB_OK;
+      }
+    }
+    Stage s;
+    s.bytes = kStageBytes;
+    cudaError_t e = cudaHostAlloc((void **)&s.h, s.bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s.d, s.bytes);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      if (s.h) cudaFreeHost(s.h);
+      if (s.d) cudaFree(s.d);
+      return fail(e == cudaErrorMemoryAllocation ? CFB_ERR_OOM : CFB_ERR_CUDA, "staging allocation: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return CFB_OK;
+  }
+  void release(int device, Stage &s) {
+    if (!s.h) return;
+    s.in_flight = false;
+    std::lock_guard<std::mutex> g(mu);
+    free_list[device & 63].push_back(s);
+    s = Stage{};
+  }
+};
+StagePool g_stage_pool;
 
 }  // namespace
 
@@ -296,14 +336,12 @@ size_t stage_cols(const cfb_ctx *c) { return (size_t)c->n + c->m + 1; }
 
 int ensure_staging(cfb_ctx *c) {
   if (c->tile_rows) return CFB_OK;
-  size_t rows = (16u << 20) / (4 * stage_cols(c));
-  if (const char *e = getenv("CFB_STAGE_ROWS")) rows = (size_t)std::max(1ll, atoll(e));
-  rows = std::max<size_t>(1024, (rows + 1023) / 1024 * 1024);
-  const size_t bytes = rows * 4 * stage_cols(c);
+  size_t rows = kStageBytes / (4 * stage_cols(c));
+  if (const char *e = getenv("CFB_STAGE_ROWS")) rows = std::min<size_t>(rows, (size_t)std::max(1ll, atoll(e)));
+  rows = std::max<size_t>(1024, rows / 1024 * 1024);
   for (int i = 0; i < 2; i++) {
-    CU(cudaHostAlloc((void **)&c->st[i].h, bytes, cudaHostAllocDefault));
-    CU(cudaMalloc((void **)&c->st[i].d, bytes));
-    CU(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming));
+    int rc = g_stage_pool.acquire(c->device, &c->st[i]);
+    if (rc) return rc;
   }
   c->tile_rows = rows;
   c->fill = 0;
@@ -430,11 +468,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   if (!c) return CFB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (auto &s : c->st) {
-    if (s.h) cudaFreeHost(s.h);
-    if (s.d) cudaFree(s.d);
-    if (s.done) cudaEventDestroy(s.done);
-  }
+  for (auto &s : c->st) g_stage_pool.release(c->device, s);  // the stream is drained: nothing in flight
   cudaFree(c->d_f64);
   cudaFree(c->d_u64);
   cudaFree(c->d_lay);
