@@ -180,7 +180,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from duckdb_imputation_b200 import CFB_TRIPLE, CofactorContext, synth
+    from duckdb_imputation_b200 import CFB_TRIPLE, CofactorContext, multi_gpu, synth
     from duckdb_imputation_b200 import _native as nat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,10 +227,7 @@ def main():
             ev[1].record(stream)
         if world > 1:
             # the one exchange step of the path: sum the per-GPU partial triples (fp64 sums, int64 counts)
-            ctx.export_partial(pf, pu, stream=stream.cuda_stream)
-            dist.all_reduce(pf, op=dist.ReduceOp.SUM)
-            dist.all_reduce(pu, op=dist.ReduceOp.SUM)
-            ctx.import_partial(pf, pu, stream=stream.cuda_stream)
+            multi_gpu.allreduce_context(ctx, pf, pu, stream=stream.cuda_stream)
 
     for i in range(args.warmup):
         step(i)

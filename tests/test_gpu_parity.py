@@ -224,3 +224,31 @@ def test_kernels_actually_launch():
     before = nat.lib().cfb_kernel_launches()
     sum_to_triple([np.ones(10, np.float32)] * 3, [])
     assert nat.lib().cfb_kernel_launches() > before
+
+
+def test_partial_export_matches_host_layout_and_roundtrips():
+    """The dense device state (state_layout.h) == multi_gpu.pack_dense of the finalized result; and
+    import(export(x)) is the identity.  This is the buffer the NCCL all-reduce sums."""
+    torch = pytest.importorskip("torch")
+    from duckdb_imputation_b200 import multi_gpu
+    rng = np.random.default_rng(2)
+    rows = 30_000
+    num, cat = _table(rng, rows, 3, 3, dom=9, lo=-2)
+    lo, hi = [-4, -2, -2], [8, 6, 10]
+    with CofactorContext(CFB_TRIPLE, 3, 3) as ctx, CofactorContext(CFB_TRIPLE, 3, 3) as other:
+        ctx.set_cat_domain(lo, hi)
+        other.set_cat_domain(lo, hi)
+        ctx.append(num, cat)
+        nf, nu = ctx.partial_sizes()
+        assert (nf, nu) == multi_gpu.dense_sizes(0, 3, 3, lo, hi)
+        f = torch.zeros(nf, dtype=torch.float64, device="cuda")
+        u = torch.zeros(nu, dtype=torch.int64, device="cuda")
+        ctx.export_partial(f, u)
+        arrays = ctx.finalize_arrays()
+        pf, pu = multi_gpu.pack_dense(arrays, lo, hi)
+        assert np.array_equal(u.cpu().numpy(), pu)
+        np.testing.assert_allclose(f.cpu().numpy(), pf, rtol=0, atol=0)
+        other.import_partial(f * 2, u * 2)  # what a 2-rank all-reduce of identical slices would give
+        twice = other.finalize_arrays()
+    assert twice["N"] == 2 * rows and np.array_equal(twice["cat_counts"], 2 * arrays["cat_counts"])
+    np.testing.assert_allclose(twice["quad"], 2 * arrays["quad"], rtol=1e-15)
