@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 
 #include "gram_launch.h"
+#include "slab_kernels.cuh"
+#include "slab_launch.h"
 #include "scatter_kernels.cuh"
 #include "state_layout.h"
 
@@ -136,6 +138,10 @@ struct cfb_ctx {
   int *d_minmax = nullptr;  // [2][kMaxCat]
   cudaStream_t stream = nullptr;
   cudaStream_t user_stream = nullptr;  // last caller-provided stream of cfb_triple_device
+  // per-CTA fp32 slabs of slab_scan_kernel (all zero between launches)
+  float *d_slab = nullptr;
+  long long slab_floats = 0;  // per CTA
+  int slab_grid = 0;
   // Gram scratch
   double *d_partials = nullptr;
   unsigned int *d_ticket = nullptr;
@@ -261,6 +267,14 @@ constexpr std::array<cudaError_t (*)(const cfb::GramLaunchParams &), sizeof...(N
 const auto kGramTriple = gram_table<false>(std::make_integer_sequence<int, CFB_MAX_NUM>{});
 const auto kGramNb = gram_table<true>(std::make_integer_sequence<int, CFB_MAX_NUM>{});
 
+template <int KIND, int... Ns>
+constexpr std::array<cudaError_t (*)(const cfb::SlabLaunchParams &), sizeof...(Ns)> slab_table(
+    std::integer_sequence<int, Ns...>) {
+  return {{cfb::slab_launch<Ns, KIND>...}};
+}
+const auto kSlabTriple = slab_table<0>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+const auto kSlabNb = slab_table<1>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -282,6 +296,50 @@ int launch_gram(cfb_ctx *c, const float *const *cols, unsigned long long rows, c
   const cudaError_t e = (c->kind == CFB_NB ? kGramNb : kGramTriple)[c->n - 1](p);
   g_launches++;
   if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "Gram kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+// Categorical / GROUP BY scan through the per-CTA fp32 slabs.  Returns 1 if the slab would be
+// too large (caller falls back to generic_scan_kernel), 0 on success, <0 on error.
+constexpr long long kMaxSlabBytesPerCta = 8ll << 20, kMaxSlabBytesTotal = 512ll << 20;
+
+int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, int do_numeric, cudaStream_t s) {
+  const cfb::SlabShape sh = cfb::slab_shape(c->lay, do_numeric);
+  const long long bytes = sh.floats * 4;
+  if (bytes > kMaxSlabBytesPerCta || getenv("CFB_NO_SLAB")) return 1;
+  int grid = dev_info(c->device).sms * 2;
+  grid = (int)std::min<long long>(grid, std::max<long long>(1, kMaxSlabBytesTotal / std::max<long long>(bytes, 1)));
+  grid = (int)std::min<unsigned long long>(grid, (rows + cfb::kSlabTile - 1) / cfb::kSlabTile);
+  grid = std::max(grid, 1);
+  if (sh.floats != c->slab_floats || grid > c->slab_grid) {
+    if (c->d_slab) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
+      cudaFree(c->d_slab);
+      c->d_slab = nullptr;
+    }
+    const int alloc_grid = std::max(grid, c->slab_grid);
+    CU(cudaMalloc(&c->d_slab, (size_t)std::max<long long>(16, bytes * alloc_grid)));
+    CU(cudaMemsetAsync(c->d_slab, 0, (size_t)std::max<long long>(16, bytes * alloc_grid), s));
+    c->slab_floats = sh.floats;
+    c->slab_grid = alloc_grid;
+  }
+  cfb::SlabLaunchParams p{};
+  p.cols = sc;
+  p.d_lay = c->d_lay;
+  p.rows = rows;
+  p.do_numeric = do_numeric;
+  // an fp32 slab entry is folded into fp64 after at most ~32K rows of one CTA
+  p.flush_tiles = std::max(1, env_int("CFB_SLAB_FLUSH_TILES", 32));
+  p.slab = c->d_slab;
+  p.f64 = c->d_f64;
+  p.u64 = c->d_u64;
+  p.err = c->d_err;
+  p.grid = grid;
+  p.stream = s;
+  const cudaError_t e = (c->kind == CFB_NB ? kSlabNb : kSlabTriple)[c->n](p);
+  g_launches++;
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "slab kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
   return CFB_OK;
 }
 
@@ -308,7 +366,13 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
     g_launches++;
   }
-  if (grouped || c->m > 0) {
+  int need_generic = (grouped || c->m > 0) ? 1 : 0;
+  if (need_generic) {
+    const int rc = launch_slab(c, sc, rows, grouped ? 1 : 0, s);
+    if (rc < 0) return rc;
+    need_generic = rc;  // 1 = slab too large for this shape
+  }
+  if (need_generic) {
     const int blocks = (int)std::min<unsigned long long>((rows + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
     cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(sc, c->d_lay, rows, grouped ? 1 : 0, c->d_f64,
                                                                  c->d_u64, c->d_err);
@@ -476,6 +540,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_minmax);
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
+  cudaFree(c->d_slab);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);

@@ -13,12 +13,6 @@
 
 namespace cfb {
 
-struct ScanCols {
-  const float *num[32];
-  const int32_t *cat[32];
-  const int32_t *group;  // per-row slot or nullptr
-};
-
 __device__ __forceinline__ void add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------------------

@@ -27,4 +27,11 @@ struct Layout {
   long long pair_off[kMaxCat * kMaxCat];  // [k*m + l], k < l, relative to pair_base
 };
 
+// Device column pointers of one scan (SoA input).
+struct ScanCols {
+  const float *num[32];
+  const int32_t *cat[32];
+  const int32_t *group;  // per-row GROUP BY slot or nullptr
+};
+
 }  // namespace cfb
