@@ -50,6 +50,7 @@ SIGNATURES = {
     "cfb_ctx_destroy": (C.c_int, [_P]),
     "cfb_ctx_set_cat_domain": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cfb_ctx_append": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t]),
+    "cfb_ctx_append_triples": (C.c_int, [_P, C.c_size_t] + [_P] * 13),
     "cfb_triple_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "cfb_ctx_sync": (C.c_int, [_P]),
     "cfb_ctx_combine": (C.c_int, [_P, _P]),

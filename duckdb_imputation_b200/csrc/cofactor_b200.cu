@@ -612,6 +612,97 @@ int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *con
   return CFB_OK;
 }
 
+int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const float *lin, const float *quad,
+                           const cfb_list_entry *lin_cat_lists, const int32_t *lc_key, const float *lc_val,
+                           const cfb_list_entry *num_cat_lists, const int32_t *nc_key, const float *nc_val,
+                           const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
+                           const float *cc_val) {
+  if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (count == 0) return CFB_OK;
+  const int n = c->n, m = c->m;
+  const size_t nq = (size_t)c->lay.nq;
+  if (!N || (n && (!lin || !quad)) || (m && !lin_cat_lists)) return fail(CFB_ERR_INVALID, "NULL child array");
+  if (c->kind == CFB_TRIPLE && m && (!cat_cat_lists || (n && !num_cat_lists)))
+    return fail(CFB_ERR_INVALID, "NULL categorical child array");
+  CU(cudaSetDevice(c->device));
+  int rc = flush_tile(c);  // keep the order of updates on the context stream
+  if (rc) return rc;
+  // sparse entries -> tagged records (host: a few entries per lifted row), key ranges for the domain
+  std::vector<cfb::LiftedEntry> ent;
+  int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+  for (int k = 0; k < m; k++) {
+    lo[k] = INT_MAX;
+    hi[k] = INT_MIN;
+  }
+  auto see = [&](int col, int key) {
+    lo[col] = std::min(lo[col], key);
+    hi[col] = std::max(hi[col], key);
+  };
+  for (size_t r = 0; r < count; r++) {
+    for (int k = 0; k < m; k++) {
+      const cfb_list_entry le = lin_cat_lists[r * m + k];
+      for (uint64_t t = le.offset; t < le.offset + le.length; t++) {
+        ent.push_back({k, lc_key[t], 0, lc_val[t]});
+        see(k, lc_key[t]);
+      }
+    }
+    if (c->kind != CFB_TRIPLE) continue;
+    for (int l = 0; l < n; l++)
+      for (int k = 0; k < m; k++) {
+        const cfb_list_entry le = num_cat_lists[(r * n + l) * m + k];
+        for (uint64_t t = le.offset; t < le.offset + le.length; t++) {
+          ent.push_back({64 + l * 32 + k, nc_key[t], 0, nc_val[t]});
+          see(k, nc_key[t]);
+        }
+      }
+    size_t p = 0;
+    for (int k = 0; k < m; k++)
+      for (int l = k; l < m; l++, p++) {
+        if (k == l) continue;  // diagonal pair lists repeat lin_cat; the state derives them
+        const cfb_list_entry le = cat_cat_lists[r * ((size_t)m * (m + 1) / 2) + p];
+        for (uint64_t t = le.offset; t < le.offset + le.length; t++) {
+          ent.push_back({2048 + k * 32 + l, cc_key1[t], cc_key2[t], cc_val[t]});
+          see(k, cc_key1[t]);
+          see(l, cc_key2[t]);
+        }
+      }
+  }
+  if (m > 0 && !c->user_domain && !ent.empty()) {
+    for (int k = 0; k < m; k++)
+      if (lo[k] > hi[k]) lo[k] = hi[k] = c->lay.has_domain ? c->lay.lo[k] : 0;
+    rc = ensure_domain(c, lo, hi);
+    if (rc) return rc;
+  }
+  // device scratch: N | lin | quad | entries
+  const size_t bN = count * 4, bL = count * n * 4, bQ = count * nq * 4, bE = ent.size() * sizeof(cfb::LiftedEntry);
+  auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  char *d = nullptr;
+  CU(cudaMalloc((void **)&d, std::max<size_t>(16, up16(bN) + up16(bL) + up16(bQ) + up16(bE))));
+  char *dN = d, *dL = dN + up16(bN), *dQ = dL + up16(bL), *dE = dQ + up16(bQ);
+  cudaStream_t s = c->stream;
+  CU(cudaMemcpyAsync(dN, N, bN, cudaMemcpyHostToDevice, s));
+  if (bL) CU(cudaMemcpyAsync(dL, lin, bL, cudaMemcpyHostToDevice, s));
+  if (bQ) CU(cudaMemcpyAsync(dQ, quad, bQ, cudaMemcpyHostToDevice, s));
+  if (bE) CU(cudaMemcpyAsync(dE, ent.data(), bE, cudaMemcpyHostToDevice, s));
+  cfb::lifted_count_kernel<<<1, 256, 0, s>>>((const int32_t *)dN, count, c->d_u64);
+  g_launches++;
+  if (n) {
+    cfb::lifted_colsum_kernel<<<std::min(n, 64), 256, 0, s>>>((const float *)dL, count, n, c->d_f64);
+    cfb::lifted_colsum_kernel<<<(int)std::min<size_t>(nq, 128), 256, 0, s>>>((const float *)dQ, count, (int)nq, c->d_f64 + n);
+    g_launches += 2;
+  }
+  if (bE) {
+    const int blocks = (int)std::min<size_t>((ent.size() + 255) / 256, (size_t)dev_info(c->device).sms * 4);
+    cfb::lifted_scatter_kernel<<<blocks, 256, 0, s>>>((const cfb::LiftedEntry *)dE, ent.size(), c->d_lay, c->d_f64,
+                                                     c->d_u64, c->d_err);
+    g_launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s));  // the host arrays (DuckDB vectors, `ent`) go away after this call
+  cudaFree(d);
+  return CFB_OK;
+}
+
 int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                       const int32_t *d_group_slot, size_t n_rows, void *stream) {
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");

@@ -363,16 +363,55 @@ class AggregateFunction {
   }
 };
 
+// ---- scalar functions (to_cofactor / to_nb_agg)
+class DataChunk {
+ public:
+  vector<Vector> data;
+  idx_t size() const { return count; }
+  void SetCardinality(idx_t c) { count = c; }
+  idx_t ColumnCount() const { return data.size(); }
+
+ private:
+  idx_t count = 0;
+};
+struct ExpressionState {};
+class ScalarFunction;
+typedef void (*scalar_function_t)(DataChunk &args, ExpressionState &state, Vector &result);
+typedef unique_ptr<FunctionData> (*bind_scalar_function_t)(ClientContext &, ScalarFunction &, vector<unique_ptr<Expression>> &);
+class ScalarFunction {
+ public:
+  ScalarFunction(string name_p, vector<LogicalType> arguments_p, LogicalType return_type_p, scalar_function_t function_p,
+                 bind_scalar_function_t bind_p = nullptr, void *dependency = nullptr, void *statistics = nullptr)
+      : name(std::move(name_p)), arguments(std::move(arguments_p)), return_type(std::move(return_type_p)),
+        function(function_p), bind(bind_p) {
+    (void)dependency;
+    (void)statistics;
+  }
+  string name;
+  vector<LogicalType> arguments;
+  LogicalType return_type;
+  LogicalType varargs;
+  FunctionNullHandling null_handling = FunctionNullHandling::DEFAULT_NULL_HANDLING;
+  scalar_function_t function;
+  bind_scalar_function_t bind;
+};
+
 // The catalog an extension registers into (ExtensionUtil::RegisterFunction).
 class DatabaseInstance {
  public:
   std::map<string, AggregateFunction> aggregates;
+  std::map<string, ScalarFunction> scalars;
 };
 struct ExtensionUtil {
   static void RegisterFunction(DatabaseInstance &db, AggregateFunction f) {
     const string name = f.name;
     db.aggregates.erase(name);
     db.aggregates.emplace(name, std::move(f));
+  }
+  static void RegisterFunction(DatabaseInstance &db, ScalarFunction f) {
+    const string name = f.name;
+    db.scalars.erase(name);
+    db.scalars.emplace(name, std::move(f));
   }
 };
 

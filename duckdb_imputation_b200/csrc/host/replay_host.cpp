@@ -88,7 +88,82 @@ char *replay_list_functions(void) {
   return strdup(s.c_str());
 }
 
-int replay_aggregate(const char *function, int n_num, int n_cat, const float *const *num,
+namespace {
+// bind + evaluate a registered scalar function on one chunk
+struct BoundScalar {
+  duckdb::ScalarFunction fun;
+  duckdb::unique_ptr<duckdb::FunctionData> bind_data;
+};
+std::unique_ptr<BoundScalar> BindScalar(const char *name, int n_num, int n_cat) {
+  using namespace duckdb;
+  auto it = Catalog().scalars.find(name);
+  if (it == Catalog().scalars.end())
+    throw InvalidInputException(std::string("Catalog Error: scalar function ") + name + " does not exist");
+  std::unique_ptr<BoundScalar> bp(new BoundScalar{it->second, nullptr});
+  BoundScalar &b = *bp;
+  ClientContext context;
+  vector<unique_ptr<Expression>> args;
+  for (int k = 0; k < n_num + n_cat; k++) {
+    args.push_back(make_uniq<Expression>());
+    args.back()->return_type = k < n_num ? LogicalType::FLOAT : LogicalType::INTEGER;
+  }
+  if (b.fun.bind) b.bind_data = b.fun.bind(context, b.fun, args);
+  return bp;
+}
+void FillChunk(duckdb::DataChunk &chunk, int n_num, int n_cat, const float *const *num, const int32_t *const *cat,
+               size_t lo, duckdb::sel_t *rel, idx_t count) {
+  using namespace duckdb;
+  chunk.data.clear();
+  for (int k = 0; k < n_num; k++) chunk.data.emplace_back(LogicalType::FLOAT, (data_ptr_t)(num[k] + lo));
+  for (int k = 0; k < n_cat; k++) chunk.data.emplace_back(LogicalType::INTEGER, (data_ptr_t)(cat[k] + lo));
+  if (rel)
+    for (auto &v : chunk.data) v.Slice(SelectionVector(rel));
+  chunk.SetCardinality(count);
+}
+}  // namespace
+
+int replay_scalar(const char *scalar, int n_num, int n_cat, const float *const *num, const int32_t *const *cat,
+                  const uint32_t *sel, size_t n_sel, size_t rows, char **json_out) {
+  using namespace duckdb;
+  try {
+    if (!scalar || !json_out) throw InvalidInputException("bad arguments");
+    *json_out = nullptr;
+    auto bp = BindScalar(scalar, n_num, n_cat);
+    BoundScalar &b = *bp;
+    std::ostringstream os;
+    os << "[";
+    bool first = true;
+    std::vector<sel_t> rel(STANDARD_VECTOR_SIZE);
+    size_t s_pos = 0;
+    for (size_t lo = 0; lo < rows; lo += STANDARD_VECTOR_SIZE) {
+      const size_t hi = std::min(rows, lo + STANDARD_VECTOR_SIZE);
+      idx_t count = hi - lo;
+      if (sel) {
+        count = 0;
+        while (s_pos < n_sel && sel[s_pos] < hi) rel[count++] = (sel_t)(sel[s_pos++] - lo);
+        if (!count) continue;
+      }
+      DataChunk chunk;
+      FillChunk(chunk, n_num, n_cat, num, cat, lo, sel ? rel.data() : nullptr, count);
+      ExpressionState state;
+      Vector result(b.fun.return_type, count);
+      b.fun.function(chunk, state, result);
+      for (idx_t r = 0; r < count; r++) {
+        if (!first) os << ", ";
+        first = false;
+        RenderValue(result, r, os);
+      }
+    }
+    os << "]";
+    *json_out = strdup(os.str().c_str());
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+int replay_aggregate(const char *function, const char *scalar, int n_num, int n_cat, const float *const *num,
                      const int32_t *const *cat, const int32_t *group, int n_groups, const uint32_t *sel,
                      size_t n_sel, size_t rows, int threads, char **json_out, double *seconds) {
   using namespace duckdb;
@@ -100,8 +175,11 @@ int replay_aggregate(const char *function, int n_num, int n_cat, const float *co
       throw InvalidInputException(std::string("Catalog Error: aggregate function ") + function + " does not exist");
     AggregateFunction fun = it->second;  // bind mutates its copy (return_type)
     const int n_cols = n_num + n_cat;
-    if ((size_t)n_cols != fun.arguments.size() && fun.varargs.id() == LogicalTypeId::INVALID)
+    const bool lifted = scalar && *scalar;
+    if (!lifted && (size_t)n_cols != fun.arguments.size() && fun.varargs.id() == LogicalTypeId::INVALID)
       throw InvalidInputException("argument count does not match the function signature");
+    std::unique_ptr<BoundScalar> lift;
+    if (lifted) lift = BindScalar(scalar, n_num, n_cat);
     ClientContext context;
     vector<unique_ptr<Expression>> args;
     unique_ptr<FunctionData> bind_data;
@@ -149,14 +227,18 @@ int replay_aggregate(const char *function, int n_num, int n_cat, const float *co
             ptrs[r] = st;
           }
           // scan vectors over the table's column storage (+ the filter's selection on top)
-          std::vector<Vector> inputs;
-          inputs.reserve(n_cols);
-          for (int k = 0; k < n_num; k++) inputs.emplace_back(LogicalType::FLOAT, (data_ptr_t)(num[k] + lo));
-          for (int k = 0; k < n_cat; k++) inputs.emplace_back(LogicalType::INTEGER, (data_ptr_t)(cat[k] + lo));
-          if (sel)
-            for (auto &v : inputs) v.Slice(SelectionVector(rel.data()));
+          DataChunk chunk;
+          FillChunk(chunk, n_num, n_cat, num, cat, lo, sel ? rel.data() : nullptr, count);
           Vector state_vector(LogicalType::POINTER, (data_ptr_t)ptrs.data());
-          fun.update(inputs.data(), aggr, (idx_t)n_cols, state_vector, count);
+          if (lifted) {
+            ExpressionState estate;
+            std::vector<Vector> one;
+            one.emplace_back(lift->fun.return_type, count);
+            lift->fun.function(chunk, estate, one[0]);
+            fun.update(one.data(), aggr, 1, state_vector, count);
+          } else {
+            fun.update(chunk.data.data(), aggr, (idx_t)n_cols, state_vector, count);
+          }
         }
       } catch (std::exception &e) {
         std::lock_guard<std::mutex> g(err_mu);

@@ -21,6 +21,9 @@ extern "C" {
 #endif
 
 /* Run  SELECT <function>(num..., cat...) FROM t [WHERE row in sel] [GROUP BY group]
+ *  or   SELECT <function>(<scalar>(num..., cat...)) FROM t ...   when `scalar` is not NULL/empty
+ *       (e.g. sum_triple(to_cofactor(...)): the scalar function is evaluated chunk by chunk and its
+ *       result vector is the aggregate's single input)
  *   function   registered name, e.g. "sum_to_triple_3_3"
  *   group      per-row group slot in [0, n_groups) or NULL; results come back in slot order,
  *              slots without rows are omitted
@@ -29,9 +32,12 @@ extern "C" {
  *   json_out   malloc'd JSON array with one STRUCT per group (free with replay_free)
  *   seconds    wall time of update + combine + finalize
  * Returns 0, or -1 with the message in replay_last_error().                             */
-int replay_aggregate(const char *function, int n_num, int n_cat, const float *const *num,
+int replay_aggregate(const char *function, const char *scalar, int n_num, int n_cat, const float *const *num,
                      const int32_t *const *cat, const int32_t *group, int n_groups, const uint32_t *sel,
                      size_t n_sel, size_t rows, int threads, char **json_out, double *seconds);
+/* Run  SELECT <scalar>(num..., cat...) FROM t [WHERE row in sel]  -> JSON array, one value per row. */
+int replay_scalar(const char *scalar, int n_num, int n_cat, const float *const *num, const int32_t *const *cat,
+                  const uint32_t *sel, size_t n_sel, size_t rows, char **json_out);
 void replay_free(char *p);
 const char *replay_last_error(void);
 /* Names of all registered aggregate functions, '\n'-separated (malloc'd). */

@@ -17,6 +17,29 @@ const char *Implementation() { return "b200"; }
 
 void Load(duckdb::DatabaseInstance &instance) {
   using namespace duckdb;
+  // sum_triple(ANY) / sum_nb_agg(ANY): aggregates over lifted triples (ext.cpp:50-55, :118-123)
+  AggregateFunction sum_triple("sum_triple", {LogicalType::ANY}, LogicalTypeId::STRUCT,
+                               AggregateFunction::StateSize<Triple::SumState>,
+                               AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>, Triple::Sum,
+                               Triple::SumStateCombine, Triple::SumStateFinalize, nullptr, Triple::SumBind,
+                               AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
+  ExtensionUtil::RegisterFunction(instance, sum_triple);
+  AggregateFunction sum_nb("sum_nb_agg", {LogicalType::ANY}, LogicalTypeId::STRUCT,
+                           AggregateFunction::StateSize<Triple::SumState>,
+                           AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>, Triple::sum_nb_agg,
+                           Triple::SumStateCombine, Triple::SumStateFinalize, nullptr, Triple::sum_nb_agg_bind,
+                           AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
+  ExtensionUtil::RegisterFunction(instance, sum_nb);
+  // to_cofactor(ANY...) / to_nb_agg(ANY...): varargs scalar lifts (ext.cpp:58-64, :126-131)
+  ScalarFunction to_cofactor("to_cofactor", {}, LogicalTypeId::STRUCT, Triple::CustomLift, Triple::CustomLiftBind, nullptr, nullptr);
+  to_cofactor.varargs = LogicalType::ANY;
+  to_cofactor.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, to_cofactor);
+  ScalarFunction to_nb_agg("to_nb_agg", {}, LogicalTypeId::STRUCT, Triple::to_nb_lift, Triple::to_nb_lift_bind, nullptr);
+  to_nb_agg.varargs = LogicalType::ANY;
+  to_nb_agg.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, to_nb_agg);
+
   constexpr int kMaxCols = 20;
   for (int i = 0; i <= kMaxCols; i++)
     for (int j = 0; j <= kMaxCols; j++) {

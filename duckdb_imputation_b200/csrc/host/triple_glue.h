@@ -36,6 +36,22 @@ duckdb::unique_ptr<duckdb::FunctionData> sum_to_nb_agg_bind(duckdb::ClientContex
 void sum_to_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, duckdb::idx_t cols,
                    duckdb::Vector &state_vector, duckdb::idx_t count);
 
+// sum_triple / sum_nb_agg over lifted triples (sum.h, sum_nb_agg.h) and the lifts (lift.h, lift_to_nb_agg.h)
+duckdb::unique_ptr<duckdb::FunctionData> SumBind(duckdb::ClientContext &context, duckdb::AggregateFunction &function,
+                                                 duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void Sum(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+         duckdb::Vector &state_vector, idx_t count);
+duckdb::unique_ptr<duckdb::FunctionData> sum_nb_agg_bind(duckdb::ClientContext &context, duckdb::AggregateFunction &function,
+                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void sum_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+                duckdb::Vector &state_vector, idx_t count);
+void CustomLift(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> CustomLiftBind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void to_nb_lift(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> to_nb_lift_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+
 void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::AggregateInputData &aggr_input_data, idx_t count);
 void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &aggr_input_data, duckdb::Vector &result,
                       idx_t count, idx_t offset);

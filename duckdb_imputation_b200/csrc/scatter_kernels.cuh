@@ -177,6 +177,89 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------
+// sum_triple / sum_nb_agg (sum.cpp:86-149): column sums of `rows` lifted triples laid out
+// row-major [rows][width] (width = n for lin, nq for quad), added into state[0..width).
+// One block per group of columns; fp64 accumulation.
+__global__ void __launch_bounds__(256)
+    lifted_colsum_kernel(const float *__restrict__ x, unsigned long long rows, int width, double *__restrict__ state) {
+  for (int col = blockIdx.x; col < width; col += gridDim.x) {
+    double acc = 0.0;
+    for (unsigned long long r = threadIdx.x; r < rows; r += blockDim.x) acc += (double)x[r * width + col];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; w++) t += part[w];
+      state[col] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// N += sum of the lifted rows' N (sum.cpp:86-89)
+__global__ void __launch_bounds__(256) lifted_count_kernel(const int32_t *__restrict__ n, unsigned long long rows,
+                                                           unsigned long long *__restrict__ u64) {
+  long long acc = 0;
+  for (unsigned long long r = threadIdx.x; r < rows; r += blockDim.x) acc += n[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(u64, (unsigned long long)acc);
+}
+
+// Sparse entries of lifted triples (sum.cpp:197-260): tag selects the table
+//   tag = c                      lin_cat   of categorical column c:        counts[key1] += value
+//   tag = 64 + l*32 + c          num_cat   of numeric l, categorical c:    numcat[l][key1] += value
+//   tag = 2048 + k*32 + l (k<l)  cat_cat   of the pair (k,l):              pairs[key1][key2] += value
+struct LiftedEntry {
+  int32_t tag, key1, key2;
+  float value;
+};
+__global__ void __launch_bounds__(256)
+    lifted_scatter_kernel(const LiftedEntry *__restrict__ e, unsigned long long n_entries, const Layout *__restrict__ lay_g,
+                          double *__restrict__ f64, unsigned long long *__restrict__ u64, int *__restrict__ err) {
+  __shared__ Layout lay;
+  {
+    const int *src = reinterpret_cast<const int *>(lay_g);
+    int *dst = reinterpret_cast<int *>(&lay);
+    for (int i = threadIdx.x; i < (int)(sizeof(Layout) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int m = lay.m;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const LiftedEntry x = e[i];
+    if (x.tag < 64) {
+      const int c = x.tag;
+      const long long s = (long long)x.key1 - lay.lo[c];
+      if (c >= m || s < 0 || s >= lay.dom[c]) {
+        atomicExch(err, 1);
+        continue;
+      }
+      atomicAdd(u64 + 1 + lay.cat_off[c] + s, (unsigned long long)llrintf(x.value));
+    } else if (x.tag < 2048) {
+      const int l = (x.tag - 64) / 32, c = (x.tag - 64) % 32;
+      const long long s = (long long)x.key1 - lay.lo[c];
+      if (c >= m || l >= lay.n || s < 0 || s >= lay.dom[c]) {
+        atomicExch(err, 1);
+        continue;
+      }
+      atomicAdd(f64 + lay.numcat_base + (long long)l * lay.total_dom + lay.cat_off[c] + s, (double)x.value);
+    } else {
+      const int k = (x.tag - 2048) / 32, l = (x.tag - 2048) % 32;
+      const long long sk = (long long)x.key1 - lay.lo[k], sl = (long long)x.key2 - lay.lo[l];
+      if (k >= l || l >= m || sk < 0 || sk >= lay.dom[k] || sl < 0 || sl >= lay.dom[l]) {
+        atomicExch(err, 1);
+        continue;
+      }
+      atomicAdd(u64 + lay.pair_base + lay.pair_off[k * m + l] + sk * lay.dom[l] + sl, (unsigned long long)llrintf(x.value));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Synthetic columns for tests and bench (counter-based, so the host can regenerate any
 // slice bit-for-bit: see duckdb_imputation_b200/synth.py).
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {

@@ -34,8 +34,11 @@ class Replay:
         l = C.CDLL(path, mode=C.RTLD_LOCAL)
         P = C.c_void_p
         l.replay_aggregate.restype = C.c_int
-        l.replay_aggregate.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
+        l.replay_aggregate.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_int, P,
                                        C.c_size_t, C.c_size_t, C.c_int, C.POINTER(P), C.POINTER(C.c_double)]
+        l.replay_scalar.restype = C.c_int
+        l.replay_scalar.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_size_t, C.c_size_t,
+                                    C.POINTER(P)]
         l.replay_free.argtypes = [P]
         l.replay_last_error.restype = C.c_char_p
         l.replay_list_functions.restype = P
@@ -54,8 +57,9 @@ class Replay:
         finally:
             self.lib.replay_free(p)
 
-    def aggregate(self, function: str, num_cols, cat_cols, group=None, n_groups=1, sel=None, threads=1):
-        """Raw call: group = int32 slots; sel = ascending uint32 row ids.  -> list of STRUCT dicts."""
+    def aggregate(self, function: str, num_cols, cat_cols, group=None, n_groups=1, sel=None, threads=1, scalar=None):
+        """Raw call: group = int32 slots; sel = ascending uint32 row ids; scalar = name of a lift to apply
+        first (sum_triple(to_cofactor(..))).  -> list of STRUCT dicts."""
         kn = [np.ascontiguousarray(c, np.float32) for c in num_cols]
         kc = [np.ascontiguousarray(c, np.int32) for c in cat_cols]
         rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
@@ -63,7 +67,7 @@ class Replay:
         s = None if sel is None else np.ascontiguousarray(sel, np.uint32)
         out = C.c_void_p()
         secs = C.c_double()
-        rc = self.lib.replay_aggregate(function.encode(), len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
+        rc = self.lib.replay_aggregate(function.encode(), (scalar or "").encode(), len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
                                        ptr_array([k.ctypes.data for k in kc]), None if g is None else g.ctypes.data,
                                        n_groups, None if s is None else s.ctypes.data, 0 if s is None else len(s), rows,
                                        threads, C.byref(out), C.byref(secs))
@@ -75,16 +79,38 @@ class Replay:
         finally:
             self.lib.replay_free(out)
 
-    def query(self, kind, num_cols, cat_cols, group_by=None, where=None, threads=1):
-        """Same signature as oracle.aggregate / aggregates._aggregate (tests/sqlmini.py backend)."""
+    def scalar(self, function: str, num_cols, cat_cols, where=None):
+        """SELECT function(cols) FROM t [WHERE ..] -> one value per (selected) row."""
+        kn = [np.ascontiguousarray(c, np.float32) for c in num_cols]
+        kc = [np.ascontiguousarray(c, np.int32) for c in cat_cols]
+        rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
+        s = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
+        out = C.c_void_p()
+        rc = self.lib.replay_scalar(function.encode(), len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
+                                    ptr_array([k.ctypes.data for k in kc]), None if s is None else s.ctypes.data,
+                                    0 if s is None else len(s), rows, C.byref(out))
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            return json.loads(C.string_at(out).decode())
+        finally:
+            self.lib.replay_free(out)
+
+    def query(self, kind, num_cols, cat_cols, group_by=None, where=None, threads=1, lifted=False):
+        """Same signature as oracle.aggregate / aggregates._aggregate (tests/sqlmini.py backend).
+        lifted=True runs sum_triple(to_cofactor(..)) / sum_nb_agg(to_nb_agg(..)) instead."""
         fn = ("sum_to_triple_%d_%d" if kind == 0 else "sum_to_nb_agg_%d_%d") % (len(num_cols), len(cat_cols))
+        scalar = None
+        if lifted:
+            fn, scalar = ("sum_triple", "to_cofactor") if kind == 0 else ("sum_nb_agg", "to_nb_agg")
         sel = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
         if group_by is None:
-            return self.aggregate(fn, num_cols, cat_cols, sel=sel, threads=threads)[0]
+            return self.aggregate(fn, num_cols, cat_cols, sel=sel, threads=threads, scalar=scalar)[0]
         gb = np.asarray(group_by)
         labels = np.unique(gb)
         slots = np.searchsorted(labels, gb).astype(np.int32)
-        return self.aggregate(fn, num_cols, cat_cols, group=slots, n_groups=max(1, len(labels)), sel=sel, threads=threads)
+        return self.aggregate(fn, num_cols, cat_cols, group=slots, n_groups=max(1, len(labels)), sel=sel, threads=threads,
+                              scalar=scalar)
 
 
 _glue = None

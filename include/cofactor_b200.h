@@ -107,6 +107,29 @@ int cfb_ctx_append(cfb_ctx *ctx, const float *const *num_cols, const uint32_t *c
 int cfb_triple_device(cfb_ctx *ctx, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                       const int32_t *d_group_slot, size_t n_rows, void *stream);
 
+/* One (offset,length) range into a flattened list child -- DuckDB's list_entry_t. */
+typedef struct cfb_list_entry {
+  uint64_t offset;
+  uint64_t length;
+} cfb_list_entry;
+
+/* Replaces the per-chunk body of Triple::Sum (sum.cpp:57-261) and Triple::sum_nb_agg
+ * (sum_nb_agg.cpp:45-175): add `count` ALREADY-LIFTED triples (rows of to_cofactor /
+ * multiply_triple output) to the state.  Arguments are the flattened children of the input
+ * STRUCT vector, exactly as DuckDB lays them out:
+ *   N[count]                                  child 0
+ *   lin[count*n], quad[count*nq]              list children 1, 2 (nq = n(n+1)/2, or n for CFB_NB)
+ *   lin_cat lists   [count*m]      -> (lc_key, lc_val)      value = count of key
+ *   num_cat lists   [count*n*m]    -> (nc_key, nc_val)      list (r*n + l)*m + c, value = sum x_l | key
+ *   cat_cat lists   [count*m(m+1)/2] -> (cc_key1, cc_key2, cc_val)   (k<=l) order, diagonal included
+ * The numeric children are summed on the device; the sparse (key,value) entries are
+ * scatter-added into the dense device tables.  num_cat / cat_cat are NULL for CFB_NB.   */
+int cfb_ctx_append_triples(cfb_ctx *ctx, size_t count, const int32_t *N, const float *lin, const float *quad,
+                           const cfb_list_entry *lin_cat_lists, const int32_t *lc_key, const float *lc_val,
+                           const cfb_list_entry *num_cat_lists, const int32_t *nc_key, const float *nc_val,
+                           const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
+                           const float *cc_val);
+
 /* Drain the context's streams; surfaces asynchronous kernel errors. */
 int cfb_ctx_sync(cfb_ctx *ctx);
 

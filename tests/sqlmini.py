@@ -44,3 +44,20 @@ def run_sum(sql, fixture, backend):
     if q["having"] is not None:
         return [r for r, l in zip(res, labels) if l == q["having"]]
     return res
+
+
+def run_lift(sql, fixture, scalar_backend):
+    """Execute a to_cofactor / to_nb_agg statement -> list of per-row STRUCTs.
+    scalar_backend(function_name, num_cols, cat_cols, where=None)."""
+    q = parse(sql)
+    cols, types = table(fixture)
+    num, cat = [], []
+    for a in q["args"]:
+        if "+" in a:  # expression argument, e.g. a+b+c (test_lift.py:58-63): a FLOAT column
+            num.append(sum(cols[t.strip()] for t in a.split("+")).astype(np.float32))
+        elif types[a] == "FLOAT":
+            num.append(cols[a])
+        else:
+            cat.append(cols[a])
+    where = None if q["where"] is None else (cols["gb"] == q["where"])
+    return scalar_backend(q["fn"], num, cat, where=where)

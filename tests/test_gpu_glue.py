@@ -58,3 +58,34 @@ def test_group_by_and_where_through_callbacks():
 def test_unknown_function_is_a_query_error():
     with pytest.raises(replay.ReplayError, match="does not exist"):
         replay.glue().aggregate("sum_to_triple_21_0", [np.zeros(4, np.float32)] * 21, [])
+
+
+def test_sum_of_lifted_equals_sum_goldens(goldens):
+    """test_sum.py:40-52 / test_nb_sum.py: sum_to_triple(..) == sum_triple(to_cofactor(..)), grouped and
+    with HAVING -- here additionally pinned to the golden STRUCTs themselves."""
+    g = replay.glue()
+    cases = [c for c in goldens["cases"] if c["file"] in ("test_sum.py", "test_nb_sum.py")]
+    for c in cases:
+        fx = goldens["fixtures"][c["file"]]
+        direct = sqlmini.run_sum(c["sql"], fx, g.query)
+        lifted = sqlmini.run_sum(c["sql"], fx, lambda *a, **k: g.query(*a, lifted=True, **k))
+        assert direct == lifted
+        assert lifted[c["index"]] == c["expected"], (c["file"], c["test"], c["index"])
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_sum_of_lifted_matches_oracle(kind):
+    rng = np.random.default_rng(8)
+    rows = 20_000
+    num = [rng.random(rows).astype(np.float32) for _ in range(5)]
+    cat = [rng.integers(-3, 12, rows).astype(np.int32) for _ in range(3)]
+    gb = rng.integers(0, 4, rows)
+    got = replay.glue().query(kind, num, cat, group_by=gb, threads=3, lifted=True)
+    ref = oracle.aggregate(kind, num, cat, group_by=gb)
+    for a, b in zip(got, ref):
+        assert_struct_parity(a, b, what=f"lifted kind {kind}")
+    # and the oracle's own restatement of sum(lift(..)) (fp32, like the reference) agrees
+    labels, slots = np.unique(gb, return_inverse=True)
+    lifted_ref = oracle.sum_of_lifted(kind, num, cat, group=slots.astype(np.int32), n_groups=len(labels))
+    for a, b in zip(got, lifted_ref):
+        assert_struct_parity(a, b, rtol=2e-4, what="vs fp32 restatement")
