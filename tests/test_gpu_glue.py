@@ -16,7 +16,8 @@ def test_registration_superset_of_the_reference():
     assert replay.glue().implementation == "b200"
     for name in ("sum_to_triple_3_3", "sum_to_triple_19_19", "sum_to_triple_20_0", "sum_to_nb_agg_12_4", "sum_to_triple_20_10"):
         assert name in fns
-    assert "sum_to_triple_0_0" not in fns and len(fns) == 2 * (21 * 21 - 1)
+    assert "sum_to_triple_0_0" not in fns and len(fns) == 2 * (21 * 21 - 1) + 2  # + sum_triple, sum_nb_agg
+    assert {"sum_triple", "sum_nb_agg"} <= fns
 
 
 def test_goldens_through_the_duckdb_callbacks(goldens):
