@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include "gram_launch.h"
 #include "slab_kernels.cuh"
@@ -130,6 +131,7 @@ StagePool g_stage_pool;
 struct cfb_ctx {
   int device = 0, kind = 0, n = 0, m = 0, G = 1;
   bool user_domain = false;  // set through cfb_ctx_set_cat_domain: out-of-range keys are errors
+  bool touched = false;      // something was aggregated since creation / recycling
   Layout lay{};
   Layout *d_lay = nullptr;
   double *d_f64 = nullptr;
@@ -158,6 +160,36 @@ struct cfb_ctx {
 };
 
 namespace {
+
+// Contexts are recycled: a DuckDB query creates one state per worker thread (and per group) and
+// destroys them all at the end; cudaMalloc / cudaFree / stream creation cost milliseconds and
+// serialise inside the driver, so a destroyed context keeps its stream, events and device
+// buffers, is zeroed, and waits here for the next cfb_ctx_create of the same shape.
+struct CtxPool {
+  std::mutex mu;
+  std::vector<cfb_ctx *> idle;
+  static constexpr size_t kMaxIdle = 256;
+  static constexpr long long kMaxStateBytes = 64ll << 20;
+  cfb_ctx *take(int device, int kind, int n, int m, int G) {
+    std::lock_guard<std::mutex> g(mu);
+    for (size_t i = 0; i < idle.size(); i++) {
+      cfb_ctx *c = idle[i];
+      if (c->device == device && c->kind == kind && c->n == n && c->m == m && c->G == G) {
+        idle[i] = idle.back();
+        idle.pop_back();
+        return c;
+      }
+    }
+    return nullptr;
+  }
+  bool give(cfb_ctx *c) {
+    std::lock_guard<std::mutex> g(mu);
+    if (idle.size() >= kMaxIdle) return false;
+    idle.push_back(c);
+    return true;
+  }
+};
+CtxPool g_ctx_pool;
 
 // ------------------------------------------------------------------------- layout
 void build_layout(Layout &L, int kind, int n, int m, int G, const int *lo, const int *hi) {
@@ -216,12 +248,16 @@ int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, d
 
 // Make the context's categorical domain cover [lo, hi] per column, re-laying out the dense
 // state if it has to grow (stream-ordered).
-int ensure_domain(cfb_ctx *c, const int *lo, const int *hi) {
+int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) {
   if (c->m == 0) return CFB_OK;
   int nlo[cfb::kMaxCat], nhi[cfb::kMaxCat];
   bool grow = !c->lay.has_domain;
   for (int k = 0; k < c->m; k++) {
-    if (c->lay.has_domain) {
+    if (exact) {  // an untouched (fresh or recycled) context takes exactly the declared domain
+      nlo[k] = lo[k];
+      nhi[k] = hi[k];
+      if (!c->lay.has_domain || c->lay.lo[k] != lo[k] || (long long)c->lay.lo[k] + c->lay.dom[k] - 1 != hi[k]) grow = true;
+    } else if (c->lay.has_domain) {
       const int clo = c->lay.lo[k], chi = (int)((long long)c->lay.lo[k] + c->lay.dom[k] - 1);
       nlo[k] = std::min(clo, lo[k]);
       nhi[k] = std::max(chi, hi[k]);
@@ -245,8 +281,10 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi) {
   CU(cudaMemcpyAsync(d_nl, &nl, sizeof(Layout), cudaMemcpyHostToDevice, c->stream));
   // carry the old contents over; an old state without a domain has only its numeric part
   // and N, which the remap handles because its tables are empty
-  rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, c->stream);
-  if (rc) return rc;
+  if (!exact) {
+    rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, c->stream);
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(c->stream));  // &nl and the old arrays must outlive the copies
   cudaFree(c->d_f64);
   cudaFree(c->d_u64);
@@ -347,6 +385,7 @@ int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, in
 int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, const int32_t *group,
                 unsigned long long rows, cudaStream_t s) {
   if (rows == 0) return CFB_OK;
+  c->touched = true;
   for (int k = 0; k < c->n; k++)
     if (!num[k] || ((uintptr_t)num[k] & 15))
       return fail(CFB_ERR_INVALID, "numeric column %d must be a 16-byte aligned device pointer", k);
@@ -425,6 +464,7 @@ int flush_tile(cfb_ctx *c) {
     int rc = ensure_domain(c, c->st_lo, c->st_hi);
     if (rc) return rc;
   }
+  _mm_sfence();  // the staging tile was filled with non-temporal stores
   if (rows == tr) {
     CU(cudaMemcpyAsync(st.d, st.h, tr * 4 * (ncol - (c->uses_group ? 0 : 1)), cudaMemcpyHostToDevice, c->stream));
   } else {
@@ -456,10 +496,32 @@ int flush_tile(cfb_ctx *c) {
   return CFB_OK;
 }
 
+// Contiguous copy into the pinned staging tile with non-temporal stores: the tile is written
+// once and next read by the DMA engine, so bypassing the cache saves the read-for-ownership
+// traffic of a plain memcpy (the host-fed path is host-memory-bandwidth bound).
+inline void copy_stream(void *dst, const void *src, size_t bytes) {
+  char *d = (char *)dst;
+  const char *s = (const char *)src;
+  if (bytes < 256 || ((uintptr_t)d & 15)) {
+    memcpy(d, s, bytes);
+    return;
+  }
+  size_t i = 0;
+  for (; i + 64 <= bytes; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i *)(s + i)), b = _mm_loadu_si128((const __m128i *)(s + i + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i *)(s + i + 32)), e = _mm_loadu_si128((const __m128i *)(s + i + 48));
+    _mm_stream_si128((__m128i *)(d + i), a);
+    _mm_stream_si128((__m128i *)(d + i + 16), b);
+    _mm_stream_si128((__m128i *)(d + i + 32), c);
+    _mm_stream_si128((__m128i *)(d + i + 48), e);
+  }
+  if (i < bytes) memcpy(d + i, s + i, bytes - i);
+}
+
 template <class T>
 inline void gather(T *dst, const T *src, const uint32_t *sel, size_t first, size_t cnt) {
   if (!sel)
-    memcpy(dst, src + first, cnt * sizeof(T));
+    copy_stream(dst, src + first, cnt * sizeof(T));
   else
     for (size_t i = 0; i < cnt; i++) dst[i] = src[sel[first + i]];
 }
@@ -488,6 +550,11 @@ int cfb_ctx_create(int device, int kind, int n_num, int n_cat, int n_groups, cfb
   if (nd == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
   if (device < 0 || device >= nd) return fail(CFB_ERR_INVALID, "device %d out of range (0..%d)", device, nd - 1);
   CU(cudaSetDevice(device));
+  if (cfb_ctx *r = g_ctx_pool.take(device, kind, n_num, n_cat, n_groups)) {
+    r->timed = g_timing.load() != 0;
+    *out = r;
+    return CFB_OK;
+  }
   cfb_ctx *c = new cfb_ctx();
   c->device = device;
   c->kind = kind;
@@ -532,7 +599,27 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   if (!c) return CFB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->user_stream) cudaStreamSynchronize(c->user_stream);
   for (auto &s : c->st) g_stage_pool.release(c->device, s);  // the stream is drained: nothing in flight
+  c->tile_rows = 0;
+  c->fill = 0;
+  c->cur = 0;
+  c->uses_group = false;
+  c->user_stream = nullptr;
+  // recycle: zero the state (its layout, i.e. the categorical domain seen so far, is kept: keys
+  // that do not occur again have count 0 and are not emitted) and park the context
+  const long long state_bytes = (c->lay.F + c->lay.U) * c->lay.n_groups * 8;
+  if (c->stream && c->d_f64 && state_bytes <= CtxPool::kMaxStateBytes && !getenv("CFB_NO_CTX_POOL")) {
+    bool ok = cudaMemsetAsync(c->d_f64, 0, std::max<long long>(8, c->lay.F * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
+              cudaMemsetAsync(c->d_u64, 0, std::max<long long>(8, c->lay.U * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
+              cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream) == cudaSuccess &&
+              cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int), c->stream) == cudaSuccess &&
+              cudaStreamSynchronize(c->stream) == cudaSuccess;
+    c->user_domain = false;
+    c->touched = false;
+    if (ok && g_ctx_pool.give(c)) return CFB_OK;
+    cudaGetLastError();
+  }
   cudaFree(c->d_f64);
   cudaFree(c->d_u64);
   cudaFree(c->d_lay);
@@ -554,7 +641,7 @@ int cfb_ctx_set_cat_domain(cfb_ctx *c, const int32_t *lo, const int32_t *hi) {
   for (int k = 0; k < c->m; k++)
     if (hi[k] < lo[k]) return fail(CFB_ERR_INVALID, "empty domain for categorical column %d", k);
   CU(cudaSetDevice(c->device));
-  int rc = ensure_domain(c, lo, hi);
+  int rc = ensure_domain(c, lo, hi, /*exact=*/!c->touched);
   if (rc) return rc;
   c->user_domain = true;
   return CFB_OK;
@@ -567,6 +654,7 @@ int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *con
   if (count == 0) return CFB_OK;
   if ((c->n && !num_cols) || (c->m && !cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
   CU(cudaSetDevice(c->device));
+  c->touched = true;
   int rc = ensure_staging(c);
   if (rc) return rc;
   if (group_slot && !c->uses_group) {
@@ -625,6 +713,7 @@ int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const flo
   if (c->kind == CFB_TRIPLE && m && (!cat_cat_lists || (n && !num_cat_lists)))
     return fail(CFB_ERR_INVALID, "NULL categorical child array");
   CU(cudaSetDevice(c->device));
+  c->touched = true;
   int rc = flush_tile(c);  // keep the order of updates on the context stream
   if (rc) return rc;
   // sparse entries -> tagged records (host: a few entries per lifted row), key ranges for the domain
@@ -749,6 +838,7 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
   int rc = cfb_ctx_sync(src);
   if (rc) return rc;
   CU(cudaSetDevice(dst->device));
+  dst->touched = true;
   rc = flush_tile(dst);
   if (rc) return rc;
   if (src->m > 0 && !src->lay.has_domain) {
@@ -922,6 +1012,7 @@ int cfb_ctx_import_partial(cfb_ctx *c, const void *d_f64, const void *d_u64, voi
   CU(cudaSetDevice(c->device));
   int rc = cfb_ctx_sync(c);
   if (rc) return rc;
+  c->touched = true;
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   if (c->lay.F) CU(cudaMemcpyAsync(c->d_f64, d_f64, c->lay.F * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->d_u64, d_u64, c->lay.U * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));

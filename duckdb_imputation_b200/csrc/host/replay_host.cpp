@@ -288,7 +288,12 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
         if (i) os << ", ";
         RenderValue(result, i, os);
       }
+      const auto t1 = std::chrono::steady_clock::now();
       if (fun.destructor) fun.destructor(states, aggr, fin.size());
+      if (getenv("CFB_REPLAY_TRACE"))
+        fprintf(stderr, "[replay] update+combine+finalize %.1f ms, render %.1f ms, destroy %.1f ms\n", secs * 1e3,
+                std::chrono::duration<double>(t1 - t0).count() * 1e3 - secs * 1e3,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() * 1e3);
     } else {
       secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
