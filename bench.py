@@ -340,7 +340,7 @@ def main():
                    "exchange": "none" if world == 1 else "NCCL all_reduce of the partial triple (fp64 sums + int64 counts) per step",
                    "accumulate": "fp32x2 FMA over bounded runs, folded into fp64"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "cfb::gram_scan_kernel<20,false,512>", "kernel_ms": kernel_ms,
+                     "traffic": None, "kernel": "cfb::gram_scan_kernel<20,false,768>", "kernel_ms": kernel_ms,
                      "peak_source": peak_src, "hbm_gbs_whole_step": world * rows * BYTES_PER_ROW / (ms_per_step * 1e-3) / 1e9},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "check": check,
     }

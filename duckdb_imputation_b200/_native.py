@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcofactor_b200.so")
+LIB_PATH = os.environ.get("CFB_LIB_PATH") or os.path.join(_HERE, "lib", "libcofactor_b200.so")  # override: A/B builds
 
 CFB_TRIPLE, CFB_NB = 0, 1
 CFB_OK, CFB_ERR_INVALID, CFB_ERR_NO_DEVICE, CFB_ERR_CUDA, CFB_ERR_OOM, CFB_ERR_DOMAIN, CFB_ERR_STATE = (

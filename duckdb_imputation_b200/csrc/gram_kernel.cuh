@@ -146,7 +146,10 @@ struct GramArgs {
 // rows per ring stage: narrow tables get longer tiles so a stage stays >= 8 KB
 template <int N>
 struct GramTile {
-  static constexpr int kRows = N <= 4 ? 2048 : (N <= 10 ? 1024 : 512);  // multiple of 128 * kGroups
+#ifndef CFB_TR_WIDE
+#define CFB_TR_WIDE 768
+#endif
+  static constexpr int kRows = N <= 4 ? 2048 : (N <= 10 ? 1024 : (N <= 20 ? CFB_TR_WIDE : 512));  // multiple of 128 * kGroups
 };
 
 template <int N, bool DIAG>
