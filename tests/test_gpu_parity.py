@@ -252,3 +252,22 @@ def test_partial_export_matches_host_layout_and_roundtrips():
         twice = other.finalize_arrays()
     assert twice["N"] == 2 * rows and np.array_equal(twice["cat_counts"], 2 * arrays["cat_counts"])
     np.testing.assert_allclose(twice["quad"], 2 * arrays["quad"], rtol=1e-15)
+
+
+def test_mice_style_filtered_device_scan_via_group_slots():
+    """MICE issues sum_to_triple(...) WHERE col_IS_NULL IS FALSE over ~80% of the rows
+    (imputation_base.cpp:21-34).  On device-resident data the filter is a 2-slot GROUP BY on the
+    null flag: slot 0 = rows that pass.  Must equal the oracle's filtered scan."""
+    torch = pytest.importorskip("torch")
+    rows = 300_000
+    dn, dc, hn, hc = _device_cols(torch, rows, 6, 3, seed=5, dom=12)
+    flag = synth.int32(rows, 4242, lo=0, rng=5)          # 0..4
+    is_null = (flag == 0).astype(np.int32)               # ~20% NULL in the imputed column
+    dflag = torch.from_numpy(is_null).cuda()
+    with CofactorContext(CFB_TRIPLE, 6, 3, n_groups=2) as ctx:
+        ctx.scan_device(dn, dc, rows, d_group=dflag)
+        got = ctx.finalize_arrays(0)
+        nulls = ctx.finalize_arrays(1)
+    sel = np.nonzero(is_null == 0)[0].astype(np.uint32)
+    assert_parity(got, oracle.aggregate_arrays(CFB_TRIPLE, hn, hc, sel=sel)[0], what="rows that pass the filter")
+    assert got["N"] + nulls["N"] == rows
