@@ -24,6 +24,7 @@
 #include <emmintrin.h>
 
 #include "gram_launch.h"
+#include "pair_hash.cuh"
 #include "slab_kernels.cuh"
 #include "slab_launch.h"
 #include "scatter_kernels.cuh"
@@ -138,6 +139,8 @@ struct cfb_ctx {
   unsigned long long *d_u64 = nullptr;
   int *d_err = nullptr;
   int *d_minmax = nullptr;  // [2][kMaxCat]
+  cfb::PairHash hash{};               // sparse pair counts (lay.pairs_hashed)
+  unsigned long long hash_upper = 0;  // host-side upper bound on occupied hash slots
   cudaStream_t stream = nullptr;
   cudaStream_t user_stream = nullptr;  // last caller-provided stream of cfb_triple_device
   // per-CTA fp32 slabs of slab_scan_kernel (all zero between launches)
@@ -192,6 +195,16 @@ struct CtxPool {
 CtxPool g_ctx_pool;
 
 // ------------------------------------------------------------------------- layout
+// Dense pair tables are used while they stay below this many bytes (all groups); above it the
+// pair counts go to the hash table of pair_hash.cuh.  CFB_DENSE_PAIR_BYTES overrides (tests).
+long long dense_pair_limit() {
+  static const long long v = [] {
+    const char *e = getenv("CFB_DENSE_PAIR_BYTES");
+    return e ? atoll(e) : (2ll << 30);
+  }();
+  return v;
+}
+
 void build_layout(Layout &L, int kind, int n, int m, int G, const int *lo, const int *hi) {
   memset(&L, 0, sizeof(L));
   L.kind = kind;
@@ -218,6 +231,10 @@ void build_layout(Layout &L, int kind, int n, int m, int G, const int *lo, const
         L.pair_off[k * m + l] = po;
         po += (long long)L.dom[k] * L.dom[l];
       }
+  if (po * 8 * G > dense_pair_limit()) {
+    L.pairs_hashed = 1;  // sparse pair counts (pair_hash.cuh)
+    po = 0;
+  }
   L.F = L.numcat_base + (kind == CFB_TRIPLE ? (long long)n * off : 0);
   L.U = L.pair_base + po;
 }
@@ -236,18 +253,87 @@ int alloc_state(const Layout &L, double **f, unsigned long long **u, cudaStream_
   return CFB_OK;
 }
 
-int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, double *df, unsigned long long *du,
-                     const double *sf, const unsigned long long *su, cudaStream_t s) {
-  const long long tot = (sl.F + sl.U) * sl.n_groups;
-  const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
-  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su);
+// ---- sparse pair counts ------------------------------------------------------------
+constexpr unsigned long long kMinHashCapacity = 1ull << 16, kMaxHashCapacity = 1ull << 30;
+
+void hash_free(cfb::PairHash &h) {
+  cudaFree(h.keys);
+  cudaFree(h.counts);
+  cudaFree(h.n_entries);
+  h = cfb::PairHash{};
+}
+
+int hash_alloc(cfb::PairHash *h, unsigned long long capacity, int G, cudaStream_t s) {
+  *h = cfb::PairHash{};
+  if (capacity > kMaxHashCapacity) return fail(CFB_ERR_DOMAIN, "pair hash table would need %llu slots per group", capacity);
+  h->capacity = capacity;
+  const size_t bytes = (size_t)capacity * G * 8;
+  cudaError_t e = cudaMalloc(&h->keys, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counts, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->n_entries, 8);
+  if (e != cudaSuccess) {
+    hash_free(*h);
+    return fail(e == cudaErrorMemoryAllocation ? CFB_ERR_OOM : CFB_ERR_CUDA, "pair hash allocation: %s", cudaGetErrorString(e));
+  }
+  cfb::pair_hash_clear_kernel<<<148 * 4, 256, 0, s>>>(*h, capacity * G);
   g_launches++;
   CU(cudaGetLastError());
   return CFB_OK;
 }
 
-// Make the context's categorical domain cover [lo, hi] per column, re-laying out the dense
-// state if it has to grow (stream-ordered).
+unsigned long long pow2_at_least(unsigned long long v) {
+  unsigned long long p = kMinHashCapacity;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Make room for `add` more distinct pairs (per group, worst case) before a scan.
+int hash_reserve(cfb_ctx *c, unsigned long long add) {
+  if (!c->lay.pairs_hashed) return CFB_OK;
+  if ((c->hash_upper + add) * 2 <= c->hash.capacity) {
+    c->hash_upper += add;
+    return CFB_OK;
+  }
+  unsigned long long exact = 0;
+  CU(cudaMemcpyAsync(&exact, c->hash.n_entries, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->hash_upper = exact;
+  if ((exact + add) * 2 > c->hash.capacity) {
+    cfb::PairHash nh;
+    int rc = hash_alloc(&nh, pow2_at_least((exact + add) * 2), c->G, c->stream);
+    if (rc) return rc;
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, nh, c->d_err);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    hash_free(c->hash);
+    c->hash = nh;
+  }
+  c->hash_upper += add;
+  return CFB_OK;
+}
+
+int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, double *df, unsigned long long *du,
+                     const double *sf, const unsigned long long *su, const cfb::PairHash &dhash, int *d_err,
+                     cudaStream_t s) {
+  const long long tot = (sl.F + sl.U) * sl.n_groups;
+  const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
+  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su, dhash, d_err);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+long long dense_pair_entries(const Layout &L) {
+  long long po = 0;
+  for (int k = 0; k < L.m; k++)
+    for (int l = k + 1; l < L.m; l++) po += (long long)L.dom[k] * L.dom[l];
+  return po;
+}
+
+// Make the context's categorical domain cover [lo, hi] per column, re-laying out the state if
+// it has to grow (stream-ordered).  A grown domain may switch the pair counts from dense
+// tables to the hash table.
 int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) {
   if (c->m == 0) return CFB_OK;
   int nlo[cfb::kMaxCat], nhi[cfb::kMaxCat];
@@ -266,8 +352,8 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) 
       nlo[k] = lo[k];
       nhi[k] = hi[k];
     }
-    if ((long long)nhi[k] - nlo[k] + 1 > (1ll << 30))
-      return fail(CFB_ERR_DOMAIN, "categorical column %d spans [%d,%d]: too large for the dense path", k, nlo[k], nhi[k]);
+    if ((long long)nhi[k] - nlo[k] + 1 > (1ll << cfb::kPairSlotBits))
+      return fail(CFB_ERR_DOMAIN, "categorical column %d spans [%d,%d]: key range too large", k, nlo[k], nhi[k]);
   }
   if (!grow) return CFB_OK;
   Layout nl;
@@ -276,23 +362,40 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) 
   unsigned long long *nu = nullptr;
   int rc = alloc_state(nl, &nf, &nu, c->stream);
   if (rc) return rc;
+  cfb::PairHash nh{};
+  if (nl.pairs_hashed) {
+    // room for what the old state can hold: its hash entries, or its dense non-zeros (<= table size)
+    unsigned long long carry = c->lay.pairs_hashed ? c->hash_upper : (unsigned long long)dense_pair_entries(c->lay);
+    carry = std::min<unsigned long long>(carry, exact ? 0 : carry);
+    rc = hash_alloc(&nh, pow2_at_least(2 * carry + 2), c->G, c->stream);
+    if (rc) return rc;
+  }
   Layout *d_nl = nullptr;
   CU(cudaMalloc(&d_nl, sizeof(Layout)));
   CU(cudaMemcpyAsync(d_nl, &nl, sizeof(Layout), cudaMemcpyHostToDevice, c->stream));
   // carry the old contents over; an old state without a domain has only its numeric part
   // and N, which the remap handles because its tables are empty
   if (!exact) {
-    rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, c->stream);
+    rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, nh, c->d_err, c->stream);
     if (rc) return rc;
+    if (c->lay.pairs_hashed) {
+      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, d_nl, c->d_lay, nu, nh, c->d_err);
+      g_launches++;
+      CU(cudaGetLastError());
+    }
   }
   CU(cudaStreamSynchronize(c->stream));  // &nl and the old arrays must outlive the copies
   cudaFree(c->d_f64);
   cudaFree(c->d_u64);
   cudaFree(c->d_lay);
+  if (c->hash.capacity) hash_free(c->hash);
   c->d_f64 = nf;
   c->d_u64 = nu;
   c->d_lay = d_nl;
   c->lay = nl;
+  c->hash = nh;
+  if (!nl.pairs_hashed || exact) c->hash_upper = 0;
+  else if (!c->hash_upper) c->hash_upper = (nh.capacity - 2) / 2;  // dense -> hashed: unknown non-zero count
   return CFB_OK;
 }
 
@@ -373,6 +476,7 @@ int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, in
   p.f64 = c->d_f64;
   p.u64 = c->d_u64;
   p.err = c->d_err;
+  p.hash = c->hash;
   p.grid = grid;
   p.stream = s;
   const cudaError_t e = (c->kind == CFB_NB ? kSlabNb : kSlabTriple)[c->n](p);
@@ -405,17 +509,34 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
     g_launches++;
   }
-  int need_generic = (grouped || c->m > 0) ? 1 : 0;
-  if (need_generic) {
-    const int rc = launch_slab(c, sc, rows, grouped ? 1 : 0, s);
-    if (rc < 0) return rc;
-    need_generic = rc;  // 1 = slab too large for this shape
-  }
-  if (need_generic) {
-    const int blocks = (int)std::min<unsigned long long>((rows + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
-    cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(sc, c->d_lay, rows, grouped ? 1 : 0, c->d_f64,
-                                                                 c->d_u64, c->d_err);
-    g_launches++;
+  if (grouped || c->m > 0) {
+    // With hashed pair counts the scan is cut into slices so that the table can be grown
+    // (host-side, between launches) before it could fill up.
+    const int npairs = c->kind == CFB_TRIPLE ? c->m * (c->m - 1) / 2 : 0;
+    const bool hashed = c->lay.pairs_hashed && npairs > 0;
+    unsigned long long slice = rows;
+    if (hashed) slice = std::max<unsigned long long>(1ull << 18, ((1ull << 24) / npairs) & ~1023ull);
+    for (unsigned long long r0 = 0; r0 < rows; r0 += slice) {
+      const unsigned long long cnt = std::min(slice, rows - r0);
+      cfb::ScanCols part = sc;
+      for (int k = 0; k < c->n; k++) part.num[k] = num[k] + r0;
+      for (int k = 0; k < c->m; k++) part.cat[k] = cat[k] + r0;
+      if (group) part.group = group + r0;
+      if (hashed) {
+        if (s != c->stream) CU(cudaStreamSynchronize(s));
+        const unsigned long long worst = std::min<unsigned long long>(cnt * npairs, (unsigned long long)dense_pair_entries(c->lay));
+        int rc = hash_reserve(c, worst);
+        if (rc) return rc;
+      }
+      int need_generic = launch_slab(c, part, cnt, grouped ? 1 : 0, s);
+      if (need_generic < 0) return need_generic;
+      if (need_generic) {  // 1 = slab too large for this shape
+        const int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
+        cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(part, c->d_lay, cnt, grouped ? 1 : 0, c->d_f64,
+                                                                     c->d_u64, c->d_err, c->hash);
+        g_launches++;
+      }
+    }
   }
   CU(cudaGetLastError());
   if (c->timed) CU(cudaEventRecord(c->ev1, s));
@@ -429,6 +550,7 @@ int check_async_error(cfb_ctx *c) {
   if (e) {
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     if (e == 1) return fail(CFB_ERR_DOMAIN, "a categorical key lies outside the declared domain");
+    if (e == 3) return fail(CFB_ERR_CUDA, "internal: the pair hash table filled up");
     return fail(CFB_ERR_INVALID, "a group slot lies outside [0, n_groups)");
   }
   return CFB_OK;
@@ -609,7 +731,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   // recycle: zero the state (its layout, i.e. the categorical domain seen so far, is kept: keys
   // that do not occur again have count 0 and are not emitted) and park the context
   const long long state_bytes = (c->lay.F + c->lay.U) * c->lay.n_groups * 8;
-  if (c->stream && c->d_f64 && state_bytes <= CtxPool::kMaxStateBytes && !getenv("CFB_NO_CTX_POOL")) {
+  if (c->stream && c->d_f64 && state_bytes <= CtxPool::kMaxStateBytes && !c->lay.pairs_hashed && !getenv("CFB_NO_CTX_POOL")) {
     bool ok = cudaMemsetAsync(c->d_f64, 0, std::max<long long>(8, c->lay.F * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
               cudaMemsetAsync(c->d_u64, 0, std::max<long long>(8, c->lay.U * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
               cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream) == cudaSuccess &&
@@ -628,6 +750,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);
+  if (c->hash.capacity) hash_free(c->hash);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -782,8 +905,10 @@ int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const flo
   }
   if (bE) {
     const int blocks = (int)std::min<size_t>((ent.size() + 255) / 256, (size_t)dev_info(c->device).sms * 4);
+    rc = hash_reserve(c, ent.size());
+    if (rc) return rc;
     cfb::lifted_scatter_kernel<<<blocks, 256, 0, s>>>((const cfb::LiftedEntry *)dE, ent.size(), c->d_lay, c->d_f64,
-                                                     c->d_u64, c->d_err);
+                                                     c->d_u64, c->d_err, c->hash);
     g_launches++;
   }
   CU(cudaGetLastError());
@@ -872,12 +997,42 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
     su = tu;
     sl = tl;
   }
-  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->stream);
+  // pairs of the source that may be new to dst: its hash entries, or its dense non-zeros
+  cfb::PairHash shash = src->hash, thash{};
+  if (dst->lay.pairs_hashed) {
+    unsigned long long add = (unsigned long long)dense_pair_entries(src->lay);
+    if (src->lay.pairs_hashed) {
+      unsigned long long exact = 0;
+      CU(cudaSetDevice(src->device));
+      CU(cudaMemcpy(&exact, src->hash.n_entries, 8, cudaMemcpyDeviceToHost));
+      CU(cudaSetDevice(dst->device));
+      add = exact;
+    }
+    rc = hash_reserve(dst, add);
+    if (rc) return rc;
+  }
+  if (src->lay.pairs_hashed && src->device != dst->device) {
+    const size_t bytes = (size_t)src->hash.capacity * src->G * 8;
+    thash.capacity = src->hash.capacity;
+    CU(cudaMalloc(&thash.keys, bytes));
+    CU(cudaMalloc(&thash.counts, bytes));
+    CU(cudaMemcpyPeerAsync(thash.keys, dst->device, src->hash.keys, src->device, bytes, dst->stream));
+    CU(cudaMemcpyPeerAsync(thash.counts, dst->device, src->hash.counts, src->device, bytes, dst->stream));
+    shash = thash;
+  }
+  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->hash, dst->d_err, dst->stream);
   if (rc) return rc;
+  if (src->lay.pairs_hashed) {
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, dst->stream>>>(shash, dst->d_lay, sl, dst->d_u64, dst->hash, dst->d_err);
+    g_launches++;
+    CU(cudaGetLastError());
+  }
   CU(cudaStreamSynchronize(dst->stream));
   cudaFree(tf);
   cudaFree(tu);
   cudaFree(tl);
+  cudaFree(thash.keys);
+  cudaFree(thash.counts);
   return CFB_OK;
 }
 
@@ -931,6 +1086,30 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
       for (size_t t = 0; t < keys.size(); t++)
         nc[(size_t)i * keys.size() + t] = f[L.numcat_base + (long long)i * L.total_dom + dense_t[t]];
     out->numcat_sums = dupv(nc);
+    // sparse pair counts: pull this group's hash partition and order it like std::map iteration
+    struct HashedPair {
+      int pair;
+      long long sk, sl;
+      unsigned long long count;
+    };
+    std::vector<HashedPair> hashed;
+    if (L.pairs_hashed && c->hash.capacity) {
+      const size_t cap = (size_t)c->hash.capacity;
+      std::vector<unsigned long long> hk(cap), hc(cap);
+      CU(cudaMemcpyAsync(hk.data(), c->hash.keys + (size_t)group * cap, cap * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(hc.data(), c->hash.counts + (size_t)group * cap, cap * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      const unsigned long long mask = (1ull << cfb::kPairSlotBits) - 1;
+      for (size_t i = 0; i < cap; i++)
+        if (hk[i] != cfb::kPairEmpty && hc[i])
+          hashed.push_back({(int)(hk[i] >> (2 * cfb::kPairSlotBits)), (long long)((hk[i] >> cfb::kPairSlotBits) & mask),
+                            (long long)(hk[i] & mask), hc[i]});
+      std::sort(hashed.begin(), hashed.end(), [](const HashedPair &a, const HashedPair &b) {
+        if (a.pair != b.pair) return a.pair < b.pair;
+        if (a.sk != b.sk) return a.sk < b.sk;
+        return a.sl < b.sl;
+      });
+    }
     out->n_pair_lists = (int64_t)m * (m + 1) / 2;
     std::vector<int64_t> po(out->n_pair_lists + 1, 0), pc;
     std::vector<int32_t> k1, k2;
@@ -943,6 +1122,14 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
             k1.push_back(keys[t]);
             k2.push_back(keys[t]);
             pc.push_back(counts[t]);
+          }
+        } else if (L.pairs_hashed) {
+          auto range = std::equal_range(hashed.begin(), hashed.end(), HashedPair{k * m + l, 0, 0, 0},
+                                        [](const HashedPair &a, const HashedPair &b) { return a.pair < b.pair; });
+          for (auto it = range.first; it != range.second; ++it) {
+            k1.push_back((int32_t)((long long)L.lo[k] + it->sk));
+            k2.push_back((int32_t)((long long)L.lo[l] + it->sl));
+            pc.push_back((int64_t)it->count);
           }
         } else {
           const unsigned long long *tab = u.data() + L.pair_base + L.pair_off[k * m + l];
@@ -997,6 +1184,7 @@ int cfb_ctx_partial_sizes(cfb_ctx *c, size_t *n_f64, size_t *n_u64) {
 
 int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
   int rc = cfb_ctx_sync(c);
   if (rc) return rc;
@@ -1009,6 +1197,7 @@ int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
 
 int cfb_ctx_import_partial(cfb_ctx *c, const void *d_f64, const void *d_u64, void *stream) {
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
   int rc = cfb_ctx_sync(c);
   if (rc) return rc;

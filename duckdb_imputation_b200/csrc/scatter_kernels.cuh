@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pair_hash.cuh"
 #include "state_layout.h"
 
 namespace cfb {
@@ -22,7 +23,7 @@ __device__ __forceinline__ void add_u64(unsigned long long *p, unsigned long lon
 __global__ void __launch_bounds__(256)
     generic_scan_kernel(const ScanCols cols, const Layout *__restrict__ lay_g, unsigned long long n_rows,
                         int do_numeric, double *__restrict__ f64, unsigned long long *__restrict__ u64,
-                        int *__restrict__ err) {
+                        int *__restrict__ err, const PairHash hash) {
   __shared__ Layout lay;
   {
     const int *src = reinterpret_cast<const int *>(lay_g);
@@ -73,8 +74,12 @@ __global__ void __launch_bounds__(256)
     }
     if (triple)
       for (int k = 0; k < m; k++)
-        for (int l = k + 1; l < m; l++)
-          add_u64(U + lay.pair_base + lay.pair_off[k * m + l] + (long long)s[k] * lay.dom[l] + s[l], 1ull);
+        for (int l = k + 1; l < m; l++) {
+          if (!lay.pairs_hashed)
+            add_u64(U + lay.pair_base + lay.pair_off[k * m + l] + (long long)s[k] * lay.dom[l] + s[l], 1ull);
+          else if (!pair_hash_add(hash, g, pair_key(k * m + l, s[k], s[l]), 1ull))
+            atomicExch(err, 3);
+        }
   }
 }
 
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     remap_add_kernel(const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g, double *__restrict__ df,
                      unsigned long long *__restrict__ du, const double *__restrict__ sf,
-                     const unsigned long long *__restrict__ su) {
+                     const unsigned long long *__restrict__ su, const PairHash dhash, int *__restrict__ err) {
   __shared__ Layout dl, sl;
   {
     const int *a = reinterpret_cast<const int *>(dl_g), *b = reinterpret_cast<const int *>(sl_g);
@@ -168,12 +173,70 @@ __global__ void __launch_bounds__(256)
             }
         const long long w = q - sl.pair_off[k * m + l];
         const long long sk = w / sl.dom[l] + (sl.lo[k] - dl.lo[k]), s2 = w % sl.dom[l] + (sl.lo[l] - dl.lo[l]);
+        if (dl.pairs_hashed) {
+          if (!pair_hash_add(dhash, g, pair_key(k * m + l, sk, s2), v)) atomicExch(err, 3);
+          continue;
+        }
         d = dl.pair_base + dl.pair_off[k * m + l] + sk * dl.dom[l] + s2;
       }
       du[g * dl.U + d] += v;
     }
   }
   (void)n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pair counts of a HASHED source state added into dst (dense or hashed), with the slot shift of
+// a domain change: combine, domain growth and hash-table growth all go through here.
+__global__ void __launch_bounds__(256)
+    pair_hash_drain_kernel(const PairHash src, const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g,
+                           unsigned long long *__restrict__ du, const PairHash dhash, int *__restrict__ err) {
+  __shared__ int s_dlo[kMaxCat], s_slo[kMaxCat], s_ddom[kMaxCat];
+  __shared__ long long s_poff[kMaxCat * kMaxCat];
+  __shared__ int s_m, s_G, s_dhashed;
+  __shared__ long long s_U, s_pbase;
+  if (threadIdx.x == 0) {
+    s_m = dl_g->m;
+    s_G = dl_g->n_groups;
+    s_dhashed = dl_g->pairs_hashed;
+    s_U = dl_g->U;
+    s_pbase = dl_g->pair_base;
+  }
+  for (int i = threadIdx.x; i < kMaxCat; i += blockDim.x) {
+    s_dlo[i] = dl_g->lo[i];
+    s_slo[i] = sl_g->lo[i];
+    s_ddom[i] = dl_g->dom[i];
+  }
+  for (int i = threadIdx.x; i < kMaxCat * kMaxCat; i += blockDim.x) s_poff[i] = dl_g->pair_off[i];
+  __syncthreads();
+  const unsigned long long total = src.capacity * (unsigned long long)s_G;
+  const unsigned long long slot_mask = (1ull << kPairSlotBits) - 1;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = src.keys[i];
+    if (key == kPairEmpty) continue;
+    const unsigned long long v = src.counts[i];
+    if (!v) continue;
+    const long long g = (long long)(i / src.capacity);
+    const int p = (int)(key >> (2 * kPairSlotBits));
+    const int k = p / s_m, l = p % s_m;
+    const long long sk = (long long)((key >> kPairSlotBits) & slot_mask) + (s_slo[k] - s_dlo[k]);
+    const long long sl2 = (long long)(key & slot_mask) + (s_slo[l] - s_dlo[l]);
+    if (s_dhashed) {
+      if (!pair_hash_add(dhash, g, pair_key(p, sk, sl2), v)) atomicExch(err, 3);
+    } else {
+      atomicAdd(du + g * s_U + s_pbase + s_poff[k * s_m + l] + sk * s_ddom[l] + sl2, v);
+    }
+  }
+}
+
+__global__ void pair_hash_clear_kernel(PairHash h, unsigned long long total) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    h.keys[i] = kPairEmpty;
+    h.counts[i] = 0ull;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *h.n_entries = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -219,7 +282,8 @@ struct LiftedEntry {
 };
 __global__ void __launch_bounds__(256)
     lifted_scatter_kernel(const LiftedEntry *__restrict__ e, unsigned long long n_entries, const Layout *__restrict__ lay_g,
-                          double *__restrict__ f64, unsigned long long *__restrict__ u64, int *__restrict__ err) {
+                          double *__restrict__ f64, unsigned long long *__restrict__ u64, int *__restrict__ err,
+                          const PairHash hash) {
   __shared__ Layout lay;
   {
     const int *src = reinterpret_cast<const int *>(lay_g);
@@ -254,7 +318,10 @@ __global__ void __launch_bounds__(256)
         atomicExch(err, 1);
         continue;
       }
-      atomicAdd(u64 + lay.pair_base + lay.pair_off[k * m + l] + sk * lay.dom[l] + sl, (unsigned long long)llrintf(x.value));
+      if (!lay.pairs_hashed)
+        atomicAdd(u64 + lay.pair_base + lay.pair_off[k * m + l] + sk * lay.dom[l] + sl, (unsigned long long)llrintf(x.value));
+      else if (!pair_hash_add(hash, 0, pair_key(k * m + l, sk, sl), (unsigned long long)llrintf(x.value)))
+        atomicExch(err, 3);
     }
   }
 }

@@ -20,6 +20,7 @@ cudaError_t slab_launch(const SlabLaunchParams &p) {
   a.f64 = p.f64;
   a.u64 = p.u64;
   a.err = p.err;
+  a.hash = p.hash;
   slab_scan_kernel<N, KIND><<<p.grid, kSlabThreads, 0, p.stream>>>(a);
   return cudaGetLastError();
 }

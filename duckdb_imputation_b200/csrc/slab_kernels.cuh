@@ -18,6 +18,7 @@
 #include <type_traits>
 #include <cuda_runtime.h>
 
+#include "pair_hash.cuh"
 #include "state_layout.h"
 
 namespace cfb {
@@ -64,6 +65,7 @@ struct SlabArgs {
   double *f64;
   unsigned long long *u64;
   int *err;
+  PairHash hash;    // used when lay->pairs_hashed
 };
 
 template <int B, int E, class F>
@@ -209,11 +211,19 @@ __global__ void __launch_bounds__(kSlabThreads) slab_scan_kernel(const __grid_co
         }
       }
       if constexpr (KIND == 0) {
-        unsigned long long *pairs = a.u64 + (long long)g * lay.U + lay.pair_base;
-        for (int k = 0; k < m; k++) {
-          const long long sk = s_slot[k][threadIdx.x];
-          for (int l = k + 1; l < m; l++)
-            red_u64(pairs + lay.pair_off[k * m + l] + sk * lay.dom[l] + s_slot[l][threadIdx.x], 1ull);
+        if (!lay.pairs_hashed) {
+          unsigned long long *pairs = a.u64 + (long long)g * lay.U + lay.pair_base;
+          for (int k = 0; k < m; k++) {
+            const long long sk = s_slot[k][threadIdx.x];
+            for (int l = k + 1; l < m; l++)
+              red_u64(pairs + lay.pair_off[k * m + l] + sk * lay.dom[l] + s_slot[l][threadIdx.x], 1ull);
+          }
+        } else {
+          for (int k = 0; k < m; k++) {
+            const long long sk = s_slot[k][threadIdx.x];
+            for (int l = k + 1; l < m; l++)
+              if (!pair_hash_add(a.hash, g, pair_key(k * m + l, sk, s_slot[l][threadIdx.x]), 1ull)) atomicExch(a.err, 3);
+          }
         }
       }
     }

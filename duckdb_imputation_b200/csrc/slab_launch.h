@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pair_hash.cuh"
 #include "state_layout.h"
 
 namespace cfb {
@@ -19,6 +20,7 @@ struct SlabLaunchParams {
   int *err;
   int grid;
   cudaStream_t stream;
+  PairHash hash;
 };
 
 template <int N, int KIND>

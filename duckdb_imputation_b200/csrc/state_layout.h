@@ -18,6 +18,8 @@ struct Layout {
   int kind, n, m, n_groups;
   int nq;                  // n(n+1)/2 or n
   int has_domain;          // 0 until a categorical domain has been fixed
+  int pairs_hashed;        // 1: pair counts live in the PairHash (pair_hash.cuh), not in the u64 array
+  int pad_;
   long long total_dom;     // sum of dom[c]
   long long F, U;          // per-group length of the f64 / u64 arrays
   long long numcat_base;   // n + nq
