@@ -1186,12 +1186,15 @@ int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
   if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
-  int rc = cfb_ctx_sync(c);
+  int rc = flush_tile(c);
   if (rc) return rc;
+  // Stream-ordered when the caller names the stream its scans and its collective run on (no host
+  // synchronisation between scan, export, NCCL and import); synchronous on the context's own stream.
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (stream && c->fill == 0 && c->tile_rows) CU(cudaStreamSynchronize(c->stream));  // staged tiles ran on the context stream
   if (c->lay.F) CU(cudaMemcpyAsync(d_f64, c->d_f64, c->lay.F * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(d_u64, c->d_u64, c->lay.U * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
-  CU(cudaStreamSynchronize(s));
+  if (!stream) CU(cudaStreamSynchronize(s));
   return CFB_OK;
 }
 
@@ -1199,13 +1202,17 @@ int cfb_ctx_import_partial(cfb_ctx *c, const void *d_f64, const void *d_u64, voi
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
   if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
-  int rc = cfb_ctx_sync(c);
+  int rc = flush_tile(c);
   if (rc) return rc;
   c->touched = true;
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (stream) {
+    c->user_stream = s;  // finalize / sync wait for it
+    if (c->tile_rows) CU(cudaStreamSynchronize(c->stream));
+  }
   if (c->lay.F) CU(cudaMemcpyAsync(c->d_f64, d_f64, c->lay.F * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->d_u64, d_u64, c->lay.U * c->lay.n_groups * 8, cudaMemcpyDeviceToDevice, s));
-  CU(cudaStreamSynchronize(s));
+  if (!stream) CU(cudaStreamSynchronize(s));
   return CFB_OK;
 }
 

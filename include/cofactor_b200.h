@@ -187,7 +187,11 @@ void cfb_result_free(cfb_result *res);
  *   u64 part: [group][N | cat counts dense | pair counts dense]
  * export copies the context's device state into caller-provided device buffers,
  * import REPLACES the context's state with the buffers' contents.  Categorical
- * domains must have been agreed with cfb_ctx_set_cat_domain on every rank.    */
+ * domains must have been agreed with cfb_ctx_set_cat_domain on every rank.
+ * With a non-NULL `stream` (the stream the scans and the collective run on) both
+ * calls are stream-ordered and do not synchronise the host; with NULL they run on
+ * the context's stream and return when done.  Contexts whose pair counts are
+ * hashed (large domains) have no dense partial: CFB_ERR_DOMAIN.               */
 int cfb_ctx_partial_sizes(cfb_ctx *ctx, size_t *n_f64, size_t *n_u64);
 int cfb_ctx_export_partial(cfb_ctx *ctx, void *d_f64, void *d_u64, void *stream);
 int cfb_ctx_import_partial(cfb_ctx *ctx, const void *d_f64, const void *d_u64, void *stream);
