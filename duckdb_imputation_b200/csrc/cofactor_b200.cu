@@ -24,6 +24,7 @@
 #include <emmintrin.h>
 
 #include "gram_launch.h"
+#include "group_kernel.cuh"
 #include "pair_hash.cuh"
 #include "slab_kernels.cuh"
 #include "slab_launch.h"
@@ -485,6 +486,64 @@ int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, in
   return CFB_OK;
 }
 
+// GROUP BY / filtered numeric part through the warp-private shared-memory tables.  Returns 1 if
+// the tables do not fit (caller lets the slab kernel do the numeric part), 0 on success.
+template <int E>
+int launch_group_e(cfb_ctx *c, const cfb::GroupArgs &a, size_t smem, int grid, cudaStream_t s) {
+  auto kern = cfb::group_scan_kernel<E>;
+  static std::once_flag once[64];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[c->device & 63], [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(c->device).smem_optin - 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  kern<<<grid, cfb::kGroupThreads, smem, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+int launch_group(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (getenv("CFB_NO_GROUP_KERNEL")) return 1;
+  const int V = cfb::group_entries(c->n, c->kind);
+  const int need = (V + 31) / 32;
+  static const int kE[] = {1, 2, 3, 4, 6, 8, 12, 18};
+  int E = 0;
+  for (int e : kE)
+    if (e >= need) {
+      E = e;
+      break;
+    }
+  if (!E) return 1;
+  const size_t smem = cfb::group_smem_bytes(c->n, c->G, E);
+  if (smem > (size_t)dev_info(c->device).smem_optin - 1024) return 1;
+  cfb::GroupArgs a{};
+  a.cols = sc;
+  a.n_rows = rows;
+  a.n = c->n;
+  a.kind = c->kind;
+  a.n_groups = c->G;
+  a.flush_rows = std::max(256, env_int("CFB_GROUP_FLUSH_ROWS", 2048));
+  a.F = c->lay.F;
+  a.U = c->lay.U;
+  a.f64 = c->d_f64;
+  a.u64 = c->d_u64;
+  a.err = c->d_err;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)dev_info(c->device).smem_optin - 1024) / std::max<size_t>(smem, 1)));
+  int grid = dev_info(c->device).sms * per_sm;
+  grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(grid, (rows + 32 * cfb::kGroupWarps - 1) / (32 * cfb::kGroupWarps)));
+  switch (E) {
+    case 1: return launch_group_e<1>(c, a, smem, grid, s);
+    case 2: return launch_group_e<2>(c, a, smem, grid, s);
+    case 3: return launch_group_e<3>(c, a, smem, grid, s);
+    case 4: return launch_group_e<4>(c, a, smem, grid, s);
+    case 6: return launch_group_e<6>(c, a, smem, grid, s);
+    case 8: return launch_group_e<8>(c, a, smem, grid, s);
+    case 12: return launch_group_e<12>(c, a, smem, grid, s);
+    default: return launch_group_e<18>(c, a, smem, grid, s);
+  }
+}
+
 // -------------------------------------------------------------------- device scan
 int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, const int32_t *group,
                 unsigned long long rows, cudaStream_t s) {
@@ -509,7 +568,13 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
     g_launches++;
   }
-  if (grouped || c->m > 0) {
+  int slab_numeric = grouped ? 1 : 0;
+  if (grouped) {
+    const int rc = launch_group(c, sc, rows, s);  // N / lin / quad of every slot (and the row filter)
+    if (rc < 0) return rc;
+    if (rc == 0) slab_numeric = 0;
+  }
+  if ((grouped && slab_numeric) || c->m > 0) {
     // With hashed pair counts the scan is cut into slices so that the table can be grown
     // (host-side, between launches) before it could fill up.
     const int npairs = c->kind == CFB_TRIPLE ? c->m * (c->m - 1) / 2 : 0;
@@ -528,11 +593,11 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         int rc = hash_reserve(c, worst);
         if (rc) return rc;
       }
-      int need_generic = launch_slab(c, part, cnt, grouped ? 1 : 0, s);
+      int need_generic = launch_slab(c, part, cnt, slab_numeric, s);
       if (need_generic < 0) return need_generic;
       if (need_generic) {  // 1 = slab too large for this shape
         const int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
-        cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(part, c->d_lay, cnt, grouped ? 1 : 0, c->d_f64,
+        cfb::generic_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(part, c->d_lay, cnt, slab_numeric, c->d_f64,
                                                                      c->d_u64, c->d_err, c->hash);
         g_launches++;
       }

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256)
   for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
        r += (unsigned long long)gridDim.x * blockDim.x) {
     int g = cols.group ? cols.group[r] : 0;
-    if (g < 0 || g >= lay.n_groups) {
+    if (g < 0) continue;  // filtered row
+    if (g >= lay.n_groups) {
       atomicExch(err, 2);
       continue;
     }

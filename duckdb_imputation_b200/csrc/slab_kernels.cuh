@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kSlabThreads) slab_scan_kernel(const __grid_co
       int g = 0;
       if (a.cols.group) {
         g = a.cols.group[r];
-        if (g < 0 || g >= lay.n_groups) {
+        if (g < 0) continue;  // filtered row (e.g. WHERE col_IS_NULL IS FALSE)
+        if (g >= lay.n_groups) {
           atomicExch(a.err, 2);
           continue;
         }

@@ -102,7 +102,8 @@ int cfb_ctx_append(cfb_ctx *ctx, const float *const *num_cols, const uint32_t *c
 /* Same reduction for DEVICE-resident columnar (SoA) input: the device-resident
  * measurement path and the multi-GPU range partition.  Column pointers are
  * device pointers (16-byte aligned); d_group_slot is a device int32 array of
- * per-row slots or NULL.  `stream` is a cudaStream_t (NULL = the context's own
+ * per-row slots or NULL; a NEGATIVE slot drops the row (a filtered scan such as
+ * MICE's WHERE col_IS_NULL IS FALSE is n_groups = 1 with slots 0 / -1).  `stream` is a cudaStream_t (NULL = the context's own
  * stream).  Asynchronous: results are visible after cfb_ctx_sync/finalize.     */
 int cfb_triple_device(cfb_ctx *ctx, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                       const int32_t *d_group_slot, size_t n_rows, void *stream);

@@ -271,3 +271,32 @@ def test_mice_style_filtered_device_scan_via_group_slots():
     sel = np.nonzero(is_null == 0)[0].astype(np.uint32)
     assert_parity(got, oracle.aggregate_arrays(CFB_TRIPLE, hn, hc, sel=sel)[0], what="rows that pass the filter")
     assert got["N"] + nulls["N"] == rows
+
+
+@pytest.mark.parametrize("kind,n,m", [(CFB_TRIPLE, 20, 0), (CFB_TRIPLE, 6, 3), (CFB_NB, 12, 4), (CFB_TRIPLE, 32, 0), (CFB_TRIPLE, 0, 2)])
+def test_negative_slot_drops_the_row(kind, n, m):
+    """A filtered device scan is n_groups = 1 with slot 0 (keep) / -1 (drop)."""
+    torch = pytest.importorskip("torch")
+    rows = 200_003
+    dn, dc, hn, hc = _device_cols(torch, rows, n, m, seed=6, dom=9)
+    keep = synth.int32(rows, 99, lo=0, rng=5) != 0
+    dslot = torch.from_numpy(np.where(keep, 0, -1).astype(np.int32)).cuda()
+    with CofactorContext(kind, n, m) as ctx:
+        ctx.scan_device(dn, dc, rows, d_group=dslot)
+        got = ctx.finalize_arrays()
+    sel = np.nonzero(keep)[0].astype(np.uint32)
+    assert_parity(got, oracle.aggregate_arrays(kind, hn, hc, sel=sel)[0], what=f"filtered n={n} m={m}")
+
+
+def test_many_groups_fall_back_when_tables_do_not_fit():
+    torch = pytest.importorskip("torch")
+    rows, G = 100_000, 300  # 300 slots x 231 entries do not fit the warp-private tables
+    dn, dc, hn, hc = _device_cols(torch, rows, 20, 0, seed=8)
+    hg = synth.int32(rows, 555, lo=0, rng=G)
+    dg = torch.from_numpy(hg).cuda()
+    with CofactorContext(CFB_TRIPLE, 20, 0, n_groups=G) as ctx:
+        ctx.scan_device(dn, dc, rows, d_group=dg)
+        got = [ctx.finalize_arrays(g) for g in (0, 17, G - 1)]
+    ref = oracle.aggregate_arrays(CFB_TRIPLE, hn, hc, group=hg, n_groups=G)
+    for g, a in zip((0, 17, G - 1), got):
+        assert_parity(a, ref[g], what=f"group {g}")
