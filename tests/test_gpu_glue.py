@@ -90,3 +90,27 @@ def test_sum_of_lifted_matches_oracle(kind):
     lifted_ref = oracle.sum_of_lifted(kind, num, cat, group=slots.astype(np.int32), n_groups=len(labels))
     for a, b in zip(got, lifted_ref):
         assert_struct_parity(a, b, rtol=2e-4, what="vs fp32 restatement")
+
+
+def test_states_spread_over_devices_when_asked():
+    """CFB_DEVICES=all: the callbacks place aggregate states round-robin on the visible GPUs and
+    SumStateCombine merges them across devices.  (Runs in a subprocess: the policy is read once.)"""
+    import os, subprocess, sys
+    from duckdb_imputation_b200 import _native as nat
+    if nat.lib().cfb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    code = (
+        "import numpy as np\n"
+        "from duckdb_imputation_b200 import replay\n"
+        "from oracle import oracle\n"
+        "from tests.parity import assert_struct_parity\n"
+        "rng = np.random.default_rng(1); rows = 120_000\n"
+        "num = [rng.random(rows).astype(np.float32) for _ in range(6)]\n"
+        "cat = [rng.integers(0, 20, rows).astype(np.int32) for _ in range(2)]\n"
+        "got = replay.glue().query(0, num, cat, threads=4)\n"
+        "assert_struct_parity(got, oracle.aggregate(0, num, cat))\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CFB_DEVICES="all"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

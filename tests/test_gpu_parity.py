@@ -300,3 +300,20 @@ def test_many_groups_fall_back_when_tables_do_not_fit():
     ref = oracle.aggregate_arrays(CFB_TRIPLE, hn, hc, group=hg, n_groups=G)
     for g, a in zip((0, 17, G - 1), got):
         assert_parity(a, ref[g], what=f"group {g}")
+
+
+def test_cross_device_combine():
+    """cfb_ctx_combine across GPUs (peer copy of the source state), dense and hashed pair counts."""
+    if nat.lib().cfb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(33)
+    rows = 40_000
+    for dom in (15, 60_000):  # dense tables / hash fallback
+        num, cat = _table(rng, rows, 4, 2, dom=dom)
+        h = rows // 2
+        with CofactorContext(CFB_TRIPLE, 4, 2, device=0) as a, CofactorContext(CFB_TRIPLE, 4, 2, device=1) as b:
+            a.append([c[:h] for c in num], [c[:h] for c in cat])
+            b.append([c[h:] for c in num], [c[h:] for c in cat])
+            a.combine(b)
+            got = a.finalize_arrays()
+        assert_parity(got, oracle.aggregate_arrays(CFB_TRIPLE, num, cat)[0], what=f"cross-device dom={dom}")
