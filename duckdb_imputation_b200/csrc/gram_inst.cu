@@ -14,7 +14,7 @@ namespace cfb {
 template <int N, bool DIAG>
 cudaError_t gram_launch(const GramLaunchParams &p) {
   using S = GramShape<N, DIAG>;
-  constexpr int TR = GramTile<N>::kRows;
+  constexpr int TR = GramTile<N, DIAG>::kRows;
   const size_t fixed = gram_smem_bytes<N, DIAG>(0);
   const size_t per_stage = (size_t)N * TR * sizeof(float) + 2 * sizeof(uint64_t);
   if ((size_t)p.smem_optin < fixed + 2 * per_stage + 1024) return cudaErrorInvalidValue;

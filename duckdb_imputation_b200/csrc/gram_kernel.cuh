@@ -61,7 +61,8 @@ struct RoleGeom {
 template <int N, bool DIAG>
 struct GramShape {
   static constexpr int kRoles = DIAG ? 1 : (N <= 10 ? 1 : (N <= 20 ? 4 : 10));
-  static constexpr int kGroups = kRoles == 1 ? 8 : (kRoles == 4 ? 2 : 1);
+  // one role: 8 row groups (4 for the wide NB shapes, whose 1024-row stages would not fit twice)
+  static constexpr int kGroups = kRoles == 1 ? (N <= 16 ? 8 : 4) : (kRoles == 4 ? 2 : 1);
   static constexpr int kConsumerWarps = kRoles * kGroups;
   // 8 consumer warps = 2 warpgroups; the producer warp sits in a third warpgroup (3 idle warps)
   // so that setmaxnreg can move its registers to the consumers.
@@ -143,18 +144,22 @@ struct GramArgs {
   unsigned int *ticket;       // zero-initialised; reset by the last CTA
 };
 
-// rows per ring stage: narrow tables get longer tiles so a stage stays >= 8 KB
-template <int N>
-struct GramTile {
+// Rows per ring stage.  A tile is consumed in 128-row warp iterations split over kGroups row
+// groups, so kRows is a multiple of 128 * kGroups (no idle warps); narrow tables get longer tiles so
+// that a column chunk (one bulk copy) stays >= 2 KB; 768 rows measured best for the 4-role shape.
 #ifndef CFB_TR_WIDE
 #define CFB_TR_WIDE 768
 #endif
-  static constexpr int kRows = N <= 4 ? 2048 : (N <= 10 ? 1024 : (N <= 20 ? CFB_TR_WIDE : 512));  // multiple of 128 * kGroups
+template <int N, bool DIAG>
+struct GramTile {
+  static constexpr int kGroups = GramShape<N, DIAG>::kGroups;
+  static constexpr int kRows = kGroups == 8 ? (N <= 4 ? 2048 : 1024) : (kGroups == 4 ? 512 : (kGroups == 2 ? CFB_TR_WIDE : 512));
+  static_assert(kRows % (128 * kGroups) == 0, "tile must split evenly over the row groups");
 };
 
 template <int N, bool DIAG>
 __host__ __device__ constexpr size_t gram_smem_bytes(int stages) {
-  return (size_t)stages * N * GramTile<N>::kRows * sizeof(float) +
+  return (size_t)stages * N * GramTile<N, DIAG>::kRows * sizeof(float) +
          (size_t)GramShape<N, DIAG>::kGroups * GramShape<N, DIAG>::kOut * sizeof(double) +
          2 * (size_t)stages * sizeof(uint64_t);
 }
