@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -25,6 +26,7 @@
 
 #include "gram_launch.h"
 #include "group_kernel.cuh"
+#include "key_dict.cuh"
 #include "pair_hash.cuh"
 #include "slab_kernels.cuh"
 #include "slab_launch.h"
@@ -141,6 +143,14 @@ struct cfb_ctx {
   int *d_err = nullptr;
   int *d_minmax = nullptr;  // [2][kMaxCat]
   cfb::PairHash hash{};               // sparse pair counts (lay.pairs_hashed)
+  struct ColDict {                    // key dictionary of a wide-range categorical column (key_dict.cuh)
+    bool on = false;
+    cfb::KeyDict d{};
+    unsigned long long code_cap = 0;
+    int n_codes = 0;                  // host copy, exact after the last dictionary pass
+  } dict[cfb::kMaxCat];
+  int32_t *d_remap = nullptr;         // [dict columns][remap_rows] keys rewritten to codes (device scans)
+  size_t remap_rows = 0, remap_cap = 0;
   unsigned long long hash_upper = 0;  // host-side upper bound on occupied hash slots
   cudaStream_t stream = nullptr;
   cudaStream_t user_stream = nullptr;  // last caller-provided stream of cfb_triple_device
@@ -303,7 +313,7 @@ int hash_reserve(cfb_ctx *c, unsigned long long add) {
     cfb::PairHash nh;
     int rc = hash_alloc(&nh, pow2_at_least((exact + add) * 2), c->G, c->stream);
     if (rc) return rc;
-    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, nh, c->d_err);
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, nh, c->d_err, cfb::SlotTrans{});
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -316,10 +326,10 @@ int hash_reserve(cfb_ctx *c, unsigned long long add) {
 
 int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, double *df, unsigned long long *du,
                      const double *sf, const unsigned long long *su, const cfb::PairHash &dhash, int *d_err,
-                     cudaStream_t s) {
+                     cudaStream_t s, const cfb::SlotTrans &tr = cfb::SlotTrans{}) {
   const long long tot = (sl.F + sl.U) * sl.n_groups;
   const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
-  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su, dhash, d_err);
+  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su, dhash, d_err, tr);
   g_launches++;
   CU(cudaGetLastError());
   return CFB_OK;
@@ -335,15 +345,18 @@ long long dense_pair_entries(const Layout &L) {
 // Make the context's categorical domain cover [lo, hi] per column, re-laying out the state if
 // it has to grow (stream-ordered).  A grown domain may switch the pair counts from dense
 // tables to the hash table.
-int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) {
+int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false, const cfb::SlotTrans *rekey = nullptr) {
   if (c->m == 0) return CFB_OK;
   int nlo[cfb::kMaxCat], nhi[cfb::kMaxCat];
   bool grow = !c->lay.has_domain;
   for (int k = 0; k < c->m; k++) {
-    if (exact) {  // an untouched (fresh or recycled) context takes exactly the declared domain
+    if (exact || (rekey && rekey->col[k])) {
+      // an untouched (fresh or recycled) context takes exactly the declared domain; a column that
+      // is being re-keyed (dense -> dictionary codes) takes its new code range
       nlo[k] = lo[k];
       nhi[k] = hi[k];
       if (!c->lay.has_domain || c->lay.lo[k] != lo[k] || (long long)c->lay.lo[k] + c->lay.dom[k] - 1 != hi[k]) grow = true;
+      if (rekey && rekey->col[k]) grow = true;
     } else if (c->lay.has_domain) {
       const int clo = c->lay.lo[k], chi = (int)((long long)c->lay.lo[k] + c->lay.dom[k] - 1);
       nlo[k] = std::min(clo, lo[k]);
@@ -377,10 +390,11 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) 
   // carry the old contents over; an old state without a domain has only its numeric part
   // and N, which the remap handles because its tables are empty
   if (!exact) {
-    rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, nh, c->d_err, c->stream);
+    const cfb::SlotTrans tr = rekey ? *rekey : cfb::SlotTrans{};
+    rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, nh, c->d_err, c->stream, tr);
     if (rc) return rc;
     if (c->lay.pairs_hashed) {
-      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, d_nl, c->d_lay, nu, nh, c->d_err);
+      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, d_nl, c->d_lay, nu, nh, c->d_err, tr);
       g_launches++;
       CU(cudaGetLastError());
     }
@@ -397,6 +411,201 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false) 
   c->hash = nh;
   if (!nl.pairs_hashed || exact) c->hash_upper = 0;
   else if (!c->hash_upper) c->hash_upper = (nh.capacity - 2) / 2;  // dense -> hashed: unknown non-zero count
+  return CFB_OK;
+}
+
+// ---- key dictionaries ----------------------------------------------------------------
+// A categorical column switches to dictionary codes when its key range gets wider than this
+// (CFB_DICT_RANGE overrides; tests force it to 1).
+long long dict_range_limit() {
+  static const long long v = [] {
+    const char *e = getenv("CFB_DICT_RANGE");
+    return e ? atoll(e) : (1ll << 22);
+  }();
+  return v;
+}
+
+void dict_free(cfb_ctx::ColDict &cd) {
+  cudaFree(cd.d.table);
+  cudaFree(cd.d.keys_of_code);
+  cudaFree(cd.d.n_codes);
+  cd = cfb_ctx::ColDict{};
+}
+
+bool any_dict(const cfb_ctx *c) {
+  for (int k = 0; k < c->m; k++)
+    if (c->dict[k].on) return true;
+  return false;
+}
+
+// Room for `add` more distinct keys in column k's dictionary (table load <= 1/2).
+int dict_reserve(cfb_ctx *c, int k, unsigned long long add, cudaStream_t s) {
+  auto &cd = c->dict[k];
+  const unsigned long long need = (unsigned long long)cd.n_codes + add;
+  if (!cd.d.n_codes) {
+    CU(cudaMalloc(&cd.d.n_codes, sizeof(int)));
+    CU(cudaMemsetAsync(cd.d.n_codes, 0, sizeof(int), s));
+  }
+  if (need > cd.code_cap) {
+    const unsigned long long cap = pow2_at_least(need);
+    int *nk = nullptr;
+    CU(cudaMalloc(&nk, cap * sizeof(int)));
+    if (cd.n_codes) CU(cudaMemcpyAsync(nk, cd.d.keys_of_code, (size_t)cd.n_codes * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(cd.d.keys_of_code);
+    cd.d.keys_of_code = nk;
+    cd.code_cap = cap;
+  }
+  if (need * 2 > cd.d.capacity) {
+    cfb::KeyDict nd = cd.d;
+    nd.capacity = pow2_at_least(need * 2);
+    if (nd.capacity > (1ull << 31)) return fail(CFB_ERR_DOMAIN, "categorical column %d has too many distinct keys", k);
+    CU(cudaMalloc(&nd.table, nd.capacity * 8));
+    cfb::dict_clear_kernel<<<148 * 4, 256, 0, s>>>(nd.table, nd.capacity);
+    if (cd.d.capacity) cfb::dict_rehash_kernel<<<148 * 4, 256, 0, s>>>(cd.d, nd);
+    g_launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    cudaFree(cd.d.table);
+    cd.d = nd;
+  }
+  return CFB_OK;
+}
+
+int dict_read_counts(cfb_ctx *c, cudaStream_t s) {
+  for (int k = 0; k < c->m; k++)
+    if (c->dict[k].on) CU(cudaMemcpyAsync(&c->dict[k].n_codes, c->dict[k].d.n_codes, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return CFB_OK;
+}
+
+// Switch column k from dense slots (key - lo) to dictionary codes, carrying its contents over.
+int dict_enable(cfb_ctx *c, int k, cudaStream_t s) {
+  auto &cd = c->dict[k];
+  if (cd.on) return CFB_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  if (s != c->stream) CU(cudaStreamSynchronize(s));
+  cd.on = true;
+  const bool has_data = c->lay.has_domain && c->lay.dom[k] > 0;
+  int rc = dict_reserve(c, k, has_data ? (unsigned long long)c->lay.dom[k] : 1024, c->stream);
+  if (rc) return rc;
+  int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+  for (int j = 0; j < c->m; j++) {
+    lo[j] = c->lay.has_domain ? c->lay.lo[j] : 0;
+    hi[j] = c->lay.has_domain ? (int)((long long)c->lay.lo[j] + c->lay.dom[j] - 1) : 0;
+  }
+  if (!has_data) {
+    if (c->lay.has_domain) {  // (cannot happen: a domain implies dom >= 1) keep the layout consistent
+      lo[k] = hi[k] = 0;
+    }
+    return CFB_OK;
+  }
+  // codes for the keys that occurred so far, then re-key the column's slots through a translation
+  int *trans = nullptr;
+  const long long dom = c->lay.dom[k];
+  CU(cudaMalloc(&trans, dom * sizeof(int)));
+  const unsigned long long *counts = c->d_u64 + 1 + c->lay.cat_off[k];
+  const int blocks = (int)std::min<long long>((dom + 255) / 256, 148 * 4);
+  cfb::dict_translate_kernel<<<blocks, 256, 0, c->stream>>>(cd.d, nullptr, c->lay.lo[k], counts, c->lay.U, c->G, dom, trans, 0);
+  cfb::dict_translate_kernel<<<blocks, 256, 0, c->stream>>>(cd.d, nullptr, c->lay.lo[k], counts, c->lay.U, c->G, dom, trans, 1);
+  g_launches += 2;
+  CU(cudaGetLastError());
+  rc = dict_read_counts(c, c->stream);
+  if (rc) return rc;
+  lo[k] = 0;
+  hi[k] = std::max(cd.n_codes - 1, 0);
+  cfb::SlotTrans tr{};
+  tr.col[k] = trans;
+  rc = ensure_domain(c, lo, hi, false, &tr);
+  cudaFree(trans);
+  return rc;
+}
+
+// Before a scan of `rows` rows whose categorical columns live at cat[] on the device and span
+// [obs_lo, obs_hi]: switch wide columns to dictionaries, give new keys their codes, grow the
+// domain, and return in eff[] the columns the scan kernels should read (codes for dictionary
+// columns: rewritten in place when `in_place`, else into the context's remap buffer).
+int prepare_cats(cfb_ctx *c, const int32_t *const *cat, unsigned long long rows, cudaStream_t s, const int *obs_lo,
+                 const int *obs_hi, bool in_place, const int32_t **eff) {
+  const int m = c->m;
+  for (int k = 0; k < m; k++) eff[k] = cat[k];
+  if (m == 0 || rows == 0) return CFB_OK;
+  int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+  for (int k = 0; k < m; k++) {
+    lo[k] = obs_lo[k];
+    hi[k] = obs_hi[k];
+    if (!c->dict[k].on && !c->user_domain) {
+      long long l = lo[k], h = hi[k];
+      if (c->lay.has_domain) {
+        l = std::min<long long>(l, c->lay.lo[k]);
+        h = std::max<long long>(h, (long long)c->lay.lo[k] + c->lay.dom[k] - 1);
+      }
+      if (h - l + 1 > dict_range_limit()) {
+        int rc = dict_enable(c, k, s);
+        if (rc) return rc;
+      }
+    }
+  }
+  if (any_dict(c)) {
+    size_t n_dict = 0;
+    for (int k = 0; k < m; k++)
+      if (c->dict[k].on) {
+        int rc = dict_reserve(c, k, rows, s);
+        if (rc) return rc;
+        const int blocks = (int)std::min<unsigned long long>((rows + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
+        cfb::dict_insert_kernel<<<blocks, 256, 0, s>>>(c->dict[k].d, cat[k], rows);
+        g_launches++;
+        n_dict++;
+      }
+    CU(cudaGetLastError());
+    int rc = dict_read_counts(c, s);
+    if (rc) return rc;
+    if (!in_place) {
+      if ((size_t)rows * n_dict > c->remap_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(c->d_remap);
+        c->d_remap = nullptr;
+        CU(cudaMalloc(&c->d_remap, (size_t)rows * n_dict * sizeof(int32_t)));
+        c->remap_cap = (size_t)rows * n_dict;
+      }
+      c->remap_rows = rows;
+    }
+    size_t j = 0;
+    for (int k = 0; k < m; k++)
+      if (c->dict[k].on) {
+        int32_t *dst = in_place ? const_cast<int32_t *>(cat[k]) : c->d_remap + j * c->remap_rows;
+        const int blocks = (int)std::min<unsigned long long>((rows + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
+        cfb::dict_remap_kernel<<<blocks, 256, 0, s>>>(c->dict[k].d, cat[k], dst, rows);
+        g_launches++;
+        eff[k] = dst;
+        lo[k] = 0;
+        hi[k] = std::max(c->dict[k].n_codes - 1, 0);
+        j++;
+      }
+    CU(cudaGetLastError());
+  }
+  if (!c->user_domain) return ensure_domain(c, lo, hi);
+  return CFB_OK;
+}
+
+// Host keys of dictionary column k -> codes (in place), inserting new keys (lifted-triple path).
+int dict_codes_for_host_keys(cfb_ctx *c, int k, std::vector<int32_t> &keys) {
+  if (keys.empty()) return CFB_OK;
+  cudaStream_t s = c->stream;
+  int rc = dict_reserve(c, k, keys.size(), s);
+  if (rc) return rc;
+  int32_t *d = nullptr;
+  CU(cudaMalloc(&d, keys.size() * sizeof(int32_t)));
+  CU(cudaMemcpyAsync(d, keys.data(), keys.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  const int blocks = (int)std::min<size_t>((keys.size() + 255) / 256, 148 * 4);
+  cfb::dict_insert_kernel<<<blocks, 256, 0, s>>>(c->dict[k].d, d, keys.size());
+  cfb::dict_remap_kernel<<<blocks, 256, 0, s>>>(c->dict[k].d, d, d, keys.size());
+  g_launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(keys.data(), d, keys.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&c->dict[k].n_codes, c->dict[k].d.n_codes, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  cudaFree(d);
   return CFB_OK;
 }
 
@@ -647,10 +856,6 @@ int flush_tile(cfb_ctx *c) {
   if (!c->fill) return CFB_OK;
   Stage &st = c->st[c->cur];
   const size_t rows = c->fill, tr = c->tile_rows, ncol = stage_cols(c);
-  if (c->m > 0 && !c->user_domain) {
-    int rc = ensure_domain(c, c->st_lo, c->st_hi);
-    if (rc) return rc;
-  }
   _mm_sfence();  // the staging tile was filled with non-temporal stores
   if (rows == tr) {
     CU(cudaMemcpyAsync(st.d, st.h, tr * 4 * (ncol - (c->uses_group ? 0 : 1)), cudaMemcpyHostToDevice, c->stream));
@@ -665,7 +870,11 @@ int flush_tile(cfb_ctx *c) {
   for (int k = 0; k < c->n; k++) num[k] = (const float *)(st.d + (size_t)k * tr * 4);
   for (int k = 0; k < c->m; k++) cat[k] = (const int32_t *)(st.d + (size_t)(c->n + k) * tr * 4);
   const int32_t *grp = c->uses_group ? (const int32_t *)(st.d + (size_t)(c->n + c->m) * tr * 4) : nullptr;
-  int rc = scan_device(c, num, cat, grp, rows, c->stream);
+  // domain growth / key dictionaries for this tile's keys (the tile is ours: codes are written in place)
+  const int32_t *eff[cfb::kMaxCat];
+  int rc = prepare_cats(c, cat, rows, c->stream, c->st_lo, c->st_hi, /*in_place=*/true, eff);
+  if (rc) return rc;
+  rc = scan_device(c, num, eff, grp, rows, c->stream);
   if (rc) return rc;
   CU(cudaEventRecord(st.done, c->stream));
   st.in_flight = true;
@@ -796,7 +1005,8 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   // recycle: zero the state (its layout, i.e. the categorical domain seen so far, is kept: keys
   // that do not occur again have count 0 and are not emitted) and park the context
   const long long state_bytes = (c->lay.F + c->lay.U) * c->lay.n_groups * 8;
-  if (c->stream && c->d_f64 && state_bytes <= CtxPool::kMaxStateBytes && !c->lay.pairs_hashed && !getenv("CFB_NO_CTX_POOL")) {
+  if (c->stream && c->d_f64 && state_bytes <= CtxPool::kMaxStateBytes && !c->lay.pairs_hashed && !any_dict(c) &&
+      !getenv("CFB_NO_CTX_POOL")) {
     bool ok = cudaMemsetAsync(c->d_f64, 0, std::max<long long>(8, c->lay.F * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
               cudaMemsetAsync(c->d_u64, 0, std::max<long long>(8, c->lay.U * c->lay.n_groups * 8), c->stream) == cudaSuccess &&
               cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream) == cudaSuccess &&
@@ -816,6 +1026,9 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);
   if (c->hash.capacity) hash_free(c->hash);
+  for (auto &cd : c->dict)
+    if (cd.on || cd.d.table) dict_free(cd);
+  cudaFree(c->d_remap);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -947,6 +1160,40 @@ int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const flo
   if (m > 0 && !c->user_domain && !ent.empty()) {
     for (int k = 0; k < m; k++)
       if (lo[k] > hi[k]) lo[k] = hi[k] = c->lay.has_domain ? c->lay.lo[k] : 0;
+    // wide-range columns: switch to dictionary codes and rewrite this chunk's keys
+    for (int k = 0; k < m; k++) {
+      if (!c->dict[k].on) {
+        long long l = lo[k], h = hi[k];
+        if (c->lay.has_domain) {
+          l = std::min<long long>(l, c->lay.lo[k]);
+          h = std::max<long long>(h, (long long)c->lay.lo[k] + c->lay.dom[k] - 1);
+        }
+        if (h - l + 1 > dict_range_limit()) {
+          rc = dict_enable(c, k, c->stream);
+          if (rc) return rc;
+        }
+      }
+      if (!c->dict[k].on) continue;
+      std::vector<int32_t> keys;
+      std::vector<std::pair<size_t, int>> where;  // (entry, 1 = key1 / 2 = key2)
+      for (size_t i = 0; i < ent.size(); i++) {
+        const int tag = ent[i].tag;
+        if (tag < 64 ? tag == k : (tag < 2048 ? (tag - 64) % 32 == k : (tag - 2048) / 32 == k)) {
+          keys.push_back(ent[i].key1);
+          where.emplace_back(i, 1);
+        }
+        if (tag >= 2048 && (tag - 2048) % 32 == k) {
+          keys.push_back(ent[i].key2);
+          where.emplace_back(i, 2);
+        }
+      }
+      rc = dict_codes_for_host_keys(c, k, keys);
+      if (rc) return rc;
+      for (size_t j = 0; j < where.size(); j++)
+        (where[j].second == 1 ? ent[where[j].first].key1 : ent[where[j].first].key2) = keys[j];
+      lo[k] = 0;
+      hi[k] = std::max(c->dict[k].n_codes - 1, 0);
+    }
     rc = ensure_domain(c, lo, hi);
     if (rc) return rc;
   }
@@ -989,15 +1236,25 @@ int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t 
   CU(cudaSetDevice(c->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   if (stream) c->user_stream = s;
-  if (c->m > 0 && !c->user_domain && n_rows > 0) {
-    // no declared domain: one extra pass finds [min,max] of every categorical column
+  if (c->m == 0 || c->user_domain || n_rows == 0) return scan_device(c, d_num_cols, d_cat_cols, d_group_slot, n_rows, s);
+  // No declared domain: one extra pass per slice finds [min,max] of every categorical column (and
+  // feeds the key dictionaries of wide-range columns); slices bound the dictionary scratch.
+  const size_t slice = (size_t)1 << 26;
+  for (size_t r0 = 0; r0 < n_rows; r0 += slice) {
+    const size_t cnt = std::min(slice, n_rows - r0);
+    const float *num[CFB_MAX_NUM];
+    const int32_t *cat[cfb::kMaxCat], *eff[cfb::kMaxCat];
+    for (int k = 0; k < c->n; k++) num[k] = d_num_cols[k] + r0;
+    for (int k = 0; k < c->m; k++) cat[k] = d_cat_cols[k] + r0;
     int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
-    int rc = cfb_cat_minmax_device(c->device, d_cat_cols, c->m, n_rows, lo, hi, s);
+    int rc = cfb_cat_minmax_device(c->device, cat, c->m, cnt, lo, hi, s);
     if (rc) return rc;
-    rc = ensure_domain(c, lo, hi);
+    rc = prepare_cats(c, cat, cnt, s, lo, hi, /*in_place=*/false, eff);
+    if (rc) return rc;
+    rc = scan_device(c, num, eff, d_group_slot ? d_group_slot + r0 : nullptr, cnt, s);
     if (rc) return rc;
   }
-  return scan_device(c, d_num_cols, d_cat_cols, d_group_slot, n_rows, s);
+  return CFB_OK;
 }
 
 int cfb_ctx_sync(cfb_ctx *c) {
@@ -1031,17 +1288,6 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
   dst->touched = true;
   rc = flush_tile(dst);
   if (rc) return rc;
-  if (src->m > 0 && !src->lay.has_domain) {
-    // src never saw a categorical key: only N / lin / quad can be non-zero, handled below
-  } else if (src->m > 0) {
-    int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
-    for (int k = 0; k < src->m; k++) {
-      lo[k] = src->lay.lo[k];
-      hi[k] = (int)((long long)src->lay.lo[k] + src->lay.dom[k] - 1);
-    }
-    rc = ensure_domain(dst, lo, hi);
-    if (rc) return rc;
-  }
   const double *sf = src->d_f64;
   const unsigned long long *su = src->d_u64;
   const Layout *sl = src->d_lay;
@@ -1061,6 +1307,64 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
     sf = tf;
     su = tu;
     sl = tl;
+  }
+  cfb::SlotTrans tr{};
+  std::vector<void *> scratch;  // translation arrays and staged dictionaries, freed at the end
+  if (src->m > 0 && src->lay.has_domain) {
+    int lo[cfb::kMaxCat], hi[cfb::kMaxCat];
+    for (int k = 0; k < src->m; k++) {
+      lo[k] = src->lay.lo[k];
+      hi[k] = (int)((long long)src->lay.lo[k] + src->lay.dom[k] - 1);
+      // a column keyed by a dictionary on either side (or too wide once united) is merged by KEY:
+      // dst gets a dictionary, and the source's slots are translated to dst codes
+      bool by_key = src->dict[k].on || dst->dict[k].on;
+      if (!by_key && dst->lay.has_domain && !dst->user_domain) {
+        const long long l = std::min<long long>(lo[k], dst->lay.lo[k]);
+        const long long h = std::max<long long>(hi[k], (long long)dst->lay.lo[k] + dst->lay.dom[k] - 1);
+        by_key = h - l + 1 > dict_range_limit();
+      } else if (!by_key && !dst->user_domain) {
+        by_key = (long long)hi[k] - lo[k] + 1 > dict_range_limit();
+      }
+      if (!by_key) continue;
+      rc = dict_enable(dst, k, dst->stream);
+      if (rc) return rc;
+      const long long n_slots = src->dict[k].on ? src->dict[k].n_codes : src->lay.dom[k];
+      if (n_slots == 0) {
+        lo[k] = 0;
+        hi[k] = std::max(dst->dict[k].n_codes - 1, 0);
+        continue;
+      }
+      const int *keys_src = nullptr;
+      if (src->dict[k].on) {
+        keys_src = src->dict[k].d.keys_of_code;
+        if (src->device != dst->device) {
+          int *tmp = nullptr;
+          CU(cudaMalloc(&tmp, n_slots * sizeof(int)));
+          CU(cudaMemcpyPeerAsync(tmp, dst->device, keys_src, src->device, n_slots * sizeof(int), dst->stream));
+          scratch.push_back(tmp);
+          keys_src = tmp;
+        }
+      }
+      rc = dict_reserve(dst, k, (unsigned long long)n_slots, dst->stream);
+      if (rc) return rc;
+      int *trans = nullptr;
+      CU(cudaMalloc(&trans, n_slots * sizeof(int)));
+      scratch.push_back(trans);
+      const unsigned long long *counts = su + 1 + src->lay.cat_off[k];
+      const int blocks = (int)std::min<long long>((n_slots + 255) / 256, 148 * 4);
+      for (int phase = 0; phase < 2; phase++)
+        cfb::dict_translate_kernel<<<blocks, 256, 0, dst->stream>>>(dst->dict[k].d, keys_src, src->lay.lo[k], counts, src->lay.U,
+                                                                   src->G, n_slots, trans, phase);
+      g_launches += 2;
+      CU(cudaGetLastError());
+      rc = dict_read_counts(dst, dst->stream);
+      if (rc) return rc;
+      tr.col[k] = trans;
+      lo[k] = 0;
+      hi[k] = std::max(dst->dict[k].n_codes - 1, 0);
+    }
+    rc = ensure_domain(dst, lo, hi);
+    if (rc) return rc;
   }
   // pairs of the source that may be new to dst: its hash entries, or its dense non-zeros
   cfb::PairHash shash = src->hash, thash{};
@@ -1085,10 +1389,10 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
     CU(cudaMemcpyPeerAsync(thash.counts, dst->device, src->hash.counts, src->device, bytes, dst->stream));
     shash = thash;
   }
-  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->hash, dst->d_err, dst->stream);
+  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->hash, dst->d_err, dst->stream, tr);
   if (rc) return rc;
   if (src->lay.pairs_hashed) {
-    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, dst->stream>>>(shash, dst->d_lay, sl, dst->d_u64, dst->hash, dst->d_err);
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, dst->stream>>>(shash, dst->d_lay, sl, dst->d_u64, dst->hash, dst->d_err, tr);
     g_launches++;
     CU(cudaGetLastError());
   }
@@ -1098,6 +1402,7 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
   cudaFree(tl);
   cudaFree(thash.keys);
   cudaFree(thash.counts);
+  for (void *p : scratch) cudaFree(p);
   return CFB_OK;
 }
 
@@ -1127,17 +1432,30 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
   };
   out->lin = dupv(std::vector<double>(f.begin(), f.begin() + n));
   out->quad = dupv(std::vector<double>(f.begin() + n, f.begin() + n + L.nq));
-  // keys that occurred, ascending per column: the iteration order of the reference's std::map
+  // keys that occurred, ascending per column: the iteration order of the reference's std::map.
+  // Dense columns: key = lo + slot (already ascending); dictionary columns: key = keys_of_code[slot],
+  // sorted here.
   std::vector<int32_t> keys;
   std::vector<int64_t> counts, offs(m + 1, 0), dense_t;
+  std::vector<std::vector<int32_t>> koc(m);  // keys of codes, dictionary columns only
+  for (int k = 0; k < m; k++)
+    if (c->dict[k].on && c->dict[k].n_codes > 0) {
+      koc[k].resize(c->dict[k].n_codes);
+      CU(cudaMemcpyAsync(koc[k].data(), c->dict[k].d.keys_of_code, koc[k].size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+  CU(cudaStreamSynchronize(c->stream));
+  auto key_of = [&](int col, long long slot) -> int32_t {
+    return c->dict[col].on ? koc[col][(size_t)slot] : (int32_t)((long long)L.lo[col] + slot);
+  };
   for (int k = 0; k < m; k++) {
-    for (int s = 0; s < L.dom[k]; s++) {
-      const unsigned long long cnt = u[1 + L.cat_off[k] + s];
-      if (cnt) {
-        keys.push_back((int32_t)((long long)L.lo[k] + s));
-        counts.push_back((int64_t)cnt);
-        dense_t.push_back(L.cat_off[k] + s);
-      }
+    std::vector<std::pair<int32_t, int>> occ;  // (key, slot)
+    for (int s = 0; s < L.dom[k]; s++)
+      if (u[1 + L.cat_off[k] + s] && (!c->dict[k].on || s < (int)koc[k].size())) occ.emplace_back(key_of(k, s), s);
+    if (c->dict[k].on) std::sort(occ.begin(), occ.end());
+    for (const auto &ks : occ) {
+      keys.push_back(ks.first);
+      counts.push_back((int64_t)u[1 + L.cat_off[k] + ks.second]);
+      dense_t.push_back(L.cat_off[k] + ks.second);
     }
     offs[k + 1] = (int64_t)keys.size();
   }
@@ -1191,10 +1509,14 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
         } else if (L.pairs_hashed) {
           auto range = std::equal_range(hashed.begin(), hashed.end(), HashedPair{k * m + l, 0, 0, 0},
                                         [](const HashedPair &a, const HashedPair &b) { return a.pair < b.pair; });
-          for (auto it = range.first; it != range.second; ++it) {
-            k1.push_back((int32_t)((long long)L.lo[k] + it->sk));
-            k2.push_back((int32_t)((long long)L.lo[l] + it->sl));
-            pc.push_back((int64_t)it->count);
+          std::vector<std::tuple<int32_t, int32_t, int64_t>> lst;
+          for (auto it = range.first; it != range.second; ++it)
+            lst.emplace_back(key_of(k, it->sk), key_of(l, it->sl), (int64_t)it->count);
+          if (c->dict[k].on || c->dict[l].on) std::sort(lst.begin(), lst.end());
+          for (const auto &e : lst) {
+            k1.push_back(std::get<0>(e));
+            k2.push_back(std::get<1>(e));
+            pc.push_back(std::get<2>(e));
           }
         } else {
           const unsigned long long *tab = u.data() + L.pair_base + L.pair_off[k * m + l];
@@ -1249,7 +1571,8 @@ int cfb_ctx_partial_sizes(cfb_ctx *c, size_t *n_f64, size_t *n_u64) {
 
 int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
-  if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
+  if (c->lay.pairs_hashed || any_dict(c))
+    return fail(CFB_ERR_DOMAIN, "sparse state (hashed pair counts / key dictionaries) has no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
   int rc = flush_tile(c);
   if (rc) return rc;
@@ -1265,7 +1588,8 @@ int cfb_ctx_export_partial(cfb_ctx *c, void *d_f64, void *d_u64, void *stream) {
 
 int cfb_ctx_import_partial(cfb_ctx *c, const void *d_f64, const void *d_u64, void *stream) {
   if (!c || !d_f64 || !d_u64) return fail(CFB_ERR_INVALID, "NULL argument");
-  if (c->lay.pairs_hashed) return fail(CFB_ERR_DOMAIN, "sparse (hashed) pair counts have no dense partial: combine with cfb_ctx_combine");
+  if (c->lay.pairs_hashed || any_dict(c))
+    return fail(CFB_ERR_DOMAIN, "sparse state (hashed pair counts / key dictionaries) has no dense partial: combine with cfb_ctx_combine");
   CU(cudaSetDevice(c->device));
   int rc = flush_tile(c);
   if (rc) return rc;

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     remap_add_kernel(const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g, double *__restrict__ df,
                      unsigned long long *__restrict__ du, const double *__restrict__ sf,
-                     const unsigned long long *__restrict__ su, const PairHash dhash, int *__restrict__ err) {
+                     const unsigned long long *__restrict__ su, const PairHash dhash, int *__restrict__ err,
+                     const SlotTrans tr) {
   __shared__ Layout dl, sl;
   {
     const int *a = reinterpret_cast<const int *>(dl_g), *b = reinterpret_cast<const int *>(sl_g);
@@ -146,7 +147,9 @@ __global__ void __launch_bounds__(256)
         const long long q = o - sl.numcat_base, i = q / sl.total_dom, t = q % sl.total_dom;
         int c = 0;
         while (c + 1 < m && t >= sl.cat_off[c + 1]) c++;
-        const long long slot = t - sl.cat_off[c] + (sl.lo[c] - dl.lo[c]);
+        const long long ss = t - sl.cat_off[c];
+        const long long slot = tr.col[c] ? (long long)tr.col[c][ss] : ss + (sl.lo[c] - dl.lo[c]);
+        if (slot < 0) continue;
         d = dl.numcat_base + i * dl.total_dom + dl.cat_off[c] + slot;
       }
       df[g * dl.F + d] += v;
@@ -161,7 +164,10 @@ __global__ void __launch_bounds__(256)
         const long long t = o - 1;
         int c = 0;
         while (c + 1 < m && t >= sl.cat_off[c + 1]) c++;
-        d = 1 + dl.cat_off[c] + (t - sl.cat_off[c]) + (sl.lo[c] - dl.lo[c]);
+        const long long ss = t - sl.cat_off[c];
+        const long long slot = tr.col[c] ? (long long)tr.col[c][ss] : ss + (sl.lo[c] - dl.lo[c]);
+        if (slot < 0) continue;
+        d = 1 + dl.cat_off[c] + slot;
       } else {
         const long long q = o - sl.pair_base;
         int k = 0, l = 1;
@@ -173,7 +179,10 @@ __global__ void __launch_bounds__(256)
               l = b;
             }
         const long long w = q - sl.pair_off[k * m + l];
-        const long long sk = w / sl.dom[l] + (sl.lo[k] - dl.lo[k]), s2 = w % sl.dom[l] + (sl.lo[l] - dl.lo[l]);
+        const long long wk = w / sl.dom[l], wl = w % sl.dom[l];
+        const long long sk = tr.col[k] ? (long long)tr.col[k][wk] : wk + (sl.lo[k] - dl.lo[k]);
+        const long long s2 = tr.col[l] ? (long long)tr.col[l][wl] : wl + (sl.lo[l] - dl.lo[l]);
+        if (sk < 0 || s2 < 0) continue;
         if (dl.pairs_hashed) {
           if (!pair_hash_add(dhash, g, pair_key(k * m + l, sk, s2), v)) atomicExch(err, 3);
           continue;
@@ -191,7 +200,8 @@ __global__ void __launch_bounds__(256)
 // a domain change: combine, domain growth and hash-table growth all go through here.
 __global__ void __launch_bounds__(256)
     pair_hash_drain_kernel(const PairHash src, const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g,
-                           unsigned long long *__restrict__ du, const PairHash dhash, int *__restrict__ err) {
+                           unsigned long long *__restrict__ du, const PairHash dhash, int *__restrict__ err,
+                           const SlotTrans tr) {
   __shared__ int s_dlo[kMaxCat], s_slo[kMaxCat], s_ddom[kMaxCat];
   __shared__ long long s_poff[kMaxCat * kMaxCat];
   __shared__ int s_m, s_G, s_dhashed;
@@ -221,8 +231,10 @@ __global__ void __launch_bounds__(256)
     const long long g = (long long)(i / src.capacity);
     const int p = (int)(key >> (2 * kPairSlotBits));
     const int k = p / s_m, l = p % s_m;
-    const long long sk = (long long)((key >> kPairSlotBits) & slot_mask) + (s_slo[k] - s_dlo[k]);
-    const long long sl2 = (long long)(key & slot_mask) + (s_slo[l] - s_dlo[l]);
+    const long long wk = (long long)((key >> kPairSlotBits) & slot_mask), wl = (long long)(key & slot_mask);
+    const long long sk = tr.col[k] ? (long long)tr.col[k][wk] : wk + (s_slo[k] - s_dlo[k]);
+    const long long sl2 = tr.col[l] ? (long long)tr.col[l][wl] : wl + (s_slo[l] - s_dlo[l]);
+    if (sk < 0 || sl2 < 0) continue;
     if (s_dhashed) {
       if (!pair_hash_add(dhash, g, pair_key(p, sk, sl2), v)) atomicExch(err, 3);
     } else {

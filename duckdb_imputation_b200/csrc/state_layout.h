@@ -29,6 +29,12 @@ struct Layout {
   long long pair_off[kMaxCat * kMaxCat];  // [k*m + l], k < l, relative to pair_base
 };
 
+// Optional per-column slot translation for remaps between states whose columns are keyed
+// differently (key dictionaries): dst slot = col[c] ? col[c][src slot] : src slot + (lo_src - lo_dst).
+struct SlotTrans {
+  const int *col[kMaxCat];
+};
+
 // Device column pointers of one scan (SoA input).
 struct ScanCols {
   const float *num[32];
