@@ -39,7 +39,7 @@ typedef enum cfb_status {
   CFB_ERR_NO_DEVICE = -2, /* no CUDA device or driver; never falls back to CPU */
   CFB_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed              */
   CFB_ERR_OOM = -4,       /* host or device allocation failed                  */
-  CFB_ERR_DOMAIN = -5,    /* categorical domain too large for the dense path   */
+  CFB_ERR_DOMAIN = -5,    /* key outside a declared domain / state too large / no dense partial */
   CFB_ERR_STATE = -6      /* call sequence violation (e.g. append after free)  */
 } cfb_status;
 
