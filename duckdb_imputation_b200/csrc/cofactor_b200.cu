@@ -92,15 +92,23 @@ struct Stage {
 };
 
 // Staging buffers (pinned host + device twin) are recycled across contexts: pinning memory costs
-// milliseconds, and a DuckDB query creates one state per worker thread (and per group).
-constexpr size_t kStageBytes = 16u << 20;
+// milliseconds, and a DuckDB query creates one state per worker thread (and per group).  Three
+// size classes: a lone aggregate gets 16 MB tiles (PCIe-efficient), a GROUP BY with hundreds of
+// live states gets 1 MB tiles so that pinned memory stays bounded.
+constexpr size_t kStageBytesClass[3] = {16u << 20, 4u << 20, 1u << 20};
 struct StagePool {
   std::mutex mu;
-  std::vector<Stage> free_list[64];
+  std::vector<Stage> free_list[64][3];
+  int live[64] = {0};  // stages handed out per device
+  static int class_of(size_t bytes) { return bytes == kStageBytesClass[0] ? 0 : (bytes == kStageBytesClass[1] ? 1 : 2); }
   int acquire(int device, Stage *out) {
+    int cls;
     {
       std::lock_guard<std::mutex> g(mu);
-      auto &fl = free_list[device & 63];
+      const int n = live[device & 63];
+      cls = n < 32 ? 0 : (n < 256 ? 1 : 2);
+      live[device & 63]++;
+      auto &fl = free_list[device & 63][cls];
       if (!fl.empty()) {
         *out = fl.back();
         fl.pop_back();
@@ -108,13 +116,15 @@ struct StagePool {
       }
     }
     Stage s;
-    s.bytes = kStageBytes;
+    s.bytes = kStageBytesClass[cls];
     cudaError_t e = cudaHostAlloc((void **)&s.h, s.bytes, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s.d, s.bytes);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       if (s.h) cudaFreeHost(s.h);
       if (s.d) cudaFree(s.d);
+      std::lock_guard<std::mutex> g(mu);
+      live[device & 63]--;
       return fail(e == cudaErrorMemoryAllocation ? CFB_ERR_OOM : CFB_ERR_CUDA, "staging allocation: %s", cudaGetErrorString(e));
     }
     *out = s;
@@ -124,7 +134,8 @@ struct StagePool {
     if (!s.h) return;
     s.in_flight = false;
     std::lock_guard<std::mutex> g(mu);
-    free_list[device & 63].push_back(s);
+    live[device & 63]--;
+    free_list[device & 63][class_of(s.bytes)].push_back(s);
     s = Stage{};
   }
 };
@@ -182,8 +193,8 @@ namespace {
 struct CtxPool {
   std::mutex mu;
   std::vector<cfb_ctx *> idle;
-  static constexpr size_t kMaxIdle = 256;
-  static constexpr long long kMaxStateBytes = 64ll << 20;
+  static constexpr size_t kMaxIdle = 128;
+  static constexpr long long kMaxStateBytes = 8ll << 20;
   cfb_ctx *take(int device, int kind, int n, int m, int G) {
     std::lock_guard<std::mutex> g(mu);
     for (size_t i = 0; i < idle.size(); i++) {
@@ -835,13 +846,13 @@ size_t stage_cols(const cfb_ctx *c) { return (size_t)c->n + c->m + 1; }
 
 int ensure_staging(cfb_ctx *c) {
   if (c->tile_rows) return CFB_OK;
-  size_t rows = kStageBytes / (4 * stage_cols(c));
-  if (const char *e = getenv("CFB_STAGE_ROWS")) rows = std::min<size_t>(rows, (size_t)std::max(1ll, atoll(e)));
-  rows = std::max<size_t>(1024, rows / 1024 * 1024);
   for (int i = 0; i < 2; i++) {
     int rc = g_stage_pool.acquire(c->device, &c->st[i]);
     if (rc) return rc;
   }
+  size_t rows = std::min(c->st[0].bytes, c->st[1].bytes) / (4 * stage_cols(c));
+  if (const char *e = getenv("CFB_STAGE_ROWS")) rows = std::min<size_t>(rows, (size_t)std::max(1ll, atoll(e)));
+  rows = std::max<size_t>(256, rows / 256 * 256);
   c->tile_rows = rows;
   c->fill = 0;
   for (int k = 0; k < c->m; k++) {
