@@ -97,6 +97,20 @@ int main(int argc, char **argv) {
     float ms = time([&] { ldg_stream<<<grid, 512>>>(cols, ncols, rows, sink); });
     printf("ldg.128 x4 grid=%4d : %7.3f ms %7.1f GB/s\n", grid, ms, gb / ms * 1e3);
   }
+  // sustained: 12 back-to-back launches of the best feed configurations (power-capped regime)
+  for (int tr : {768, 1024}) {
+    const int stages = tr == 768 ? 3 : 2;
+    const size_t smem = (size_t)stages * ncols * tr * 4 + 2 * stages * 8;
+    bulk_ring<<<sms, 288, smem>>>(cols, ncols, rows, tr, stages, 0, sink);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    for (int i = 0; i < 12; i++) bulk_ring<<<sms, 288, smem>>>(cols, ncols, rows, tr, stages, 0, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms12;
+    cudaEventElapsedTime(&ms12, e0, e1);
+    printf("sustained x12: bulk tr=%d stages=%d (single issuing thread): %7.3f ms per launch %7.1f GB/s\n", tr, stages, ms12 / 12, gb / (ms12 / 12) * 1e3);
+  }
   // copy baseline (what MEASURED_PEAKS counts: read+write bytes)
   float ms = time([&] { cudaMemcpyAsync((void *)cols.p[1], cols.p[0], rows * 4, cudaMemcpyDeviceToDevice); });
   printf("cudaMemcpy D2D %.3f ms -> %.1f GB/s (read+write)\n", ms, 2.0 * rows * 4 / 1e9 / ms * 1e3);
