@@ -54,6 +54,7 @@ SIGNATURES = {
     "cfb_triple_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "cfb_ctx_sync": (C.c_int, [_P]),
     "cfb_ctx_combine": (C.c_int, [_P, _P]),
+    "cfb_ctx_combine_slots": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cfb_ctx_finalize": (C.c_int, [_P, C.c_int, C.POINTER(Result)]),
     "cfb_result_free": (None, [C.POINTER(Result)]),
     "cfb_ctx_partial_sizes": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

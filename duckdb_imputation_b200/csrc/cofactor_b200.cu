@@ -324,7 +324,7 @@ int hash_reserve(cfb_ctx *c, unsigned long long add) {
     cfb::PairHash nh;
     int rc = hash_alloc(&nh, pow2_at_least((exact + add) * 2), c->G, c->stream);
     if (rc) return rc;
-    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, nh, c->d_err, cfb::SlotTrans{});
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, nh, c->d_err, cfb::SlotTrans{}, nullptr, c->G);
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -337,10 +337,10 @@ int hash_reserve(cfb_ctx *c, unsigned long long add) {
 
 int launch_remap_add(const Layout *d_dl, const Layout *d_sl, const Layout &sl, double *df, unsigned long long *du,
                      const double *sf, const unsigned long long *su, const cfb::PairHash &dhash, int *d_err,
-                     cudaStream_t s, const cfb::SlotTrans &tr = cfb::SlotTrans{}) {
+                     cudaStream_t s, const cfb::SlotTrans &tr = cfb::SlotTrans{}, const int *group_map = nullptr) {
   const long long tot = (sl.F + sl.U) * sl.n_groups;
   const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
-  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su, dhash, d_err, tr);
+  cfb::remap_add_kernel<<<std::max(blocks, 1), 256, 0, s>>>(d_dl, d_sl, df, du, sf, su, dhash, d_err, tr, group_map);
   g_launches++;
   CU(cudaGetLastError());
   return CFB_OK;
@@ -405,7 +405,7 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false, 
     rc = launch_remap_add(d_nl, c->d_lay, c->lay, nf, nu, c->d_f64, c->d_u64, nh, c->d_err, c->stream, tr);
     if (rc) return rc;
     if (c->lay.pairs_hashed) {
-      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, d_nl, c->d_lay, nu, nh, c->d_err, tr);
+      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, d_nl, c->d_lay, nu, nh, c->d_err, tr, nullptr, c->G);
       g_launches++;
       CU(cudaGetLastError());
     }
@@ -1287,12 +1287,31 @@ double cfb_last_scan_ms(cfb_ctx *c) {
   return (double)ms;
 }
 
-int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
+int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src) {
+  if (dst && src && dst->G != src->G) return fail(CFB_ERR_INVALID, "combine: group counts differ (use cfb_ctx_combine_slots)");
+  return cfb_ctx_combine_slots(dst, src, 0, nullptr, nullptr);
+}
+
+int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src_c, size_t n_pairs, const int32_t *dst_slots,
+                          const int32_t *src_slots) {
   cfb_ctx *src = const_cast<cfb_ctx *>(src_c);
   if (!dst || !src) return fail(CFB_ERR_INVALID, "ctx is NULL");
   if (dst == src) return fail(CFB_ERR_INVALID, "cannot combine a context with itself");
-  if (dst->kind != src->kind || dst->n != src->n || dst->m != src->m || dst->G != src->G)
-    return fail(CFB_ERR_INVALID, "combine: shapes differ");
+  if (dst->kind != src->kind || dst->n != src->n || dst->m != src->m) return fail(CFB_ERR_INVALID, "combine: shapes differ");
+  // slot map: dst slot of every src slot (-1 = not combined); identity when no pairs are given
+  std::vector<int> gmap;
+  if (n_pairs) {
+    if (!dst_slots || !src_slots) return fail(CFB_ERR_INVALID, "slot arrays are NULL");
+    gmap.assign(src->G, -1);
+    std::vector<char> used(dst->G, 0);
+    for (size_t i = 0; i < n_pairs; i++) {
+      if (src_slots[i] < 0 || src_slots[i] >= src->G || dst_slots[i] < 0 || dst_slots[i] >= dst->G)
+        return fail(CFB_ERR_INVALID, "combine: slot out of range");
+      if (gmap[src_slots[i]] != -1 || used[dst_slots[i]]) return fail(CFB_ERR_INVALID, "combine: a slot appears twice");
+      gmap[src_slots[i]] = dst_slots[i];
+      used[dst_slots[i]] = 1;
+    }
+  }
   int rc = cfb_ctx_sync(src);
   if (rc) return rc;
   CU(cudaSetDevice(dst->device));
@@ -1400,10 +1419,17 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src_c) {
     CU(cudaMemcpyPeerAsync(thash.counts, dst->device, src->hash.counts, src->device, bytes, dst->stream));
     shash = thash;
   }
-  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->hash, dst->d_err, dst->stream, tr);
+  int *d_gmap = nullptr;
+  if (!gmap.empty()) {
+    CU(cudaMalloc(&d_gmap, gmap.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(d_gmap, gmap.data(), gmap.size() * sizeof(int), cudaMemcpyHostToDevice, dst->stream));
+    scratch.push_back(d_gmap);
+  }
+  rc = launch_remap_add(dst->d_lay, sl, src->lay, dst->d_f64, dst->d_u64, sf, su, dst->hash, dst->d_err, dst->stream, tr, d_gmap);
   if (rc) return rc;
   if (src->lay.pairs_hashed) {
-    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, dst->stream>>>(shash, dst->d_lay, sl, dst->d_u64, dst->hash, dst->d_err, tr);
+    cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, dst->stream>>>(shash, dst->d_lay, sl, dst->d_u64, dst->hash, dst->d_err, tr,
+                                                                   d_gmap, src->G);
     g_launches++;
     CU(cudaGetLastError());
   }
@@ -1423,6 +1449,15 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
   memset(out, 0, sizeof(*out));
   int rc = cfb_ctx_sync(c);
   if (rc) return rc;
+  // the aggregate is complete: hand the (drained) staging tiles back; a later append re-acquires them
+  if (c->tile_rows && c->fill == 0) {
+    for (auto &st : c->st) {
+      if (st.in_flight) CU(cudaEventSynchronize(st.done));
+      g_stage_pool.release(c->device, st);
+    }
+    c->tile_rows = 0;
+    c->cur = 0;
+  }
   const Layout &L = c->lay;
   std::vector<double> f(std::max<long long>(1, L.F));
   std::vector<unsigned long long> u(std::max<long long>(1, L.U));

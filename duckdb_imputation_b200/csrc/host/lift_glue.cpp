@@ -257,8 +257,8 @@ void SumLifted(int kind, duckdb::Vector inputs[], idx_t input_count, duckdb::Vec
       }
     }
     SumState *s = order[b];
-    if (!s->ctx) CheckRc(cfb_ctx_create(0, kind, (int)n, (int)m, 1, &s->ctx));
-    CheckRc(cfb_ctx_append_triples(s->ctx, rows.size(), gN.data(), gl.data(), gq.data(), glc.data(),
+    if (s->arena && s->arena->capacity != 1) throw InvalidInputException("sum over lifted triples: state belongs to a GROUP BY arena");
+    CheckRc(cfb_ctx_append_triples(PrivateContext(*s, kind, (int)n, (int)m), rows.size(), gN.data(), gl.data(), gq.data(), glc.data(),
                                    FlatVector::GetData<int32_t>(*lc_kv[0]), FlatVector::GetData<float>(*lc_kv[1]),
                                    nb ? nullptr : gnc.data(), nc_key, nc_val, nb ? nullptr : gcc.data(), cc_k1, cc_k2, cc_val));
   }

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../../include/cofactor_b200.h"
 
@@ -41,6 +42,53 @@ int PickDevice() {
   static std::atomic<unsigned> next{0};
   return n_dev == 1 ? 0 : (int)(next.fetch_add(1) % (unsigned)n_dev);
 }
+
+Arena *NewArena(int kind, int n, int m, int capacity) {
+  Arena *a = new Arena();
+  a->kind = kind;
+  a->n = n;
+  a->m = m;
+  a->capacity = capacity;
+  const int rc = cfb_ctx_create(PickDevice(), kind, n, m, capacity, &a->ctx);
+  if (rc != CFB_OK) {
+    delete a;
+    Check(rc);
+  }
+  return a;
+}
+
+// Slots per shared arena: bounded by what the GROUP BY kernel keeps in shared memory
+// (group_kernel.cuh) and, with pair tables, by the per-slot state size.
+int SharedCapacity(int kind, int n, int m) {
+  if (kind == CFB_TRIPLE && m >= 2) return 8;
+  const int entries = 1 + n + (kind == CFB_TRIPLE ? n * (n + 1) / 2 : n);
+  return entries <= 128 ? 32 : 16;
+}
+
+// The arenas this thread is currently filling, one per aggregate shape.
+struct OpenArenas {
+  std::vector<Arena *> open;
+  ~OpenArenas() {
+    for (Arena *a : open) a->Release();
+  }
+  Arena *Get(int kind, int n, int m) {
+    for (size_t i = 0; i < open.size(); i++) {
+      Arena *a = open[i];
+      if (a->kind == kind && a->n == n && a->m == m) {
+        if (a->next_slot < a->capacity) return a;
+        a->Release();  // full: the states keep it alive; start the next one
+        open[i] = NewArena(kind, n, m, SharedCapacity(kind, n, m));
+        open[i]->refs.fetch_add(1);
+        return open[i];
+      }
+    }
+    Arena *a = NewArena(kind, n, m, SharedCapacity(kind, n, m));
+    a->refs.fetch_add(1);
+    open.push_back(a);
+    return a;
+  }
+};
+thread_local OpenArenas t_open;
 
 duckdb::LogicalType KeyValueList() {
   duckdb::child_list_t<duckdb::LogicalType> kv;
@@ -97,61 +145,67 @@ void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state
       cat_sel[m++] = fmt[j].sel->sel;
     }
   }
-  auto ensure = [&](SumState *s) {
-    if (!s->ctx) Check(cfb_ctx_create(PickDevice(), kind, n, m, 1, &s->ctx));  // lazy shape, sum_no_lift.cpp:96-116
-  };
-
   // Ungrouped aggregates (and single-group chunks) send every row to one state.
   SumState *first = states[sdata.sel->get_index(0)];
   bool uniform = true;
   for (idx_t r = 1; r < count && uniform; r++) uniform = states[sdata.sel->get_index(r)] == first;
-  if (uniform) {
-    ensure(first);
-    Check(cfb_ctx_append(first->ctx, num, num_sel, cat, cat_sel, nullptr, count));
+  if (uniform && (!first->arena || first->arena->capacity == 1)) {
+    // a state that is fed alone gets a private one-slot context: the ungrouped kernels apply
+    Check(cfb_ctx_append(PrivateContext(*first, kind, n, m), num, num_sel, cat, cat_sel, nullptr, count));
     return;
   }
-  // GROUP BY: bucket the chunk's rows by state and append each bucket through composed
-  // selection vectors (the states[sdata.sel->get_index(j)] indirection of the reference).
-  SumState *seen[STANDARD_VECTOR_SIZE];
-  uint32_t n_seen = 0;
-  std::vector<std::vector<uint32_t>> rows_of;
+  // GROUP BY: new states get a slot in this thread's open arena; the chunk is shipped once per arena
+  // present in it (normally one) with a slot id per row -- rows of other arenas are marked -1 and
+  // dropped on the device (the states[sdata.sel->get_index(j)] indirection of the reference).
+  static thread_local std::vector<uint32_t> slots;
+  slots.resize(count);
+  Arena *seen[8];
+  int n_seen = 0;
+  bool overflow = false;
   for (idx_t r = 0; r < count; r++) {
     SumState *s = states[sdata.sel->get_index(r)];
-    uint32_t b = 0;
-    while (b < n_seen && seen[b] != s) b++;
+    if (!s->arena) {
+      Arena *a = t_open.Get(kind, n, m);
+      s->arena = a;
+      s->slot = a->next_slot++;
+      a->refs.fetch_add(1);
+    }
+    int b = 0;
+    while (b < n_seen && seen[b] != s->arena) b++;
     if (b == n_seen) {
-      seen[n_seen++] = s;
-      rows_of.emplace_back();
+      if (n_seen == 8)
+        overflow = true;
+      else
+        seen[n_seen++] = s->arena;
     }
-    rows_of[b].push_back((uint32_t)r);
   }
-  std::vector<uint32_t> composed((size_t)(n + m) * count);
-  for (uint32_t b = 0; b < n_seen; b++) {
-    const auto &rows = rows_of[b];
-    const uint32_t *nsel[CFB_MAX_NUM], *csel[CFB_MAX_CAT];
-    for (int k = 0; k < n + m; k++) {
-      const uint32_t *src = k < n ? num_sel[k] : cat_sel[k - n];
-      uint32_t *dst = composed.data() + (size_t)k * count;
-      if (src)
-        for (size_t i = 0; i < rows.size(); i++) dst[i] = src[rows[i]];
-      else
-        memcpy(dst, rows.data(), rows.size() * sizeof(uint32_t));
-      if (k < n)
-        nsel[k] = dst;
-      else
-        csel[k - n] = dst;
+  if (overflow) throw duckdb::InternalException("ring aggregate: too many state arenas in one chunk");
+  for (int b = 0; b < n_seen; b++) {
+    Arena *a = seen[b];
+    if (a->kind != kind || a->n != n || a->m != m) throw duckdb::InvalidInputException("ring aggregate: state shape changed");
+    for (idx_t r = 0; r < count; r++) {
+      const SumState *s = states[sdata.sel->get_index(r)];
+      slots[r] = s->arena == a ? (uint32_t)s->slot : 0xFFFFFFFFu;  // -1 as int32: row not for this arena
     }
-    ensure(seen[b]);
-    Check(cfb_ctx_append(seen[b]->ctx, num, nsel, cat, csel, nullptr, rows.size()));
+    Check(cfb_ctx_append(a->ctx, num, num_sel, cat, cat_sel, slots.data(), count));
   }
 }
 
 }  // namespace
 
+cfb_ctx *PrivateContext(SumState &state, int kind, int n_num, int n_cat) {
+  if (!state.arena) {
+    state.arena = NewArena(kind, n_num, n_cat, 1);  // lazy shape, sum_no_lift.cpp:96-116
+    state.arena->refs.fetch_add(1);
+    state.slot = 0;
+  }
+  return state.arena->ctx;
+}
+
 template <class STATE>
 void StateFunction::Destroy(STATE &state, duckdb::AggregateInputData &) {
-  cfb_ctx_destroy(state.ctx);
-  state.ctx = nullptr;
+  if (state.arena) state.arena->Release();
+  state.arena = nullptr;
 }
 template void StateFunction::Destroy<SumState>(SumState &, duckdb::AggregateInputData &);
 
@@ -182,17 +236,32 @@ void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::Ag
   state.ToUnifiedFormat(count, sdata);
   auto src = (SumState **)sdata.data;
   auto dst = duckdb::FlatVector::GetData<SumState *>(combined);
+  // states that live in the same pair of arenas are merged with one call (slot lists)
+  struct Batch {
+    Arena *d, *s;
+    std::vector<int32_t> ds, ss;
+  };
+  std::vector<Batch> batches;
   for (idx_t i = 0; i < count; i++) {
     SumState *s = src[sdata.sel->get_index(i)];
-    if (!s->ctx) continue;  // the source never saw a row
-    if (!dst[i]->ctx) {
-      // empty target adopts the source's device state (sum_state.cpp:26-60); the source stays
-      // destroyable: its destructor sees a null handle
-      dst[i]->ctx = s->ctx;
-      s->ctx = nullptr;
-    } else {
-      Check(cfb_ctx_combine(dst[i]->ctx, s->ctx));
+    if (!s->arena) continue;  // the source never saw a row
+    if (!dst[i]->arena) {
+      // empty target adopts the source's slot (sum_state.cpp:26-60); the source stays destroyable:
+      // its destructor sees a null handle
+      dst[i]->arena = s->arena;
+      dst[i]->slot = s->slot;
+      s->arena = nullptr;
+      continue;
     }
+    size_t b = 0;
+    while (b < batches.size() && (batches[b].d != dst[i]->arena || batches[b].s != s->arena)) b++;
+    if (b == batches.size()) batches.push_back(Batch{dst[i]->arena, s->arena, {}, {}});
+    batches[b].ds.push_back(dst[i]->slot);
+    batches[b].ss.push_back(s->slot);
+  }
+  for (auto &b : batches) {
+    if (b.d == b.s) throw duckdb::InternalException("ring aggregate: combine of two states of one arena");
+    Check(cfb_ctx_combine_slots(b.d->ctx, b.s->ctx, b.ds.size(), b.ds.data(), b.ss.data()));
   }
 }
 
@@ -219,8 +288,8 @@ void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &
   for (idx_t i = 0; i < count; i++) {
     SumState *s = states[sdata.sel->get_index(i)];
     memset(&res[i], 0, sizeof(cfb_result));
-    if (s->ctx) {
-      Check(cfb_ctx_finalize(s->ctx, 0, &res[i]));
+    if (s->arena) {
+      Check(cfb_ctx_finalize(s->arena->ctx, s->slot, &res[i]));
       n = res[i].n_num;
       m = res[i].n_cat;
     }

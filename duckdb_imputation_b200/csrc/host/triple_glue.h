@@ -4,27 +4,53 @@
 // duckdb_extension/src/include/triple/sum/{sum_state.h,sum_no_lift.h,sum_to_nb_agg.h}; the
 // bodies call the C ABI of include/cofactor_b200.h instead of looping on the CPU.
 #pragma once
+#include <atomic>
+
 #include <duckdb.hpp>
 
-struct cfb_ctx;
+#include "../../../include/cofactor_b200.h"
 
 namespace Triple {
 
+// An arena is one device context (cfb_ctx) that holds the aggregate states of MANY GROUP BY groups of
+// one worker thread as slots: DuckDB hands update() a state pointer per row, the glue turns it into a
+// slot id per row and ships the chunk once -- the GPU routes rows to slots.  Arenas are reference
+// counted by the states that live in them (and by the thread that is still filling them).
+struct Arena {
+  cfb_ctx *ctx = nullptr;
+  int kind = 0, n = 0, m = 0;
+  int capacity = 1;          // GROUP BY slots of ctx
+  int next_slot = 0;         // only the owning thread hands out slots
+  std::atomic<int> refs{0};  // live states + 1 while a thread keeps it open
+  void Release() {
+    if (refs.fetch_sub(1) == 1) {
+      cfb_ctx_destroy(ctx);
+      delete this;
+    }
+  }
+};
+
 // sum_state.h:14-28 shrunk to a handle.  DuckDB relocates states with memcpy (hash-table row
-// storage), so the state is a plain pointer to extension-owned memory and nothing else.
+// storage), so the state is plain data: which arena, which slot.
 struct SumState {
-  cfb_ctx *ctx;
+  Arena *arena;
+  int32_t slot;
 };
 
 struct StateFunction {
   template <class STATE>
   static void Initialize(STATE &state) {  // sum_state.h:33-45
-    state.ctx = nullptr;
+    state.arena = nullptr;
+    state.slot = 0;
   }
   template <class STATE>
   static void Destroy(STATE &state, duckdb::AggregateInputData &aggr_input_data);  // sum_state.h:48-52
   static bool IgnoreNull() { return false; }  // NULL rows are delivered (sum_state.h:54-56)
 };
+
+// The context of a state that is fed alone (ungrouped aggregates, sum_triple / sum_nb_agg): a private
+// arena with one slot, created on first use.
+cfb_ctx *PrivateContext(SumState &state, int kind, int n_num, int n_cat);
 
 duckdb::unique_ptr<duckdb::FunctionData> SumNoLiftBind(duckdb::ClientContext &context, duckdb::AggregateFunction &function,
                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(256)
     remap_add_kernel(const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g, double *__restrict__ df,
                      unsigned long long *__restrict__ du, const double *__restrict__ sf,
                      const unsigned long long *__restrict__ su, const PairHash dhash, int *__restrict__ err,
-                     const SlotTrans tr) {
+                     const SlotTrans tr, const int *__restrict__ group_map) {
+  // group_map: dst GROUP BY slot of every src slot (nullptr = identity, < 0 = skip); must be injective
   __shared__ Layout dl, sl;
   {
     const int *a = reinterpret_cast<const int *>(dl_g), *b = reinterpret_cast<const int *>(sl_g);
@@ -137,7 +138,9 @@ __global__ void __launch_bounds__(256)
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < totF + totU;
        e += (long long)gridDim.x * blockDim.x) {
     if (e < totF) {
-      const long long g = e / sl.F, o = e % sl.F;
+      const long long sg = e / sl.F, o = e % sl.F;
+      const long long g = group_map ? group_map[sg] : sg;
+      if (g < 0) continue;
       const double v = sf[e];
       if (v == 0.0) continue;
       long long d;
@@ -154,7 +157,9 @@ __global__ void __launch_bounds__(256)
       }
       df[g * dl.F + d] += v;
     } else {
-      const long long e2 = e - totF, g = e2 / sl.U, o = e2 % sl.U;
+      const long long e2 = e - totF, sg = e2 / sl.U, o = e2 % sl.U;
+      const long long g = group_map ? group_map[sg] : sg;
+      if (g < 0) continue;
       const unsigned long long v = su[e2];
       if (v == 0ull) continue;
       long long d;
@@ -201,14 +206,14 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     pair_hash_drain_kernel(const PairHash src, const Layout *__restrict__ dl_g, const Layout *__restrict__ sl_g,
                            unsigned long long *__restrict__ du, const PairHash dhash, int *__restrict__ err,
-                           const SlotTrans tr) {
+                           const SlotTrans tr, const int *__restrict__ group_map, int src_groups) {
   __shared__ int s_dlo[kMaxCat], s_slo[kMaxCat], s_ddom[kMaxCat];
   __shared__ long long s_poff[kMaxCat * kMaxCat];
   __shared__ int s_m, s_G, s_dhashed;
   __shared__ long long s_U, s_pbase;
   if (threadIdx.x == 0) {
     s_m = dl_g->m;
-    s_G = dl_g->n_groups;
+    s_G = src_groups;
     s_dhashed = dl_g->pairs_hashed;
     s_U = dl_g->U;
     s_pbase = dl_g->pair_base;
@@ -228,7 +233,9 @@ __global__ void __launch_bounds__(256)
     if (key == kPairEmpty) continue;
     const unsigned long long v = src.counts[i];
     if (!v) continue;
-    const long long g = (long long)(i / src.capacity);
+    const long long sg = (long long)(i / src.capacity);
+    const long long g = group_map ? group_map[sg] : sg;
+    if (g < 0) continue;
     const int p = (int)(key >> (2 * kPairSlotBits));
     const int k = p / s_m, l = p % s_m;
     const long long wk = (long long)((key >> kPairSlotBits) & slot_mask), wl = (long long)(key & slot_mask);

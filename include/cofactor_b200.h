@@ -139,6 +139,12 @@ int cfb_ctx_sync(cfb_ctx *ctx);
  * src stays valid and destroyable.  Works across devices (peer or staged copy). */
 int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src);
 
+/* Same for individual GROUP BY slots: dst[dst_slots[i]] += src[src_slots[i]], i < n_pairs; all other
+ * slots of both contexts are untouched (n_groups may differ).  This is what the DuckDB glue calls when
+ * the thread-local hash tables are merged: one context holds all groups of a worker thread.   */
+int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src, size_t n_pairs, const int32_t *dst_slots,
+                          const int32_t *src_slots);
+
 /* ------------------------------------------------------------------- result */
 
 /* Flat canonical result of ONE state (group).  Mirrors the STRUCT written by
