@@ -57,12 +57,17 @@ Arena *NewArena(int kind, int n, int m, int capacity) {
   return a;
 }
 
-// Slots per shared arena: bounded by what the GROUP BY kernel keeps in shared memory
-// (group_kernel.cuh) and, with pair tables, by the per-slot state size.
-int SharedCapacity(int kind, int n, int m) {
+// Slots of a thread's FIRST shared arena: what the GROUP BY kernel keeps in shared memory
+// (group_kernel.cuh); with pair tables the per-slot state is large, so few slots.  When an arena is
+// full the next one is twice as large (up to kMaxCapacity), so G groups need O(log G) arenas.
+int FirstCapacity(int kind, int n, int m) {
   if (kind == CFB_TRIPLE && m >= 2) return 8;
   const int entries = 1 + n + (kind == CFB_TRIPLE ? n * (n + 1) / 2 : n);
   return entries <= 128 ? 32 : 16;
+}
+int NextCapacity(int kind, int m, int prev) {
+  const int max_cap = (kind == CFB_TRIPLE && m >= 2) ? 8 : 4096;
+  return prev * 2 < max_cap ? prev * 2 : max_cap;
 }
 
 // The arenas this thread is currently filling, one per aggregate shape.
@@ -76,13 +81,14 @@ struct OpenArenas {
       Arena *a = open[i];
       if (a->kind == kind && a->n == n && a->m == m) {
         if (a->next_slot < a->capacity) return a;
-        a->Release();  // full: the states keep it alive; start the next one
-        open[i] = NewArena(kind, n, m, SharedCapacity(kind, n, m));
+        const int cap = NextCapacity(kind, m, a->capacity);
+        a->Release();  // full: the states keep it alive; start the next, larger one
+        open[i] = NewArena(kind, n, m, cap);
         open[i]->refs.fetch_add(1);
         return open[i];
       }
     }
-    Arena *a = NewArena(kind, n, m, SharedCapacity(kind, n, m));
+    Arena *a = NewArena(kind, n, m, FirstCapacity(kind, n, m));
     a->refs.fetch_add(1);
     open.push_back(a);
     return a;
@@ -159,9 +165,8 @@ void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state
   // dropped on the device (the states[sdata.sel->get_index(j)] indirection of the reference).
   static thread_local std::vector<uint32_t> slots;
   slots.resize(count);
-  Arena *seen[8];
-  int n_seen = 0;
-  bool overflow = false;
+  static thread_local std::vector<Arena *> seen;
+  seen.clear();
   for (idx_t r = 0; r < count; r++) {
     SumState *s = states[sdata.sel->get_index(r)];
     if (!s->arena) {
@@ -170,17 +175,11 @@ void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state
       s->slot = a->next_slot++;
       a->refs.fetch_add(1);
     }
-    int b = 0;
-    while (b < n_seen && seen[b] != s->arena) b++;
-    if (b == n_seen) {
-      if (n_seen == 8)
-        overflow = true;
-      else
-        seen[n_seen++] = s->arena;
-    }
+    size_t b = 0;
+    while (b < seen.size() && seen[b] != s->arena) b++;
+    if (b == seen.size()) seen.push_back(s->arena);
   }
-  if (overflow) throw duckdb::InternalException("ring aggregate: too many state arenas in one chunk");
-  for (int b = 0; b < n_seen; b++) {
+  for (size_t b = 0; b < seen.size(); b++) {
     Arena *a = seen[b];
     if (a->kind != kind || a->n != n || a->m != m) throw duckdb::InvalidInputException("ring aggregate: state shape changed");
     for (idx_t r = 0; r < count; r++) {
