@@ -114,3 +114,20 @@ def test_states_spread_over_devices_when_asked():
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CFB_DEVICES="all"),
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("kind,n,m,G", [(0, 6, 0, 700), (1, 4, 2, 150), (0, 3, 2, 40)])
+def test_many_groups_span_several_arenas(kind, n, m, G):
+    """More groups than one arena has slots: a worker thread chains arenas (32, 64, 128, ... slots;
+    8 per arena when pair tables make a slot large) and ships a chunk once per arena present in it."""
+    rng = np.random.default_rng(G)
+    rows = 120_000
+    num = [rng.random(rows).astype(np.float32) for _ in range(n)]
+    cat = [rng.integers(0, 7, rows).astype(np.int32) for _ in range(m)]
+    gb = rng.integers(0, G, rows)
+    got = replay.glue().query(kind, num, cat, group_by=gb, threads=3)
+    ref = oracle.aggregate(kind, num, cat, group_by=gb)
+    assert len(got) == len(ref) == len(np.unique(gb))
+    for g in (0, 1, len(ref) // 2, len(ref) - 1):
+        assert_struct_parity(got[g], ref[g], what=f"group {g} of {G}")
+    assert all(a["N"] == b["N"] for a, b in zip(got, ref))
