@@ -152,7 +152,6 @@ struct cfb_ctx {
   double *d_f64 = nullptr;
   unsigned long long *d_u64 = nullptr;
   int *d_err = nullptr;
-  int *d_minmax = nullptr;  // [2][kMaxCat]
   cfb::PairHash hash{};               // sparse pair counts (lay.pairs_hashed)
   struct ColDict {                    // key dictionary of a wide-range categorical column (key_dict.cuh)
     bool on = false;
@@ -988,7 +987,6 @@ int cfb_ctx_create(int device, int kind, int n_num, int n_cat, int n_groups, cfb
   CUB(cudaMemcpyAsync(c->d_lay, &c->lay, sizeof(Layout), cudaMemcpyHostToDevice, c->stream));
   CUB(cudaMalloc(&c->d_err, sizeof(int)));
   CUB(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-  CUB(cudaMalloc(&c->d_minmax, 2 * cfb::kMaxCat * sizeof(int)));
   c->gram_grid = dev_info(device).sms;
   if (const char *e = getenv("CFB_GRAM_GRID")) c->gram_grid = std::max(1, atoi(e));
   CUB(cudaMalloc(&c->d_partials, (size_t)c->gram_grid * (n_num + n_num * (n_num + 1) / 2 + 1) * sizeof(double)));
@@ -1032,7 +1030,6 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_u64);
   cudaFree(c->d_lay);
   cudaFree(c->d_err);
-  cudaFree(c->d_minmax);
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);

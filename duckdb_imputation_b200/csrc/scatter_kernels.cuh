@@ -1,10 +1,7 @@
-// scatter_kernels.cuh -- kernel family K3 (categorical aggregates) and the grouped path.
-//
-// Replaces the per-row std::map updates of Triple::SumNoLift (sum_no_lift.cpp:158-214) and
-// Triple::sum_to_nb_agg (sum_to_nb_agg.cpp:124-145): per categorical column the key count
-// (lin_cat) and the per-key numeric sums (quad_num_cat), per column pair the (key1,key2)
-// counts (quad_cat) -- and, when rows are routed to GROUP BY slots, also N / lin / quad of
-// each slot (the states[sdata.sel->get_index(j)] indirection of the reference).
+// scatter_kernels.cuh -- the small kernels around the scans: the scalar-atomic fallback scan, key
+// range pre-pass, combine / re-layout of dense states (remap_add), draining of hashed pair counts,
+// the sum_triple / sum_nb_agg kernels over lifted triples, and the synthetic-data generators.
+// (The main categorical / GROUP BY kernels are slab_kernels.cuh and group_kernel.cuh.)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,9 +14,9 @@ namespace cfb {
 __device__ __forceinline__ void add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------------------
-// Generic scan: one thread per row, every update an atomic on the dense context state.
-// Used for GROUP BY scans and as the categorical kernel for domains too large for the
-// shared-memory privatised kernel below.  do_numeric = also accumulate N / lin / quad.
+// Generic scan: one thread per row, every update a scalar atomic on the context state.  The
+// fallback behind slab_scan_kernel (slab_kernels.cuh) for shapes whose per-CTA slab would be too
+// large (very many GROUP BY slots x wide domains).  do_numeric = also accumulate N / lin / quad.
 __global__ void __launch_bounds__(256)
     generic_scan_kernel(const ScanCols cols, const Layout *__restrict__ lay_g, unsigned long long n_rows,
                         int do_numeric, double *__restrict__ f64, unsigned long long *__restrict__ u64,
