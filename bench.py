@@ -267,7 +267,9 @@ def main():
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    per_step = [a.elapsed_time(b) for a, b in kev]
+    log(f"[rank {rank}] scan kernel ms per step: " + " ".join(f"{t:.2f}" for t in per_step))
+    kernel_ms = sum(per_step) / args.steps
     ms_per_step = ms_total / args.steps
     value = world * rows / (ms_per_step * 1e-3)
 
