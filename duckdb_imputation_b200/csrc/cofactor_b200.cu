@@ -1590,6 +1590,119 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
   return CFB_OK;
 }
 
+int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *out) {
+  if (!a || !b || !out) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (a->kind != b->kind) return fail(CFB_ERR_INVALID, "multiply: a triple and an NB aggregate do not mix");
+  const bool nb = a->kind == CFB_NB;
+  const int na = a->n_num, nbn = b->n_num, n = na + nbn, ma = a->n_cat, mb = b->n_cat, m = ma + mb;
+  if (n > CFB_MAX_NUM || m > CFB_MAX_CAT) return fail(CFB_ERR_INVALID, "multiply: too many columns in the product");
+  memset(out, 0, sizeof(*out));
+  const double Na = (double)a->N, Nb = (double)b->N;
+  auto dupv = [](const auto &v) {
+    using T = typename std::decay<decltype(v)>::type::value_type;
+    T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+    if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+  };
+  out->kind = a->kind;
+  out->n_num = n;
+  out->n_cat = m;
+  out->N = a->N * b->N;
+  out->n_quad = nb ? n : (int64_t)n * (n + 1) / 2;
+  std::vector<double> lin(n), quad(out->n_quad, 0.0);
+  for (int i = 0; i < na; i++) lin[i] = Nb * a->lin[i];
+  for (int i = 0; i < nbn; i++) lin[na + i] = Na * b->lin[i];
+  if (nb) {
+    for (int i = 0; i < na; i++) quad[i] = Nb * a->quad[i];
+    for (int i = 0; i < nbn; i++) quad[na + i] = Na * b->quad[i];
+  } else {
+    auto tri = [](int nn, int i, int j) { return i * nn - i * (i + 1) / 2 + j; };
+    for (int i = 0; i < n; i++)
+      for (int j = i; j < n; j++) {
+        double v;
+        if (j < na)
+          v = Nb * a->quad[tri(na, i, j)];
+        else if (i >= na)
+          v = Na * b->quad[tri(nbn, i - na, j - na)];
+        else
+          v = a->lin[i] * b->lin[j - na];
+        quad[tri(n, i, j)] = v;
+      }
+  }
+  out->lin = dupv(lin);
+  out->quad = dupv(quad);
+  // categorical columns: a's, then b's
+  const int64_t ta = a->total_keys, tb = b->total_keys, tk = ta + tb;
+  std::vector<int64_t> offs(m + 1), counts(tk);
+  std::vector<int32_t> keys(tk);
+  for (int c = 0; c <= ma; c++) offs[c] = a->cat_offsets[c];
+  for (int c = 0; c <= mb; c++) offs[ma + c] = ta + b->cat_offsets[c];
+  for (int64_t t = 0; t < ta; t++) {
+    keys[t] = a->cat_keys[t];
+    counts[t] = a->cat_counts[t] * b->N;
+  }
+  for (int64_t t = 0; t < tb; t++) {
+    keys[ta + t] = b->cat_keys[t];
+    counts[ta + t] = b->cat_counts[t] * a->N;
+  }
+  out->total_keys = tk;
+  out->cat_offsets = dupv(offs);
+  out->cat_keys = dupv(keys);
+  out->cat_counts = dupv(counts);
+  if (nb) {
+    out->n_pair_lists = 0;
+    out->pair_offsets = dupv(std::vector<int64_t>(1, 0));
+    return CFB_OK;
+  }
+  std::vector<double> nc((size_t)n * tk);
+  for (int i = 0; i < n; i++)
+    for (int64_t t = 0; t < tk; t++) {
+      double v;
+      if (i < na)
+        v = t < ta ? Nb * a->numcat_sums[(size_t)i * ta + t] : a->lin[i] * (double)b->cat_counts[t - ta];
+      else
+        v = t < ta ? b->lin[i - na] * (double)a->cat_counts[t] : Na * b->numcat_sums[(size_t)(i - na) * tb + (t - ta)];
+      nc[(size_t)i * tk + t] = v;
+    }
+  out->numcat_sums = dupv(nc);
+  out->n_pair_lists = (int64_t)m * (m + 1) / 2;
+  std::vector<int64_t> po(out->n_pair_lists + 1, 0), pc;
+  std::vector<int32_t> k1, k2;
+  auto pair_index = [](int mm, int k, int l) { return k * mm - k * (k + 1) / 2 + l; };
+  int p = 0;
+  for (int k = 0; k < m; k++)
+    for (int l = k; l < m; l++, p++) {
+      if (l < ma) {  // both on a's side
+        const int q = pair_index(ma, k, l);
+        for (int64_t t = a->pair_offsets[q]; t < a->pair_offsets[q + 1]; t++) {
+          k1.push_back(a->pair_key1[t]);
+          k2.push_back(a->pair_key2[t]);
+          pc.push_back(a->pair_counts[t] * b->N);
+        }
+      } else if (k >= ma) {  // both on b's side
+        const int q = pair_index(mb, k - ma, l - ma);
+        for (int64_t t = b->pair_offsets[q]; t < b->pair_offsets[q + 1]; t++) {
+          k1.push_back(b->pair_key1[t]);
+          k2.push_back(b->pair_key2[t]);
+          pc.push_back(b->pair_counts[t] * a->N);
+        }
+      } else {  // across the join: outer product of the key counts (ascending (key1,key2))
+        for (int64_t x = a->cat_offsets[k]; x < a->cat_offsets[k + 1]; x++)
+          for (int64_t y = b->cat_offsets[l - ma]; y < b->cat_offsets[l - ma + 1]; y++) {
+            k1.push_back(a->cat_keys[x]);
+            k2.push_back(b->cat_keys[y]);
+            pc.push_back(a->cat_counts[x] * b->cat_counts[y]);
+          }
+      }
+      po[p + 1] = (int64_t)k1.size();
+    }
+  out->pair_offsets = dupv(po);
+  out->pair_key1 = dupv(k1);
+  out->pair_key2 = dupv(k2);
+  out->pair_counts = dupv(pc);
+  return CFB_OK;
+}
+
 void cfb_result_free(cfb_result *r) {
   if (!r) return;
   free(r->lin);

@@ -163,6 +163,139 @@ int replay_scalar(const char *scalar, int n_num, int n_cat, const float *const *
   }
 }
 
+namespace {
+// Type-directed reader of the JSON RenderValue writes: fills row `row` of `v`.
+void SkipWs(const char *&p) {
+  while (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r') p++;
+}
+void Expect(const char *&p, char c) {
+  SkipWs(p);
+  if (*p != c) throw duckdb::InvalidInputException(std::string("replay: malformed STRUCT literal, expected '") + c + "'");
+  p++;
+}
+void ParseValue(const char *&p, duckdb::Vector &v, idx_t row) {
+  using namespace duckdb;
+  SkipWs(p);
+  switch (v.GetType().id()) {
+    case LogicalTypeId::INTEGER: {
+      char *end;
+      FlatVector::GetData<int32_t>(v)[row] = (int32_t)strtol(p, &end, 10);
+      p = end;
+      break;
+    }
+    case LogicalTypeId::FLOAT: {
+      char *end;
+      FlatVector::GetData<float>(v)[row] = (float)strtod(p, &end);
+      p = end;
+      break;
+    }
+    case LogicalTypeId::LIST: {
+      Expect(p, '[');
+      const idx_t start = ListVector::GetListSize(v);
+      idx_t len = 0;
+      SkipWs(p);
+      while (*p != ']') {
+        if (len) Expect(p, ',');
+        ListVector::Reserve(v, start + len + 1);
+        ListVector::SetListSize(v, start + len + 1);
+        ParseValue(p, ListVector::GetEntry(v), start + len);
+        len++;
+        SkipWs(p);
+      }
+      p++;
+      ListVector::GetData(v)[row] = {start, len};
+      break;
+    }
+    case LogicalTypeId::STRUCT: {
+      Expect(p, '{');
+      auto &kids = StructVector::GetEntries(v);
+      for (size_t i = 0; i < kids.size(); i++) {
+        if (i) Expect(p, ',');
+        Expect(p, '"');
+        while (*p && *p != '"') p++;  // field names are not checked: the ring functions read children positionally
+        Expect(p, '"');
+        Expect(p, ':');
+        ParseValue(p, *kids[i], row);
+      }
+      Expect(p, '}');
+      break;
+    }
+    default:
+      throw InternalException("replay: cannot parse this type");
+  }
+}
+duckdb::LogicalType RingType(bool nb) {
+  using namespace duckdb;
+  child_list_t<LogicalType> kv;
+  kv.emplace_back("key", LogicalType::INTEGER);
+  kv.emplace_back("value", LogicalType::FLOAT);
+  child_list_t<LogicalType> f;
+  f.emplace_back("N", LogicalType::INTEGER);
+  f.emplace_back("lin_agg", LogicalType::LIST(LogicalType::FLOAT));
+  f.emplace_back("quad_agg", LogicalType::LIST(LogicalType::FLOAT));
+  f.emplace_back("lin_cat", LogicalType::LIST(LogicalType::LIST(LogicalType::STRUCT(kv))));
+  if (!nb) {
+    f.emplace_back("quad_num_cat", LogicalType::LIST(LogicalType::LIST(LogicalType::STRUCT(kv))));
+    child_list_t<LogicalType> kkv;
+    kkv.emplace_back("key1", LogicalType::INTEGER);
+    kkv.emplace_back("key2", LogicalType::INTEGER);
+    kkv.emplace_back("value", LogicalType::FLOAT);
+    f.emplace_back("quad_cat", LogicalType::LIST(LogicalType::LIST(LogicalType::STRUCT(kkv))));
+  }
+  return LogicalType::STRUCT(f);
+}
+}  // namespace
+
+int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out) {
+  using namespace duckdb;
+  try {
+    if (!scalar || !json_out || n_args < 1 || !json_args) throw InvalidInputException("bad arguments");
+    *json_out = nullptr;
+    auto it = Catalog().scalars.find(scalar);
+    if (it == Catalog().scalars.end())
+      throw InvalidInputException(std::string("Catalog Error: scalar function ") + scalar + " does not exist");
+    ScalarFunction fun = it->second;
+    const LogicalType arg_type = RingType(nb != 0);
+    ClientContext context;
+    vector<unique_ptr<Expression>> args;
+    for (int k = 0; k < n_args; k++) {
+      args.push_back(make_uniq<Expression>());
+      args.back()->return_type = arg_type;
+    }
+    unique_ptr<FunctionData> bind_data;
+    if (fun.bind) bind_data = fun.bind(context, fun, args);
+    std::ostringstream os;
+    os << "[";
+    std::vector<const char *> cur(json_args, json_args + n_args);
+    for (auto &p : cur) Expect(p, '[');
+    for (size_t lo = 0; lo < rows; lo += STANDARD_VECTOR_SIZE) {
+      const idx_t count = std::min<size_t>(rows - lo, STANDARD_VECTOR_SIZE);
+      DataChunk chunk;
+      for (int k = 0; k < n_args; k++) {
+        chunk.data.emplace_back(arg_type, count);
+        for (idx_t r = 0; r < count; r++) {
+          if (lo + r) Expect(cur[k], ',');
+          ParseValue(cur[k], chunk.data[k], r);
+        }
+      }
+      chunk.SetCardinality(count);
+      ExpressionState state;
+      Vector result(fun.return_type, count);
+      fun.function(chunk, state, result);
+      for (idx_t r = 0; r < count; r++) {
+        if (lo + r) os << ", ";
+        RenderValue(result, r, os);
+      }
+    }
+    os << "]";
+    *json_out = strdup(os.str().c_str());
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 int replay_aggregate(const char *function, const char *scalar, int n_num, int n_cat, const float *const *num,
                      const int32_t *const *cat, const int32_t *group, int n_groups, const uint32_t *sel,
                      size_t n_sel, size_t rows, int threads, char **json_out, double *seconds) {

@@ -38,6 +38,10 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
 /* Run  SELECT <scalar>(num..., cat...) FROM t [WHERE row in sel]  -> JSON array, one value per row. */
 int replay_scalar(const char *scalar, int n_num, int n_cat, const float *const *num, const int32_t *const *cat,
                   const uint32_t *sel, size_t n_sel, size_t rows, char **json_out);
+/* Run  SELECT <scalar>(A, B, ...) FROM j  where every argument is a column of ring STRUCTs (the output of
+ * a join over aggregate results): json_args[k] is a JSON array with one STRUCT per row, in the rendering
+ * of json_out (field names are ignored; nb != 0: the four-field Naive-Bayes ring).  e.g. multiply_triple. */
+int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out);
 void replay_free(char *p);
 const char *replay_last_error(void);
 /* Names of all registered aggregate functions, '\n'-separated (malloc'd). */

@@ -40,6 +40,18 @@ void Load(duckdb::DatabaseInstance &instance) {
   to_nb_agg.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
   ExtensionUtil::RegisterFunction(instance, to_nb_agg);
 
+  // multiply_triple(A, B) / multiply_nb_agg(A, B): the ring product for factorised joins (ext.cpp:68-76,
+  // :135-142).  The reference's MultiplyStats (statistics propagation) has no counterpart here.
+  ScalarFunction mul("multiply_triple", {LogicalType::ANY}, LogicalTypeId::STRUCT, Triple::MultiplyFunction, Triple::MultiplyBind, nullptr,
+                     nullptr);
+  mul.varargs = LogicalType::ANY;
+  mul.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, mul);
+  ScalarFunction mul_nb("multiply_nb_agg", {LogicalType::ANY}, LogicalTypeId::STRUCT, Triple::multiply_nb, Triple::multiply_nb_bind, nullptr);
+  mul_nb.varargs = LogicalType::ANY;
+  mul_nb.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, mul_nb);
+
   constexpr int kMaxCols = 20;
   for (int i = 0; i <= kMaxCols; i++)
     for (int j = 0; j <= kMaxCols; j++) {

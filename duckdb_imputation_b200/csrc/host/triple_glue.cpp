@@ -264,36 +264,15 @@ void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::Ag
   }
 }
 
-void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &, duckdb::Vector &result, idx_t count,
-                      idx_t offset) {
+// Writes `count` canonical results into the nested STRUCT vector in the reference's layout
+// (sum_state.cpp:132-461); shared by finalize and by multiply_triple / multiply_nb_agg.
+void WriteResults(const std::vector<cfb_result> &res, duckdb::Vector &result, bool nb, int n, int m) {
   using namespace duckdb;
-  if (offset != 0) throw InternalException("ring aggregate finalize expects offset 0");  // sum_state.cpp:120
-  if (count == 0) return;
-  UnifiedVectorFormat sdata;
-  state_vector.ToUnifiedFormat(count, sdata);
-  auto states = (SumState **)sdata.data;
-
-  // Pull every group's canonical result first: list children are sized once, then filled.
-  std::vector<cfb_result> res(count);
-  struct Guard {
-    std::vector<cfb_result> &r;
-    ~Guard() {
-      for (auto &x : r) cfb_result_free(&x);
-    }
-  } guard{res};
-  const bool nb = StructVector::GetEntries(result).size() == 4;
-  int n = 0, m = 0;
+  const idx_t count = res.size();
   idx_t total_keys = 0, total_pairs = 0;
-  for (idx_t i = 0; i < count; i++) {
-    SumState *s = states[sdata.sel->get_index(i)];
-    memset(&res[i], 0, sizeof(cfb_result));
-    if (s->arena) {
-      Check(cfb_ctx_finalize(s->arena->ctx, s->slot, &res[i]));
-      n = res[i].n_num;
-      m = res[i].n_cat;
-    }
-    total_keys += (idx_t)res[i].total_keys;
-    if (res[i].pair_offsets) total_pairs += (idx_t)res[i].pair_offsets[res[i].n_pair_lists];
+  for (const cfb_result &r : res) {
+    total_keys += (idx_t)r.total_keys;
+    if (r.pair_offsets) total_pairs += (idx_t)r.pair_offsets[r.n_pair_lists];
   }
   const idx_t nq = nb ? (idx_t)n : (idx_t)n * (n + 1) / 2;
   const idx_t npl = (idx_t)m * (m + 1) / 2;
@@ -396,6 +375,37 @@ void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &
       }
     }
   }
+}
+
+void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &, duckdb::Vector &result, idx_t count,
+                      idx_t offset) {
+  using namespace duckdb;
+  if (offset != 0) throw InternalException("ring aggregate finalize expects offset 0");  // sum_state.cpp:120
+  if (count == 0) return;
+  UnifiedVectorFormat sdata;
+  state_vector.ToUnifiedFormat(count, sdata);
+  auto states = (SumState **)sdata.data;
+
+  // Pull every group's canonical result first: list children are sized once, then filled.
+  std::vector<cfb_result> res(count);
+  struct Guard {
+    std::vector<cfb_result> &r;
+    ~Guard() {
+      for (auto &x : r) cfb_result_free(&x);
+    }
+  } guard{res};
+  const bool nb = StructVector::GetEntries(result).size() == 4;
+  int n = 0, m = 0;
+  for (idx_t i = 0; i < count; i++) {
+    SumState *s = states[sdata.sel->get_index(i)];
+    memset(&res[i], 0, sizeof(cfb_result));
+    if (s->arena) {
+      Check(cfb_ctx_finalize(s->arena->ctx, s->slot, &res[i]));
+      n = res[i].n_num;
+      m = res[i].n_cat;
+    }
+  }
+  WriteResults(res, result, nb, n, m);
 }
 
 }  // namespace Triple

@@ -78,8 +78,19 @@ void to_nb_lift(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb:
 duckdb::unique_ptr<duckdb::FunctionData> to_nb_lift_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 
+// multiply_triple / multiply_nb_agg: the ring product as a scalar function (mul.h, mul_nb.h)
+void MultiplyFunction(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> MultiplyBind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                      duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void multiply_nb(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> multiply_nb_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+
 void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::AggregateInputData &aggr_input_data, idx_t count);
 void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &aggr_input_data, duckdb::Vector &result,
                       idx_t count, idx_t offset);
+
+// Writes canonical results (one per output row) into the nested STRUCT vector (sum_state.cpp:132-461).
+void WriteResults(const std::vector<cfb_result> &res, duckdb::Vector &result, bool nb, int n_num, int n_cat);
 
 }  // namespace Triple

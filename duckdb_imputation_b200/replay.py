@@ -39,6 +39,8 @@ class Replay:
         l.replay_scalar.restype = C.c_int
         l.replay_scalar.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(P), C.POINTER(P), P, C.c_size_t, C.c_size_t,
                                     C.POINTER(P)]
+        l.replay_scalar_structs.restype = C.c_int
+        l.replay_scalar_structs.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(P)]
         l.replay_free.argtypes = [P]
         l.replay_last_error.restype = C.c_char_p
         l.replay_list_functions.restype = P
@@ -89,6 +91,23 @@ class Replay:
         rc = self.lib.replay_scalar(function.encode(), len(kn), len(kc), ptr_array([k.ctypes.data for k in kn]),
                                     ptr_array([k.ctypes.data for k in kc]), None if s is None else s.ctypes.data,
                                     0 if s is None else len(s), rows, C.byref(out))
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            return json.loads(C.string_at(out).decode())
+        finally:
+            self.lib.replay_free(out)
+
+    def scalar_structs(self, function: str, *columns):
+        """SELECT function(A, B, ..) FROM j, every argument a column (list) of ring STRUCT dicts, e.g.
+        multiply_triple over the rows of a join of aggregate results -> one STRUCT per row."""
+        rows = len(columns[0])
+        if rows == 0:
+            return []
+        nb = 0 if "quad_cat" in columns[0][0] else 1
+        texts = (C.c_char_p * len(columns))(*[json.dumps(col).encode() for col in columns])
+        out = C.c_void_p()
+        rc = self.lib.replay_scalar_structs(function.encode(), nb, len(columns), texts, rows, C.byref(out))
         if rc:
             raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
         try:

@@ -186,6 +186,18 @@ typedef struct cfb_result {
 int cfb_ctx_finalize(cfb_ctx *ctx, int group, cfb_result *out);
 void cfb_result_free(cfb_result *res);
 
+/* Ring product of two results -- replaces the arithmetic of Triple::MultiplyFunction
+ * (mul.cpp:19-611) and Triple::multiply_nb (mul_nb.cpp) for factorised joins:
+ *   N = Na*Nb;  lin = [Nb*lin_a | Na*lin_b];
+ *   quad = packed upper triangle over the concatenated columns: [Nb*quad_a | lin_a (x) lin_b | Na*quad_b]
+ *          (CFB_NB: [Nb*quad_a | Na*quad_b], the diagonal only);
+ *   categorical columns of a, then of b: key counts scaled by the other side's N; per-key numeric
+ *   sums scaled likewise or, across the two sides, lin_x[i] * count_y[key]; pair counts scaled
+ *   likewise or, across the two sides, the outer product count_a[key1] * count_b[key2].
+ * A host-side function on two small per-group results (the reference runs it per joined row);
+ * `out` is owned by the caller afterwards (cfb_result_free).                               */
+int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *out);
+
 /* ------------------------------------------------- multi-GPU partial exchange */
 
 /* Dense partial layout for the NCCL reduce of SURVEY 8(e): the caller

@@ -104,3 +104,55 @@ def sum_of_lifted(kind, num_cols, cat_cols, group=None, n_groups=1):
 
 def last_seconds() -> float:
     return float(lib().orc_last_seconds())
+
+
+def multiply(a: dict, b: dict) -> dict:
+    """Ring product of two result STRUCTs -- restatement of Triple::MultiplyFunction
+    (duckdb_extension/src/triple/mul.cpp:17-611) and Triple::multiply_nb (mul_nb.cpp) on the
+    Python form of the STRUCT (pure Python: the operands are per-group results, tens of values).
+    fp32 arithmetic like the reference (float * int, float * float)."""
+    f = np.float32
+    la, lb = a.get("lin_agg", a.get("lin_num")), b.get("lin_agg", b.get("lin_num"))
+    qa, qb = a.get("quad_agg", a.get("quad_num")), b.get("quad_agg", b.get("quad_num"))
+    na, nb_, Na, Nb = len(la), len(lb), a["N"], b["N"]
+    is_nb = "quad_cat" not in a
+    out = {"N": Na * Nb}                                                           # mul.cpp:42-47
+    out["lin_num"] = [float(f(x) * f(Nb)) for x in la] + [float(f(x) * f(Na)) for x in lb]   # :96-107
+    if is_nb:                                                                      # mul_nb.cpp: diagonals only
+        out["quad_num"] = [float(f(x) * f(Nb)) for x in qa] + [float(f(x) * f(Na)) for x in qb]
+    else:
+        quad, p = [], 0
+        for j in range(na):                                                        # mul.cpp:262-283
+            for _ in range(j, na):
+                quad.append(float(f(qa[p]) * f(Nb)))
+                p += 1
+            quad += [float(f(la[j]) * f(x)) for x in lb]
+        quad += [float(f(x) * f(Na)) for x in qb]                                  # :285-288
+        out["quad_num"] = quad
+    scale = lambda lst, N: [{**e, "value": float(f(e["value"]) * f(N))} for e in lst]
+    lca, lcb = a["lin_cat"], b["lin_cat"]
+    ma, mb = len(lca), len(lcb)
+    out["lin_cat"] = [scale(l, Nb) for l in lca] + [scale(l, Na) for l in lcb]      # :184-217
+    if is_nb:
+        return out
+    nca, ncb = a["quad_num_cat"], b["quad_num_cat"]
+    nc = []
+    for j in range(na):                                                            # :377-411
+        nc += [scale(nca[j * ma + k], Nb) for k in range(ma)]
+        nc += [[{"key": e["key"], "value": float(f(la[j]) * f(e["value"]))} for e in lcb[k]] for k in range(mb)]
+    for j in range(nb_):                                                           # :414-445
+        nc += [[{"key": e["key"], "value": float(f(lb[j]) * f(e["value"]))} for e in lca[k]] for k in range(ma)]
+        nc += [scale(ncb[j * mb + k], Na) for k in range(mb)]
+    out["quad_num_cat"] = nc
+    cca, ccb = a["quad_cat"], b["quad_cat"]
+    cc, p = [], 0
+    for c1 in range(ma):                                                           # :546-581
+        for _ in range(c1, ma):
+            cc.append(scale(cca[p], Nb))
+            p += 1
+        for c2 in range(mb):
+            cc.append([{"key1": x["key"], "key2": y["key"], "value": float(f(x["value"]) * f(y["value"]))}
+                       for x in lca[c1] for y in lcb[c2]])
+    cc += [scale(l, Na) for l in ccb]                                              # :583-597
+    out["quad_cat"] = cc
+    return out

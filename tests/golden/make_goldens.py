@@ -6,7 +6,7 @@ test-suite reads -- /root/reference does not exist on the GPU box.
     python tests/golden/make_goldens.py
 
 For every `duckdb_conn.execute("<SQL>")` followed by `assert(res[i][0] == eval("<dict>"))` in
-duckdb_extension/test/python/{test_sum,test_nb_sum,test_lift,test_nb_lift}.py the script
+duckdb_extension/test/python/{test_sum,test_nb_sum,test_lift,test_nb_lift,test_mul,test_nb_mul}.py the script
 records {file, test, sql, index, expected}.  The fixture tables (CREATE TABLE / INSERT) are
 recorded too.
 """
@@ -16,7 +16,7 @@ import os
 import re
 
 REF = "/root/reference/duckdb_extension/test/python"
-FILES = ["test_sum.py", "test_nb_sum.py", "test_lift.py", "test_nb_lift.py"]
+FILES = ["test_sum.py", "test_nb_sum.py", "test_lift.py", "test_nb_lift.py", "test_mul.py", "test_nb_mul.py"]
 
 
 def main():
@@ -32,6 +32,7 @@ def main():
         for m in re.finditer(r"def (test_\w+)\s*\(duckdb_conn\):(.*?)(?=\ndef |\Z)", src, re.S):
             name, body = m.group(1), m.group(2)
             sql = None
+            body = re.sub(r'"\s*\n\s*"', "", body)  # adjacent string literals (test_mul.py splits its SQL)
             for line in body.splitlines():
                 e = re.search(r'execute\("(.*)"\)', line)
                 if e:

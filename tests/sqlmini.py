@@ -61,3 +61,35 @@ def run_lift(sql, fixture, scalar_backend):
             cat.append(cols[a])
     where = None if q["where"] is None else (cols["gb"] == q["where"])
     return scalar_backend(q["fn"], num, cat, where=where)
+
+
+def run_mul(sql, fixture, backend, multiply, reference_layout=False):
+    """Execute the reference's multiply statements (test_mul.py, test_nb_mul.py):
+        SELECT multiply_x(A, B) FROM (SELECT [gb,] fn(..) AS A FROM test ..) INNER JOIN (SELECT [gb,] fn(..) AS B ..)
+               ON TRUE | on a.gb = b.gb
+    `backend` as in run_sum; multiply(list_of_A_rows, list_of_B_rows) -> list of product STRUCTs.
+    Row order of the cross join as DuckDB 0.9.2 emits it (and the goldens index it): B-major, one chunk
+    per B row holding all A rows next to a CONSTANT B vector.
+
+    reference_layout=True reproduces what the reference computes on that chunk: mul.cpp reads B's N through
+    the vector's selection (:42-47) but indexes B's list children by the row's position in the chunk
+    (`k + i * num_attr_size_2`, :96-107, :262-288; `col + i * cat_attr_size_2`, :186-217, ...) instead of
+    through the list offsets, so row i of a chunk gets N of the chunk's B row and the LISTS of B row i.
+    Two of the four cross-join goldens (index 1 and 2) are such mixtures; the equi-join goldens and
+    index 0 / 3 are true products."""
+    cols, _ = table(fixture)
+    subs = re.findall(r"\(SELECT (?:gb as gb, )?(\w+\(.*?\)) AS [AB] FROM test\s*(.*?)\)", sql, re.I)
+    assert len(subs) == 2, sql
+    sides = []
+    for call, tail in subs:
+        res = run_sum("SELECT %s from test %s" % (call, tail), fixture, backend)
+        where = re.search(r"where gb = (\d+)", tail, re.I)
+        gb = cols["gb"] if where is None else cols["gb"][cols["gb"] == int(where.group(1))]
+        labels = list(np.unique(gb)) if re.search(r"GROUP BY", tail, re.I) else [None]
+        sides.append(list(zip(labels, res)))
+    if re.search(r"on a\.gb = b\.gb", sql, re.I):
+        pairs = [(ra, rb) for la, ra in sides[0] for lb, rb in sides[1] if la == lb]
+    else:
+        B = [rb for _, rb in sides[1]]
+        pairs = [(ra, {**B[i], "N": rb["N"]} if reference_layout else rb) for rb in B for i, (_, ra) in enumerate(sides[0])]
+    return multiply([p[0] for p in pairs], [p[1] for p in pairs])

@@ -131,3 +131,29 @@ def test_many_groups_span_several_arenas(kind, n, m, G):
     for g in (0, 1, len(ref) // 2, len(ref) - 1):
         assert_struct_parity(got[g], ref[g], what=f"group {g} of {G}")
     assert all(a["N"] == b["N"] for a, b in zip(got, ref))
+
+
+def test_multiply_over_gpu_aggregates(goldens):
+    """test_mul.py / test_nb_mul.py end to end: the operands come from OUR aggregates on the GPU, the product
+    from OUR multiply_triple / multiply_nb_agg; plus the ring homomorphism on random data:
+    multiply(sum A, sum B) == sum over the cross join."""
+    g = replay.glue()
+    cases = [c for c in goldens["cases"] if c["file"] in ("test_mul.py", "test_nb_mul.py")]
+    assert len(cases) == 12
+    for c in cases:
+        fn = "multiply_triple" if c["file"] == "test_mul.py" else "multiply_nb_agg"
+        got = sqlmini.run_mul(c["sql"], goldens["fixtures"][c["file"]], g.query, lambda A, B: g.scalar_structs(fn, A, B),
+                              reference_layout=True)
+        assert got[c["index"]] == c["expected"], (c["file"], c["test"], c["index"])
+    rng = np.random.default_rng(11)
+    ra, rb = 700, 300
+    An = [rng.integers(0, 6, ra).astype(np.float32) for _ in range(3)]
+    Ac = [rng.integers(-2, 4, ra).astype(np.int32) for _ in range(2)]
+    Bn = [rng.integers(0, 6, rb).astype(np.float32) for _ in range(2)]
+    Bc = [rng.integers(5, 9, rb).astype(np.int32) for _ in range(1)]
+    for kind, fn in ((0, "multiply_triple"), (1, "multiply_nb_agg")):
+        prod = g.scalar_structs(fn, [g.query(kind, An, Ac)], [g.query(kind, Bn, Bc)])[0]
+        whole = g.query(kind, [np.repeat(c, rb) for c in An] + [np.tile(c, ra) for c in Bn],
+                        [np.repeat(c, rb) for c in Ac] + [np.tile(c, ra) for c in Bc])
+        prod["lin_agg"], prod["quad_agg"] = prod.pop("lin_num"), prod.pop("quad_num")
+        assert prod == whole
