@@ -29,6 +29,8 @@
 #include "key_dict.cuh"
 #include "pair_hash.cuh"
 #include "slab_kernels.cuh"
+#include "role_kernels.cuh"
+#include "role_launch.h"
 #include "slab_launch.h"
 #include "scatter_kernels.cuh"
 #include "state_layout.h"
@@ -168,6 +170,12 @@ struct cfb_ctx {
   float *d_slab = nullptr;
   long long slab_floats = 0;  // per CTA
   int slab_grid = 0;
+  // role plan of role_scan_kernel (shared-memory pair tables), rebuilt when the domains change
+  cfb::RolePlan *role_plan = nullptr;  // host copy; travels in the kernel parameters
+  int role_state = 0;  // 0: no plan for the current domains yet, 1: plan valid, -1: shape does not fit
+  int role_dom[cfb::kMaxCat] = {0};
+  int role_roles = 0, role_bits = 0;
+  size_t role_smem = 0;
   // Gram scratch
   double *d_partials = nullptr;
   unsigned int *d_ticket = nullptr;
@@ -636,6 +644,14 @@ constexpr std::array<cudaError_t (*)(const cfb::SlabLaunchParams &), sizeof...(N
 const auto kSlabTriple = slab_table<0>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
 const auto kSlabNb = slab_table<1>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
 
+template <int BITS, int... Ns>
+constexpr std::array<cudaError_t (*)(const cfb::RoleLaunchParams &), sizeof...(Ns)> role_table(
+    std::integer_sequence<int, Ns...>) {
+  return {{cfb::role_launch<Ns, BITS>...}};
+}
+const auto kRole16 = role_table<16>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+const auto kRole32 = role_table<32>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -664,15 +680,10 @@ int launch_gram(cfb_ctx *c, const float *const *cols, unsigned long long rows, c
 // too large (caller falls back to generic_scan_kernel), 0 on success, <0 on error.
 constexpr long long kMaxSlabBytesPerCta = 8ll << 20, kMaxSlabBytesTotal = 512ll << 20;
 
-int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, int do_numeric, cudaStream_t s) {
-  const cfb::SlabShape sh = cfb::slab_shape(c->lay, do_numeric);
-  const long long bytes = sh.floats * 4;
-  if (bytes > kMaxSlabBytesPerCta || getenv("CFB_NO_SLAB")) return 1;
-  int grid = dev_info(c->device).sms * 2;
-  grid = (int)std::min<long long>(grid, std::max<long long>(1, kMaxSlabBytesTotal / std::max<long long>(bytes, 1)));
-  grid = (int)std::min<unsigned long long>(grid, (rows + cfb::kSlabTile - 1) / cfb::kSlabTile);
-  grid = std::max(grid, 1);
-  if (sh.floats != c->slab_floats || grid > c->slab_grid) {
+// Per-CTA fp32 slabs: `floats` per CTA for `grid` CTAs, all zero.
+int ensure_slab(cfb_ctx *c, long long floats, int grid, cudaStream_t s) {
+  const long long bytes = floats * 4;
+  if (floats != c->slab_floats || grid > c->slab_grid) {
     if (c->d_slab) {
       CU(cudaStreamSynchronize(c->stream));
       if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
@@ -682,9 +693,124 @@ int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, in
     const int alloc_grid = std::max(grid, c->slab_grid);
     CU(cudaMalloc(&c->d_slab, (size_t)std::max<long long>(16, bytes * alloc_grid)));
     CU(cudaMemsetAsync(c->d_slab, 0, (size_t)std::max<long long>(16, bytes * alloc_grid), s));
-    c->slab_floats = sh.floats;
+    c->slab_floats = floats;
     c->slab_grid = alloc_grid;
   }
+  return CFB_OK;
+}
+
+// Pair tables of the current domains cut into shared-memory roles (role_kernels.cuh).  Tables are
+// taken in (k,l) order, so the tables of one role share their first column as far as possible.
+bool build_role_plan(const Layout &L, size_t budget_bytes, int bits, cfb::RolePlan *out) {
+  memset(out, 0, sizeof(*out));
+  out->bits = bits;
+  const long long budget_words = (long long)budget_bytes / 4;
+  if (budget_words <= 0) return false;
+  int role = 0;
+  long long used = 0;
+  for (int k = 0; k < L.m; k++) {
+    for (int l = k + 1; l < L.m; l++) {
+      const long long cells = (long long)L.dom[k] * L.dom[l];
+      const long long words = bits == 32 ? cells : (cells + 1) / 2;
+      if (words > budget_words) return false;
+      if (used + words > budget_words || out->n_tables[role] == cfb::kRoleMaxTables) {
+        if (++role == cfb::kRoleMaxRoles) return false;
+        used = 0;
+      }
+      cfb::RoleTable &t = out->tbl[role][out->n_tables[role]++];
+      t.k = k;
+      t.l = l;
+      t.dom_l = L.dom[l];
+      t.cells = (int)cells;
+      t.word_off = (int)used;
+      if (L.pair_off[k * L.m + l] > INT_MAX) return false;
+      t.state_off = (int)L.pair_off[k * L.m + l];
+      used += words;
+      out->words[role] = (int)used;
+    }
+  }
+  out->n_roles = role + 1;
+  return true;
+}
+
+// Categorical part through shared-memory pair tables + L2 vector reductions.  Returns 1 if this
+// shape / scan does not qualify (caller uses the slab kernel), 0 on success, <0 on error.
+int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (c->kind != CFB_TRIPLE || c->m < 2 || c->G != 1 || c->lay.pairs_hashed || getenv("CFB_NO_ROLE")) return 1;
+  if (rows < (unsigned long long)std::max(1, env_int("CFB_ROLE_MIN_ROWS", 16384))) return 1;
+  for (int k = 0; k < c->m; k++)
+    if ((uintptr_t)sc.cat[k] & 15) return 1;  // the kernel reads 4 rows of a column per 128-bit load
+  if ((uintptr_t)sc.group & 15) return 1;
+  if (c->role_state == 1 && memcmp(c->role_dom, c->lay.dom, sizeof(int) * c->m) != 0) c->role_state = 0;
+  if (c->role_state == 0) {
+    c->role_state = -1;
+    memcpy(c->role_dom, c->lay.dom, sizeof(c->role_dom));
+    const int force_bits = env_int("CFB_ROLE_BITS", 0);
+    const size_t budget = (size_t)dev_info(c->device).smem_optin - 1024;
+    cfb::RolePlan p32, p16;
+    const bool ok32 = force_bits != 16 && build_role_plan(c->lay, budget, 32, &p32);
+    const bool ok16 = force_bits != 32 && build_role_plan(c->lay, budget, 16, &p16);
+    // 32-bit cells fold once per scan instead of every 65 K rows, which measured faster than the fewer
+    // passes over the key columns that 16-bit cells buy (C3: 9 roles 4.4 G rows/s, 5 roles 4.2 G rows/s)
+    const int max_roles = std::max(1, dev_info(c->device).sms / 8);
+    const cfb::RolePlan *pick = nullptr;
+    if (ok32 && p32.n_roles <= max_roles) pick = &p32;
+    else if (ok16) pick = &p16;
+    if (pick && pick->n_roles <= max_roles) {
+      if (!c->role_plan) c->role_plan = new cfb::RolePlan;
+      *c->role_plan = *pick;
+      int words = 0;
+      for (int r = 0; r < pick->n_roles; r++) words = std::max(words, pick->words[r]);
+      c->role_roles = pick->n_roles;
+      c->role_bits = pick->bits;
+      c->role_smem = (size_t)words * 4;
+      c->role_state = 1;
+    }
+  }
+  if (c->role_state != 1) return 1;
+  const int n_reps = std::max(1, dev_info(c->device).sms / c->role_roles);
+  long long chunk = (long long)((rows + n_reps - 1) / n_reps);
+  chunk = std::min<long long>(cfb::kRoleMaxChunkRows, std::max<long long>(1024, (chunk + 1023) / 1024 * 1024));
+  const cfb::SlabShape sh = cfb::slab_shape(c->lay, 0);
+  // several fp32 slabs per CTA while they stay small (they live in L2): thins out same-address reductions
+  const int grid = c->role_roles * n_reps;
+  int n_sub = std::max(1, env_int("CFB_ROLE_SUBSLABS", 4));
+  while (n_sub > 1 && sh.floats * 4 * grid * n_sub > (48ll << 20)) n_sub /= 2;
+  int rc = ensure_slab(c, sh.floats, grid * n_sub, s);
+  if (rc) return rc;
+  cfb::RoleLaunchParams p{};
+  p.cols = sc;
+  p.lay = &c->lay;
+  p.plan = c->role_plan;
+  p.rows = rows;
+  p.chunk_rows = (int)chunk;
+  p.pair_fold_chunks = c->role_bits == 16 ? std::max(1, cfb::kRoleFoldRows16 / (int)chunk) : (1 << 30) / (int)chunk;
+  p.n_roles = c->role_roles;
+  p.n_reps = n_reps;
+  p.smem_bytes = c->role_smem;
+  p.debug_skip = env_int("CFB_ROLE_DEBUG", 0);
+  p.n_sub = n_sub;
+  p.slab = c->d_slab;
+  p.f64 = c->d_f64;
+  p.u64 = c->d_u64;
+  p.err = c->d_err;
+  p.stream = s;
+  const cudaError_t e = (c->role_bits == 16 ? kRole16 : kRole32)[c->n](p);
+  g_launches++;
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "role kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+int launch_slab(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, int do_numeric, cudaStream_t s) {
+  const cfb::SlabShape sh = cfb::slab_shape(c->lay, do_numeric);
+  const long long bytes = sh.floats * 4;
+  if (bytes > kMaxSlabBytesPerCta || getenv("CFB_NO_SLAB")) return 1;
+  int grid = dev_info(c->device).sms * 2;
+  grid = (int)std::min<long long>(grid, std::max<long long>(1, kMaxSlabBytesTotal / std::max<long long>(bytes, 1)));
+  grid = (int)std::min<unsigned long long>(grid, (rows + cfb::kSlabTile - 1) / cfb::kSlabTile);
+  grid = std::max(grid, 1);
+  int erc = ensure_slab(c, sh.floats, grid, s);
+  if (erc) return erc;
   cfb::SlabLaunchParams p{};
   p.cols = sc;
   p.d_lay = c->d_lay;
@@ -812,7 +938,10 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         int rc = hash_reserve(c, worst);
         if (rc) return rc;
       }
-      int need_generic = launch_slab(c, part, cnt, slab_numeric, s);
+      int need_generic = slab_numeric ? 1 : launch_role(c, part, cnt, s);
+      if (need_generic < 0) return need_generic;
+      if (need_generic == 0) continue;
+      need_generic = launch_slab(c, part, cnt, slab_numeric, s);
       if (need_generic < 0) return need_generic;
       if (need_generic) {  // 1 = slab too large for this shape
         const int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);
@@ -1033,6 +1162,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);
+  delete c->role_plan;
   if (c->hash.capacity) hash_free(c->hash);
   for (auto &cd : c->dict)
     if (cd.on || cd.d.table) dict_free(cd);

