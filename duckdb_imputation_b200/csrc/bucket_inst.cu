@@ -1,6 +1,6 @@
-// role_inst.cu -- explicit instantiations of role_scan_kernel for n in [CFB_INST_LO, CFB_INST_HI].
-#include "role_kernels.cuh"
-#include "role_launch.h"
+// bucket_inst.cu -- explicit instantiations of bucket_sum_kernel for n in [CFB_INST_LO, CFB_INST_HI].
+#include "bucket_kernels.cuh"
+#include "bucket_launch.h"
 
 #ifndef CFB_INST_LO
 #error "compile with -DCFB_INST_LO=<n> -DCFB_INST_HI=<n>"
@@ -8,41 +8,34 @@
 
 namespace cfb {
 
-template <int N, int BITS>
-cudaError_t role_launch(const RoleLaunchParams &p) {
-  RoleArgs a{};
+template <int N>
+cudaError_t bucket_launch(const BucketLaunchParams &p) {
+  BucketArgs a{};
   a.cols = p.cols;
+  a.n_rows = p.rows;
   const Layout &L = *p.lay;
   a.m = L.m;
+  a.total_dom = (int)L.total_dom;
+  a.tile_rows = p.tile_rows;
+  a.fold_tiles = p.fold_tiles;
   for (int c = 0; c < kMaxCat; c++) {
     a.lo[c] = L.lo[c];
     a.dom[c] = L.dom[c];
   }
   for (int c = 0; c <= kMaxCat; c++) a.cat_off[c] = (int)L.cat_off[c];
-  a.total_dom = L.total_dom;
   a.numcat_base = L.numcat_base;
-  a.pair_base = L.pair_base;
-  a.plan = *p.plan;
-  a.n_rows = p.rows;
-  a.chunk_rows = p.chunk_rows;
-  a.pair_fold_chunks = p.pair_fold_chunks;
-  a.n_reps = p.n_reps;
-  a.skip = p.skip;
-  a.n_sub = p.n_sub;
   a.slab = p.slab;
   a.f64 = p.f64;
   a.u64 = p.u64;
   a.err = p.err;
-  auto kern = role_scan_kernel<N, BITS>;
+  auto kern = bucket_sum_kernel<N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<p.n_roles * p.n_reps, kRoleThreads, p.smem_bytes, p.stream>>>(a);
+  kern<<<p.grid, kBucketThreads, p.smem_bytes, p.stream>>>(a);
   return cudaGetLastError();
 }
 
-#define CFB_INST(N)                                                     \
-  template cudaError_t role_launch<N, 16>(const RoleLaunchParams &);    \
-  template cudaError_t role_launch<N, 32>(const RoleLaunchParams &);
+#define CFB_INST(N) template cudaError_t bucket_launch<N>(const BucketLaunchParams &);
 #define CFB_IN_RANGE(N) ((N) >= CFB_INST_LO && (N) <= CFB_INST_HI)
 
 #if CFB_IN_RANGE(0)

@@ -29,6 +29,8 @@
 #include "key_dict.cuh"
 #include "pair_hash.cuh"
 #include "slab_kernels.cuh"
+#include "bucket_kernels.cuh"
+#include "bucket_launch.h"
 #include "role_kernels.cuh"
 #include "role_launch.h"
 #include "slab_launch.h"
@@ -652,6 +654,12 @@ constexpr std::array<cudaError_t (*)(const cfb::RoleLaunchParams &), sizeof...(N
 const auto kRole16 = role_table<16>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
 const auto kRole32 = role_table<32>(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
 
+template <int... Ns>
+constexpr std::array<cudaError_t (*)(const cfb::BucketLaunchParams &), sizeof...(Ns)> bucket_table(std::integer_sequence<int, Ns...>) {
+  return {{cfb::bucket_launch<Ns>...}};
+}
+const auto kBucket = bucket_table(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -735,9 +743,43 @@ bool build_role_plan(const Layout &L, size_t budget_bytes, int bits, cfb::RolePl
 
 // Categorical part through shared-memory pair tables + L2 vector reductions.  Returns 1 if this
 // shape / scan does not qualify (caller uses the slab kernel), 0 on success, <0 on error.
-int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+// Per-key payload sums of every categorical column by tile-level bucketing in shared memory
+// (bucket_kernels.cuh).  Returns 1 if the shape does not qualify, 0 on success, <0 on error.
+int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (c->kind != CFB_TRIPLE || c->m < 1 || c->G != 1 || getenv("CFB_NO_BUCKET")) return 1;
+  if (c->lay.total_dom > cfb::kBucketMaxDom) return 1;
+  const int P = cfb::pad4(1 + c->n), D = (int)c->lay.total_dom;
+  const long long budget = (long long)dev_info(c->device).smem_optin - 1024 - 8ll * D;
+  int tile = (int)(budget / (4 * P + 2 * c->m)) / cfb::kBucketThreads * cfb::kBucketThreads;
+  tile = std::min(tile, 4096);
+  if (tile < cfb::kBucketThreads) return 1;
+  const unsigned long long n_tiles = (rows + tile - 1) / tile;
+  const int grid = (int)std::min<unsigned long long>(dev_info(c->device).sms, n_tiles);
+  int rc = ensure_slab(c, (long long)D * P, grid, s);
+  if (rc) return rc;
+  cfb::BucketLaunchParams p{};
+  p.cols = sc;
+  p.lay = &c->lay;
+  p.rows = rows;
+  p.tile_rows = tile;
+  p.fold_tiles = std::max(1, 32768 / tile);  // an fp32 slab entry is folded into fp64 after at most ~32K rows of one CTA
+  p.grid = grid;
+  p.smem_bytes = cfb::bucket_smem_bytes(c->n, c->m, D, tile);
+  p.slab = c->d_slab;
+  p.f64 = c->d_f64;
+  p.u64 = c->d_u64;
+  p.err = c->d_err;
+  p.stream = s;
+  const cudaError_t e = kBucket[c->n](p);
+  g_launches++;
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "bucket kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+// Is the role kernel usable for this scan?  Builds / refreshes the plan.  1 = no, 0 = yes.
+int role_prepare(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows) {
   if (c->kind != CFB_TRIPLE || c->m < 2 || c->G != 1 || c->lay.pairs_hashed || getenv("CFB_NO_ROLE")) return 1;
-  if (rows < (unsigned long long)std::max(1, env_int("CFB_ROLE_MIN_ROWS", 16384))) return 1;
+  (void)rows;
   for (int k = 0; k < c->m; k++)
     if ((uintptr_t)sc.cat[k] & 15) return 1;  // the kernel reads 4 rows of a column per 128-bit load
   if ((uintptr_t)sc.group & 15) return 1;
@@ -767,7 +809,12 @@ int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cu
       c->role_state = 1;
     }
   }
-  if (c->role_state != 1) return 1;
+  return c->role_state == 1 ? 0 : 1;
+}
+
+// Pair counts through shared-memory tables (+ the per-key payloads as L2 vector reductions when
+// `do_sums`); call role_prepare first.
+int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, bool do_sums, cudaStream_t s) {
   const int n_reps = std::max(1, dev_info(c->device).sms / c->role_roles);
   long long chunk = (long long)((rows + n_reps - 1) / n_reps);
   chunk = std::min<long long>(cfb::kRoleMaxChunkRows, std::max<long long>(1024, (chunk + 1023) / 1024 * 1024));
@@ -776,8 +823,11 @@ int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cu
   const int grid = c->role_roles * n_reps;
   int n_sub = std::max(1, env_int("CFB_ROLE_SUBSLABS", 4));
   while (n_sub > 1 && sh.floats * 4 * grid * n_sub > (48ll << 20)) n_sub /= 2;
-  int rc = ensure_slab(c, sh.floats, grid * n_sub, s);
-  if (rc) return rc;
+  if (!do_sums) n_sub = 1;
+  else {
+    int rc = ensure_slab(c, sh.floats, grid * n_sub, s);
+    if (rc) return rc;
+  }
   cfb::RoleLaunchParams p{};
   p.cols = sc;
   p.lay = &c->lay;
@@ -788,7 +838,7 @@ int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cu
   p.n_roles = c->role_roles;
   p.n_reps = n_reps;
   p.smem_bytes = c->role_smem;
-  p.debug_skip = env_int("CFB_ROLE_DEBUG", 0);
+  p.skip = env_int("CFB_ROLE_DEBUG", 0) | (do_sums ? 0 : 2);
   p.n_sub = n_sub;
   p.slab = c->d_slab;
   p.f64 = c->d_f64;
@@ -938,10 +988,21 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         int rc = hash_reserve(c, worst);
         if (rc) return rc;
       }
-      int need_generic = slab_numeric ? 1 : launch_role(c, part, cnt, s);
-      if (need_generic < 0) return need_generic;
-      if (need_generic == 0) continue;
-      need_generic = launch_slab(c, part, cnt, slab_numeric, s);
+      if (!slab_numeric && cnt >= (unsigned long long)std::max(1, env_int("CFB_ROLE_MIN_ROWS", 16384))) {
+        // dense small domains: pair counts in shared-memory tables, per-key sums by tile bucketing
+        const bool pairs_here = role_prepare(c, part, cnt) == 0;
+        if (pairs_here || (c->m == 1 && c->kind == CFB_TRIPLE)) {
+          const int b = launch_bucket(c, part, cnt, s);
+          if (b < 0) return b;
+          if (pairs_here) {
+            const int rc = launch_role(c, part, cnt, b != 0, s);
+            if (rc < 0) return rc;
+            continue;
+          }
+          if (b == 0) continue;
+        }
+      }
+      int need_generic = launch_slab(c, part, cnt, slab_numeric, s);
       if (need_generic < 0) return need_generic;
       if (need_generic) {  // 1 = slab too large for this shape
         const int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256, (unsigned long long)dev_info(c->device).sms * 8);

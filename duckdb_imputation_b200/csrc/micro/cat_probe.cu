@@ -270,6 +270,104 @@ __global__ void __launch_bounds__(M * 32) s2_kernel(Cols c, size_t rows, double 
   }
 }
 
+// ------------------------------------------------------------------ S3: tile-level counting sort by key, bucket-owner threads
+// No atomics on floats at all: the rows of a tile are bucketed by key per column (two ATOMS per row and
+// column: count, then cursor), thread b = (column, key) then adds the payload rows of its bucket from
+// shared memory into 12 registers that live across tiles.
+constexpr int S3_T = 3072, S3_THREADS = 1024;
+__global__ void __launch_bounds__(S3_THREADS, 1) s3_kernel(Cols c, size_t rows, double *sums, int flush_tiles) {
+  extern __shared__ float4 smem_f4[];
+  float4 *pay = smem_f4;                                                     // [S3_T][3]
+  unsigned short *ids = reinterpret_cast<unsigned short *>(pay + S3_T * 3);  // [M][S3_T]
+  unsigned *off = reinterpret_cast<unsigned *>(ids + M * S3_T);              // [M*DOM] exclusive starts
+  unsigned *cur = off + M * DOM;                                             // [M*DOM] counts, then cursors
+  const int tid = threadIdx.x;
+  float4 acc[3] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+  const size_t ntiles = (rows + S3_T - 1) / S3_T;
+  int since = 0;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t lo = tile * S3_T;
+    const int cnt = (int)min((size_t)S3_T, rows - lo);
+    for (int i = tid; i < M * DOM; i += S3_THREADS) cur[i] = 0;
+    __syncthreads();
+    // pass 1: payload rows into shared memory, bucket sizes
+#pragma unroll
+    for (int u = 0; u < S3_T / S3_THREADS; u++) {
+      const int row = tid + u * S3_THREADS;
+      if (row < cnt) {
+        const size_t r = lo + row;
+        pay[row * 3 + 0] = make_float4(1.f, c.num[0][r], c.num[1][r], c.num[2][r]);
+        pay[row * 3 + 1] = make_float4(c.num[3][r], c.num[4][r], c.num[5][r], c.num[6][r]);
+        pay[row * 3 + 2] = make_float4(c.num[7][r], c.num[8][r], c.num[9][r], 0.f);
+#pragma unroll
+        for (int k = 0; k < M; k++) atomicAdd(&cur[k * DOM + c.cat[k][r]], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the bucket sizes, one warp per column
+    {
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < M) {
+        unsigned run = 0;
+        for (int base = 0; base < DOM; base += 32) {
+          const int i = base + lane;
+          const unsigned v = i < DOM ? cur[w * DOM + i] : 0;
+          unsigned x = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+          }
+          if (i < DOM) {
+            off[w * DOM + i] = run + x - v;
+            cur[w * DOM + i] = run + x - v;
+          }
+          run += __shfl_sync(0xffffffffu, x, 31);
+        }
+      }
+    }
+    __syncthreads();
+    // pass 2: row ids in bucket order
+#pragma unroll
+    for (int u = 0; u < S3_T / S3_THREADS; u++) {
+      const int row = tid + u * S3_THREADS;
+      if (row < cnt) {
+        const size_t r = lo + row;
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+          const unsigned pos = atomicAdd(&cur[k * DOM + c.cat[k][r]], 1u);
+          ids[k * S3_T + pos] = (unsigned short)row;
+        }
+      }
+    }
+    __syncthreads();
+    // reduce: thread b = (column, key) adds the payload rows of its bucket
+    if (tid < M * DOM) {
+      const int k = tid / DOM;
+      const unsigned b0 = off[tid], b1 = cur[tid];
+      for (unsigned i = b0; i < b1; i++) {
+        const int row = ids[k * S3_T + i];
+        const float4 p0 = pay[row * 3], p1 = pay[row * 3 + 1], p2 = pay[row * 3 + 2];
+        acc[0].x += p0.x; acc[0].y += p0.y; acc[0].z += p0.z; acc[0].w += p0.w;
+        acc[1].x += p1.x; acc[1].y += p1.y; acc[1].z += p1.z; acc[1].w += p1.w;
+        acc[2].x += p2.x; acc[2].y += p2.y; acc[2].z += p2.z; acc[2].w += p2.w;
+      }
+    }
+    __syncthreads();
+    if (++since >= flush_tiles || tile + gridDim.x >= ntiles) {
+      since = 0;
+      if (tid < M * DOM) {
+        double *dst = sums + (size_t)tid * P;
+        const float v[12] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w, acc[2].x, acc[2].y, acc[2].z, acc[2].w};
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+          if (v[j] != 0.f) atomicAdd(dst + j, (double)v[j]);
+        acc[0] = acc[1] = acc[2] = make_float4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ S1: warp-private fp32 tables, plain RMW
 constexpr int S1_WARPS = 4, S1_ROWS = 10;  // 10 rows x 3 lanes (float4 each) per step
 __global__ void __launch_bounds__(S1_WARPS * 32) s1_kernel(Cols c, size_t rows, double *sums, int chunk_rows) {
@@ -483,6 +581,23 @@ int main(int argc, char **argv) {
   }
   std::vector<double> s2_host(sum_cells);
   CK(cudaMemcpy(s2_host.data(), sums1, sum_cells * 8, cudaMemcpyDeviceToHost));
+  // S3
+  const int s3_smem = S3_T * 48 + M * S3_T * 2 + 2 * M * DOM * 4;
+  CK(cudaFuncSetAttribute(s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s3_smem));
+  for (int rep = 0; rep < 2; rep++) {
+    CK(cudaMemset(sums1, 0, sum_cells * 8));
+    CK(cudaEventRecord(e0));
+    s3_kernel<<<sms, S3_THREADS, s3_smem>>>(c, rows, sums1, 10);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  }
+  CK(cudaEventElapsedTime(&ms, e0, e1)); report("S3 sums: tile counting sort + bucket-owner threads (no float atomics)", ms);
+  std::vector<double> s3_host(sum_cells);
+  CK(cudaMemcpy(s3_host.data(), sums1, sum_cells * 8, cudaMemcpyDeviceToHost));
+  {
+    double w3 = 0;
+    for (size_t i = 0; i < sum_cells; i++) if (s2_host[i] != 0) w3 = fmax(w3, fabs(s3_host[i] - s2_host[i]) / fabs(s2_host[i]));
+    printf("   S3 vs S2: max rel diff %.3g\n", w3);
+  }
   // S0
   for (int rep = 0; rep < 2; rep++) {
     CK(cudaMemset(sums0, 0, sum_cells * 4));

@@ -60,7 +60,7 @@ struct RoleArgs {
   int pair_fold_chunks;  // fold the pair tables every this many chunks of a CTA (16-bit cells: <= kRoleFoldRows16 rows)
   int n_reps;            // replicas per role: gridDim.x = n_roles * n_reps
   int m;
-  int debug_skip;  // measurement only (CFB_ROLE_DEBUG): 1 = no pair counts, 2 = no per-key payloads
+  int skip;  // bit 0: no pair counts (measurement only), bit 1: no per-key payloads (bucket_sum_kernel does them)
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];  // of the Layout
   long long total_dom, numcat_base, pair_base;
   int n_sub;    // fp32 slabs per CTA (1, 2 or 4): threads are spread over them to thin out same-address reductions
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
       // first column are reloaded only when k changes (a CTA-uniform branch).
       int prev_k = -1;
       unsigned sk[4] = {0, 0, 0, 0};
-      for (int t = 0; t < ((a.debug_skip & 1) ? 0 : nt); t++) {
+      for (int t = 0; t < ((a.skip & 1) ? 0 : nt); t++) {
         const RoleTable &d = a.plan.tbl[role][t];
         if (d.k != prev_k) {
           prev_k = d.k;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
       // reductions, one quad of the payload at a time (4 rows x 4 values in registers)
       const bool sums_mine = tile == role;
       tile = tile + 1 == n_roles ? 0 : tile + 1;
-      if (sums_mine && !(a.debug_skip & 2)) {
+      if (sums_mine && !(a.skip & 2)) {
 #pragma unroll
         for (int q = 0; q < P / 4; q++) {
           float4 x[4];  // x[e] = payload element 4q+e of the 4 rows
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
     // fold this CTA's slab into the fp64 / u64 state once it has taken kRoleMaxChunkRows rows (bounds every fp32 run)
     for (int t = 0, who = (int)(ch % n_roles); t * 4 * kRoleThreads < (int)(hi - lo); t++, who = who + 1 == n_roles ? 0 : who + 1)
       if (who == role) slab_rows += 4 * kRoleThreads;
-    if (slab_rows + 2 * 4 * kRoleThreads > kRoleMaxChunkRows || ch + a.n_reps >= n_chunks) {
+    if (!(a.skip & 2) && (slab_rows + 2 * 4 * kRoleThreads > kRoleMaxChunkRows || ch + a.n_reps >= n_chunks)) {
       slab_rows = 0;
       for (long long i = threadIdx.x; i < a.total_dom * P; i += kRoleThreads) {
         float v = 0.f;

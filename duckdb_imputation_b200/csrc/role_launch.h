@@ -15,7 +15,7 @@ struct RoleLaunchParams {
   const RolePlan *plan;  // host copy (travels in the kernel parameters)
   unsigned long long rows;
   int chunk_rows, pair_fold_chunks, n_roles, n_reps;
-  int debug_skip, n_sub;
+  int skip, n_sub;
   size_t smem_bytes;  // dynamic shared memory: the largest role's tables + the slot scratch
   float *slab;
   double *f64;
