@@ -16,6 +16,9 @@ cudaError_t bucket_launch(const BucketLaunchParams &p) {
   const Layout &L = *p.lay;
   a.m = L.m;
   a.total_dom = (int)L.total_dom;
+  a.n_groups = L.n_groups;
+  a.F = L.F;
+  a.U = L.U;
   a.tile_rows = p.tile_rows;
   a.fold_tiles = p.fold_tiles;
   for (int c = 0; c < kMaxCat; c++) {

@@ -28,32 +28,34 @@
 namespace cfb {
 
 constexpr int kBucketThreads = 1024;
-constexpr int kBucketMaxDom = 4096;  // sum of the domains: two u32 tables of this size live in shared memory
+constexpr int kBucketMaxDom = 4096;  // slots x sum of the domains: two u32 tables of this size live in shared memory
 
 struct BucketArgs {
   ScanCols cols;
   unsigned long long n_rows;
   int m, total_dom;
+  int n_groups;    // GROUP BY slots: bucket = (slot, column, key); n_groups * total_dom <= kBucketMaxDom
+  long long F, U;  // per-slot strides of the f64 / u64 state
   int tile_rows;   // multiple of kBucketThreads
   int fold_tiles;  // fold the slab into the state every this many tiles of a CTA
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];
   long long numcat_base;
-  float *slab;  // [gridDim.x][total_dom * P], all zero on entry and on exit
+  float *slab;  // [gridDim.x][n_groups * total_dom * P], all zero on entry and on exit
   double *f64;
   unsigned long long *u64;
   int *err;
 };
 
 // dynamic shared memory: payload tile, row ids in bucket order, bucket starts and cursors
-__host__ __device__ inline size_t bucket_smem_bytes(int n, int m, int total_dom, int tile_rows) {
-  return (size_t)tile_rows * pad4(1 + n) * 4 + (size_t)m * tile_rows * 2 + (size_t)2 * total_dom * 4;
+__host__ __device__ inline size_t bucket_smem_bytes(int n, int m, int buckets, int tile_rows) {
+  return (size_t)tile_rows * pad4(1 + n) * 4 + (size_t)m * tile_rows * 2 + (size_t)2 * buckets * 4;
 }
 
 template <int N>
 __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __grid_constant__ BucketArgs a) {
   extern __shared__ float4 bucket_smem[];
   constexpr int P = pad4(1 + N), Q = P / 4;
-  const int T = a.tile_rows, m = a.m, D = a.total_dom, tid = threadIdx.x;
+  const int T = a.tile_rows, m = a.m, D = a.n_groups * a.total_dom, tid = threadIdx.x;  // D buckets
   float4 *pay = bucket_smem;                                             // [T][Q]
   unsigned short *ids = reinterpret_cast<unsigned short *>(pay + (size_t)T * Q);  // [m * T] row ids, bucket order
   unsigned *off = reinterpret_cast<unsigned *>(ids + (size_t)m * T);     // [D] first entry of the bucket
@@ -72,12 +74,14 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __g
     bool bad = false;
     for (int row = tid; row < cnt; row += kBucketThreads) {
       const unsigned long long r = lo + row;
+      int gbase = 0;
       if (a.cols.group) {
         const int g = a.cols.group[r];
-        if (g != 0) {  // < 0: filtered row; >= 1: not a slot of this context
+        if (g < 0 || g >= a.n_groups) {  // < 0: filtered row
           if (g > 0) atomicExch(a.err, 2);
           continue;
         }
+        gbase = g * a.total_dom;
       }
       float v[P];
       v[0] = 1.f;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __g
 #pragma unroll
         for (int e = 0; e < 4; e++)
           if (c0 + e < m) {
-            if (s[e] < (unsigned)a.dom[c0 + e]) atomicAdd(&cur[a.cat_off[c0 + e] + s[e]], 1u);
+            if (s[e] < (unsigned)a.dom[c0 + e]) atomicAdd(&cur[gbase + a.cat_off[c0 + e] + s[e]], 1u);
             else bad = true;
           }
       }
@@ -141,14 +145,19 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __g
     // ---- 3. row ids in bucket order
     for (int row = tid; row < cnt; row += kBucketThreads) {
       const unsigned long long r = lo + row;
-      if (a.cols.group && a.cols.group[r] != 0) continue;
+      int gbase = 0;
+      if (a.cols.group) {
+        const int g = a.cols.group[r];
+        if (g < 0 || g >= a.n_groups) continue;
+        gbase = g * a.total_dom;
+      }
       for (int c0 = 0; c0 < m; c0 += 4) {
         unsigned s[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) s[e] = c0 + e < m ? (unsigned)(a.cols.cat[c0 + e][r] - a.lo[c0 + e]) : 0u;
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          if (c0 + e < m && s[e] < (unsigned)a.dom[c0 + e]) ids[atomicAdd(&cur[a.cat_off[c0 + e] + s[e]], 1u)] = (unsigned short)row;
+          if (c0 + e < m && s[e] < (unsigned)a.dom[c0 + e]) ids[atomicAdd(&cur[gbase + a.cat_off[c0 + e] + s[e]], 1u)] = (unsigned short)row;
       }
     }
     __syncthreads();
@@ -183,11 +192,11 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __g
         const float v = __ldcg(slab + i);
         if (v == 0.f) continue;
         __stcg(slab + i, 0.f);
-        const int key = i / P, j = i % P;
+        const int b = i / P, j = i % P, g = b / a.total_dom, key = b % a.total_dom;
         if (j == 0)
-          red_u64(a.u64 + 1 + key, (unsigned long long)v);
+          red_u64(a.u64 + g * a.U + 1 + key, (unsigned long long)v);
         else if (j <= N)
-          atomicAdd(a.f64 + a.numcat_base + (long long)(j - 1) * D + key, (double)v);
+          atomicAdd(a.f64 + g * a.F + a.numcat_base + (long long)(j - 1) * a.total_dom + key, (double)v);
       }
       __syncthreads();
     }

@@ -719,7 +719,8 @@ bool build_role_plan(const Layout &L, size_t budget_bytes, int bits, cfb::RolePl
   for (int k = 0; k < L.m; k++) {
     for (int l = k + 1; l < L.m; l++) {
       const long long cells = (long long)L.dom[k] * L.dom[l];
-      const long long words = bits == 32 ? cells : (cells + 1) / 2;
+      const long long gwords = bits == 32 ? cells : (cells + 1) / 2;
+      const long long words = gwords * L.n_groups;  // one sub-table per GROUP BY slot
       if (words > budget_words) return false;
       if (used + words > budget_words || out->n_tables[role] == cfb::kRoleMaxTables) {
         if (++role == cfb::kRoleMaxRoles) return false;
@@ -730,6 +731,7 @@ bool build_role_plan(const Layout &L, size_t budget_bytes, int bits, cfb::RolePl
       t.l = l;
       t.dom_l = L.dom[l];
       t.cells = (int)cells;
+      t.gwords = (int)gwords;
       t.word_off = (int)used;
       if (L.pair_off[k * L.m + l] > INT_MAX) return false;
       t.state_off = (int)L.pair_off[k * L.m + l];
@@ -746,9 +748,9 @@ bool build_role_plan(const Layout &L, size_t budget_bytes, int bits, cfb::RolePl
 // Per-key payload sums of every categorical column by tile-level bucketing in shared memory
 // (bucket_kernels.cuh).  Returns 1 if the shape does not qualify, 0 on success, <0 on error.
 int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
-  if (c->kind != CFB_TRIPLE || c->m < 1 || c->G != 1 || getenv("CFB_NO_BUCKET")) return 1;
-  if (c->lay.total_dom > cfb::kBucketMaxDom) return 1;
-  const int P = cfb::pad4(1 + c->n), D = (int)c->lay.total_dom;
+  if (c->kind != CFB_TRIPLE || c->m < 1 || getenv("CFB_NO_BUCKET")) return 1;
+  if (c->lay.total_dom * c->G > cfb::kBucketMaxDom) return 1;
+  const int P = cfb::pad4(1 + c->n), D = (int)c->lay.total_dom * c->G;  // buckets
   const long long budget = (long long)dev_info(c->device).smem_optin - 1024 - 8ll * D;
   int tile = (int)(budget / (4 * P + 2 * c->m)) / cfb::kBucketThreads * cfb::kBucketThreads;
   tile = std::min(tile, 4096);
@@ -778,7 +780,7 @@ int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, 
 
 // Is the role kernel usable for this scan?  Builds / refreshes the plan.  1 = no, 0 = yes.
 int role_prepare(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows) {
-  if (c->kind != CFB_TRIPLE || c->m < 2 || c->G != 1 || c->lay.pairs_hashed || getenv("CFB_NO_ROLE")) return 1;
+  if (c->kind != CFB_TRIPLE || c->m < 2 || c->lay.pairs_hashed || getenv("CFB_NO_ROLE")) return 1;
   (void)rows;
   for (int k = 0; k < c->m; k++)
     if ((uintptr_t)sc.cat[k] & 15) return 1;  // the kernel reads 4 rows of a column per 128-bit load
@@ -994,12 +996,13 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         if (pairs_here || (c->m == 1 && c->kind == CFB_TRIPLE)) {
           const int b = launch_bucket(c, part, cnt, s);
           if (b < 0) return b;
-          if (pairs_here) {
+          if (pairs_here && (b == 0 || c->G == 1)) {  // (the role kernel's own payload path has single-slot slabs)
             const int rc = launch_role(c, part, cnt, b != 0, s);
             if (rc < 0) return rc;
             continue;
           }
-          if (b == 0) continue;
+          if (b == 0 && c->m == 1) continue;
+          if (b == 0) return fail(CFB_ERR_CUDA, "internal: bucket sums without pair counts");
         }
       }
       int need_generic = launch_slab(c, part, cnt, slab_numeric, s);

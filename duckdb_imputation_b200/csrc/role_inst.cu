@@ -14,6 +14,8 @@ cudaError_t role_launch(const RoleLaunchParams &p) {
   a.cols = p.cols;
   const Layout &L = *p.lay;
   a.m = L.m;
+  a.n_groups = L.n_groups;
+  a.U = L.U;
   for (int c = 0; c < kMaxCat; c++) {
     a.lo[c] = L.lo[c];
     a.dom[c] = L.dom[c];

@@ -40,7 +40,8 @@ constexpr int kRoleFoldRows16 = 65024;    // <= 65535: rows a 16-bit cell can ta
 struct RoleTable {
   int k, l;             // the pair (k < l)
   int dom_l;            // cell = slot_k * dom_l + slot_l
-  int cells;            // dom_k * dom_l
+  int cells;            // dom_k * dom_l (per GROUP BY slot)
+  int gwords;           // 32-bit words of one slot's cells; the table holds n_groups of them
   int word_off;         // first 32-bit word of the table in the role's shared memory
   int state_off;        // Layout::pair_off[k*m+l] (dense pair regions are < 2 GB: kDensePairBytes)
 };
@@ -59,7 +60,8 @@ struct RoleArgs {
   int chunk_rows;        // <= kRoleMaxChunkRows
   int pair_fold_chunks;  // fold the pair tables every this many chunks of a CTA (16-bit cells: <= kRoleFoldRows16 rows)
   int n_reps;            // replicas per role: gridDim.x = n_roles * n_reps
-  int m;
+  int m, n_groups;
+  long long U;  // per-slot stride of the u64 state
   int skip;  // bit 0: no pair counts (measurement only), bit 1: no per-key payloads (bucket_sum_kernel does them)
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];  // of the Layout
   long long total_dom, numcat_base, pair_base;
@@ -110,14 +112,15 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
     // what hides the L2 / HBM latency (the loop over tables is data dependent and cannot be unrolled)
     for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
       bool on[4] = {true, r + 1 < hi, r + 2 < hi, r + 3 < hi};
+      int gv[4] = {0, 0, 0, 0};  // GROUP BY slot of the row
       bool bad = false;
       if (a.cols.group) {
         const int4 g = load_rows4<int4>(a.cols.group, r, hi);
-        const int gv[4] = {g.x, g.y, g.z, g.w};
+        gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (on[i] && gv[i] >= 1) atomicExch(a.err, 2);
-          on[i] = on[i] && gv[i] == 0;  // < 0: filtered row
+          if (on[i] && gv[i] >= a.n_groups) atomicExch(a.err, 2);
+          on[i] = on[i] && gv[i] >= 0 && gv[i] < a.n_groups;  // < 0: filtered row
         }
       }
       // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the
@@ -145,9 +148,9 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
           }
           const unsigned cell = sk[i] * dom_l + sl[i];
           if constexpr (BITS == 32)
-            atomicAdd(&role_smem[d.word_off + cell], 1u);
+            atomicAdd(&role_smem[d.word_off + gv[i] * d.gwords + cell], 1u);
           else
-            atomicAdd(&role_smem[d.word_off + (cell >> 1)], 1u << ((cell & 1u) * 16));
+            atomicAdd(&role_smem[d.word_off + gv[i] * d.gwords + (cell >> 1)], 1u << ((cell & 1u) * 16));
         }
       }
       // per-key payload [1, x_0..x_{N-1}] of the columns this role owns in this chunk: L2 vector
@@ -191,10 +194,11 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
     // fold the pair tables into the u64 state and zero them
     const bool fold_pairs = ++since_fold >= a.pair_fold_chunks || ch + a.n_reps >= n_chunks;
     if (fold_pairs) since_fold = 0;
-    for (int t = 0; fold_pairs && t < nt; t++) {
-      const RoleTable &d = a.plan.tbl[role][t];
-      unsigned long long *dst = pairs + d.state_off;
-      unsigned *src = role_smem + d.word_off;
+    for (int tg = 0; fold_pairs && tg < nt * a.n_groups; tg++) {
+      const RoleTable &d = a.plan.tbl[role][tg / a.n_groups];
+      const int g = tg % a.n_groups;
+      unsigned long long *dst = pairs + g * a.U + d.state_off;
+      unsigned *src = role_smem + d.word_off + g * d.gwords;
       if constexpr (BITS == 32) {
         for (int i = threadIdx.x; i < d.cells; i += kRoleThreads) {
           const unsigned v = src[i];
