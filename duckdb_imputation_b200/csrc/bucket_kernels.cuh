@@ -11,9 +11,9 @@
 //      the bucket sizes (bucket = (column, key); one integer ATOMS per row and column);
 //   2. block-wide exclusive scan of the bucket sizes;
 //   3. every thread writes its row ids in bucket order (a second ATOMS per row and column);
-//   4. thread b adds up the payload rows of bucket b, b + 1024, ... with plain LDS.128 / FADD and
-//      adds the result to this CTA's fp32 slab (global, L2-resident) with a plain load/store -- the
-//      bucket has exactly one owner thread in the CTA;
+//   4. the payload rows of a bucket are added up by its owner lanes (one per 16-byte quad of the payload)
+//      with plain LDS.128 / FADD; the result is added to this CTA's fp32 slab (global, L2-resident) with
+//      a plain load/store -- a bucket has exactly one set of owner lanes in the CTA;
 //   5. every `fold_tiles` tiles (<= ~32 K rows: bounds every fp32 run) the slab is folded into the
 //      fp64 / u64 state.
 // Measured on the B200 (C3 shape, profiles/r01_cat_probe.txt): 14.5 G rows/s against 6.6 G rows/s for
@@ -161,27 +161,25 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_sum_kernel(const __g
       }
     }
     __syncthreads();
-    // ---- 4. every bucket is added up by its owner thread and goes to the CTA's slab
-    for (int b = tid; b < D; b += kBucketThreads) {
-      const unsigned b0 = off[b], b1 = cur[b];
-      if (b0 == b1) continue;
-      float4 acc[Q];
-#pragma unroll
-      for (int q = 0; q < Q; q++) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (unsigned i = b0; i < b1; i++) {
-        const float4 *p = pay + (size_t)ids[i] * Q;
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-          const float4 w = p[q];
-          acc[q].x += w.x, acc[q].y += w.y, acc[q].z += w.z, acc[q].w += w.w;
+    // ---- 4. every bucket is added up by its Q owner lanes (one quad of the payload each: the lanes of a
+    //         bucket read one payload row as contiguous 16-byte pieces) and goes to the CTA's slab
+    {
+      constexpr int BPW = 32 / Q;  // buckets per warp and pass
+      const int lane = tid & 31, bw = lane / Q, q = lane - bw * Q;
+      for (int base = (tid >> 5) * BPW; base < D; base += (kBucketThreads / 32) * BPW) {
+        const int b = base + bw;
+        if (bw >= BPW || b >= D) continue;
+        const unsigned b0 = off[b], b1 = cur[b];
+        if (b0 == b1) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned i = b0; i < b1; i++) {
+          const float4 w = pay[(size_t)ids[i] * Q + q];
+          acc.x += w.x, acc.y += w.y, acc.z += w.z, acc.w += w.w;
         }
-      }
-      float4 *dst = reinterpret_cast<float4 *>(slab + (size_t)b * P);
-#pragma unroll
-      for (int q = 0; q < Q; q++) {
-        float4 w = __ldcg(dst + q);
-        w.x += acc[q].x, w.y += acc[q].y, w.z += acc[q].z, w.w += acc[q].w;
-        __stcg(dst + q, w);
+        float4 *dst = reinterpret_cast<float4 *>(slab + (size_t)b * P) + q;
+        float4 w = __ldcg(dst);
+        w.x += acc.x, w.y += acc.y, w.z += acc.z, w.w += acc.w;
+        __stcg(dst, w);
       }
     }
     __syncthreads();

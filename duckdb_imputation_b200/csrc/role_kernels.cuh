@@ -86,6 +86,100 @@ __device__ __forceinline__ T4 load_rows4(const T *col, unsigned long long r, uns
   return v;
 }
 
+// One step of a thread: 4 consecutive rows [r, r+4) against the pair tables of the CTA's role (and, when
+// `sums_mine`, their per-key payloads).  TAIL: the rows may run past `hi`.
+template <int N, int BITS, bool TAIL>
+__device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, unsigned *role_smem, float *slab,
+                                          unsigned long long r, unsigned long long hi, bool sums_mine) {
+  constexpr int P = pad4(1 + N);
+  auto rows4 = [&](const int *col) {
+    if constexpr (TAIL) return load_rows4<int4>(col, r, hi);
+    else return *reinterpret_cast<const int4 *>(col + r);
+  };
+  bool on[4] = {true, !TAIL || r + 1 < hi, !TAIL || r + 2 < hi, !TAIL || r + 3 < hi};
+  int gv[4] = {0, 0, 0, 0};  // GROUP BY slot of the row
+  bool bad = false;
+  if (a.cols.group) {
+    const int4 g = rows4(a.cols.group);
+    gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (on[i] && gv[i] >= a.n_groups) atomicExch(a.err, 2);
+      on[i] = on[i] && gv[i] >= 0 && gv[i] < a.n_groups;  // < 0: filtered row
+    }
+  }
+  // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the first
+  // column (and whether the row counts at all) are refreshed only when k changes (a CTA-uniform branch).
+  int prev_k = -1;
+  unsigned sk[4] = {0, 0, 0, 0};
+  bool ok[4] = {false, false, false, false};
+  for (int t = 0; t < ((a.skip & 1) ? 0 : nt); t++) {
+    const RoleTable &d = a.plan.tbl[role][t];
+    if (d.k != prev_k) {
+      prev_k = d.k;
+      const int4 v = rows4(a.cols.cat[d.k]);
+      const int lo_k = a.lo[d.k];
+      const unsigned dom_k = (unsigned)a.dom[d.k];
+      sk[0] = (unsigned)(v.x - lo_k), sk[1] = (unsigned)(v.y - lo_k), sk[2] = (unsigned)(v.z - lo_k), sk[3] = (unsigned)(v.w - lo_k);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ok[i] = on[i] && sk[i] < dom_k;
+        bad |= on[i] && !ok[i];
+      }
+    }
+    const int4 v = rows4(a.cols.cat[d.l]);
+    const int lo_l = a.lo[d.l];
+    const unsigned sl[4] = {(unsigned)(v.x - lo_l), (unsigned)(v.y - lo_l), (unsigned)(v.z - lo_l), (unsigned)(v.w - lo_l)};
+    const unsigned dom_l = (unsigned)d.dom_l;
+    unsigned *tbl = role_smem + d.word_off;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool hit = ok[i] && sl[i] < dom_l;
+      bad |= ok[i] && !hit;
+      if (!hit) continue;
+      unsigned cell = sk[i] * dom_l + sl[i];
+      if (a.n_groups > 1) cell += (unsigned)gv[i] * (unsigned)d.gwords * (BITS == 32 ? 1u : 2u);
+      if constexpr (BITS == 32)
+        atomicAdd(tbl + cell, 1u);
+      else
+        atomicAdd(tbl + (cell >> 1), 1u << ((cell & 1u) * 16));
+    }
+  }
+  // per-key payload [1, x_0..x_{N-1}] of all columns when this tile is this role's: L2 vector reductions,
+  // one quad of the payload at a time (4 rows x 4 values in registers)
+  if (sums_mine && !(a.skip & 2)) {
+#pragma unroll
+    for (int q = 0; q < P / 4; q++) {
+      float4 x[4];  // x[e] = payload element 4q+e of the 4 rows
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        constexpr int kNone = -1;
+        const int col = 4 * q + e - 1;  // payload element 0 is the count
+        if (col == kNone) x[e] = make_float4(1.f, 1.f, 1.f, 1.f);
+        else if (col < N) x[e] = load_rows4<float4>(a.cols.num[col < N ? col : 0], r, hi);
+        else x[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int c = 0; c < a.m; c++) {
+        const int4 v = rows4(a.cols.cat[c]);
+        const int lo_c = a.lo[c];
+        const unsigned sc[4] = {(unsigned)(v.x - lo_c), (unsigned)(v.y - lo_c), (unsigned)(v.z - lo_c), (unsigned)(v.w - lo_c)};
+        const float xr[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (!on[i]) continue;
+          if (sc[i] >= (unsigned)a.dom[c]) {
+            bad = true;
+            continue;
+          }
+          red_v4(slab + (size_t)(a.cat_off[c] + (int)sc[i]) * P + 4 * q, xr[i][0], xr[i][1], xr[i][2], xr[i][3]);
+        }
+      }
+    }
+  }
+  if (bad) atomicExch(a.err, 1);  // a key outside the declared domain: the scan reports CFB_ERR_DOMAIN
+}
+
 template <int N, int BITS>
 __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid_constant__ RoleArgs a) {
   extern __shared__ unsigned role_smem[];  // [plan.words[role]] pair tables of this CTA's role
@@ -110,84 +204,17 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
     int tile = (int)(ch % n_roles);
     // every thread takes 4 consecutive rows per step: keys and values arrive as 128-bit loads, which is
     // what hides the L2 / HBM latency (the loop over tables is data dependent and cannot be unrolled)
-    for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
-      bool on[4] = {true, r + 1 < hi, r + 2 < hi, r + 3 < hi};
-      int gv[4] = {0, 0, 0, 0};  // GROUP BY slot of the row
-      bool bad = false;
-      if (a.cols.group) {
-        const int4 g = load_rows4<int4>(a.cols.group, r, hi);
-        gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (on[i] && gv[i] >= a.n_groups) atomicExch(a.err, 2);
-          on[i] = on[i] && gv[i] >= 0 && gv[i] < a.n_groups;  // < 0: filtered row
-        }
+    // the last chunk of a table whose row count is not a multiple of 4 takes the variant with tail checks
+    if ((hi - lo) % 4 == 0) {
+      for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+        role_step<N, BITS, false>(a, role, nt, role_smem, slab, r, hi, tile == role);
+        tile = tile + 1 == n_roles ? 0 : tile + 1;
       }
-      // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the
-      // first column are reloaded only when k changes (a CTA-uniform branch).
-      int prev_k = -1;
-      unsigned sk[4] = {0, 0, 0, 0};
-      for (int t = 0; t < ((a.skip & 1) ? 0 : nt); t++) {
-        const RoleTable &d = a.plan.tbl[role][t];
-        if (d.k != prev_k) {
-          prev_k = d.k;
-          const int4 v = load_rows4<int4>(a.cols.cat[d.k], r, hi);
-          const int lo_k = a.lo[d.k];
-          sk[0] = (unsigned)(v.x - lo_k), sk[1] = (unsigned)(v.y - lo_k), sk[2] = (unsigned)(v.z - lo_k), sk[3] = (unsigned)(v.w - lo_k);
-        }
-        const int4 v = load_rows4<int4>(a.cols.cat[d.l], r, hi);
-        const int lo_l = a.lo[d.l];
-        const unsigned sl[4] = {(unsigned)(v.x - lo_l), (unsigned)(v.y - lo_l), (unsigned)(v.z - lo_l), (unsigned)(v.w - lo_l)};
-        const unsigned dom_k = (unsigned)a.dom[d.k], dom_l = (unsigned)d.dom_l;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (!on[i]) continue;
-          if (sk[i] >= dom_k || sl[i] >= dom_l) {
-            bad = true;
-            continue;
-          }
-          const unsigned cell = sk[i] * dom_l + sl[i];
-          if constexpr (BITS == 32)
-            atomicAdd(&role_smem[d.word_off + gv[i] * d.gwords + cell], 1u);
-          else
-            atomicAdd(&role_smem[d.word_off + gv[i] * d.gwords + (cell >> 1)], 1u << ((cell & 1u) * 16));
-        }
+    } else {
+      for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+        role_step<N, BITS, true>(a, role, nt, role_smem, slab, r, hi, tile == role);
+        tile = tile + 1 == n_roles ? 0 : tile + 1;
       }
-      // per-key payload [1, x_0..x_{N-1}] of the columns this role owns in this chunk: L2 vector
-      // reductions, one quad of the payload at a time (4 rows x 4 values in registers)
-      const bool sums_mine = tile == role;
-      tile = tile + 1 == n_roles ? 0 : tile + 1;
-      if (sums_mine && !(a.skip & 2)) {
-#pragma unroll
-        for (int q = 0; q < P / 4; q++) {
-          float4 x[4];  // x[e] = payload element 4q+e of the 4 rows
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            constexpr int kNone = -1;
-            const int col = 4 * q + e - 1;  // payload element 0 is the count
-            if (col == kNone) x[e] = make_float4(1.f, 1.f, 1.f, 1.f);
-            else if (col < N) x[e] = load_rows4<float4>(a.cols.num[col < N ? col : 0], r, hi);
-            else x[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          for (int c = 0; c < m; c++) {
-            const int4 v = load_rows4<int4>(a.cols.cat[c], r, hi);
-            const int lo_c = a.lo[c];
-            const unsigned sc[4] = {(unsigned)(v.x - lo_c), (unsigned)(v.y - lo_c), (unsigned)(v.z - lo_c), (unsigned)(v.w - lo_c)};
-            const float xr[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
-                                    {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              if (!on[i]) continue;
-              if (sc[i] >= (unsigned)a.dom[c]) {
-                bad = true;
-                continue;
-              }
-              red_v4(slab + (size_t)(a.cat_off[c] + (int)sc[i]) * P + 4 * q, xr[i][0], xr[i][1], xr[i][2], xr[i][3]);
-            }
-          }
-        }
-      }
-      if (bad) atomicExch(a.err, 1);  // a key outside the declared domain: the scan reports CFB_ERR_DOMAIN
     }
     __threadfence();
     __syncthreads();
