@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -28,6 +29,7 @@
 #include "group_kernel.cuh"
 #include "key_dict.cuh"
 #include "pair_hash.cuh"
+#include "predict_kernel.cuh"
 #include "slab_kernels.cuh"
 #include "bucket_kernels.cuh"
 #include "bucket_launch.h"
@@ -1126,6 +1128,203 @@ inline void gather(T *dst, const T *src, const uint32_t *sel, size_t first, size
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------ model scores (MICE write-back)
+struct cfb_model {
+  int device = 0;
+  double *d_model = nullptr;
+  int *d_map = nullptr;
+  cfb::PredictArgs args{};
+  size_t smem = 0;
+};
+
+namespace {
+
+int predict_launch(cfb_model *M, const float *const *num, const int32_t *const *cat, const int32_t *mask, size_t rows,
+                   int mode, void *d_out, cudaStream_t s) {
+  if (mode != CFB_PREDICT_SCORE && mode != CFB_PREDICT_ARGMAX) return fail(CFB_ERR_INVALID, "unknown predict mode %d", mode);
+  cfb::PredictArgs a = M->args;
+  bool aligned = (((uintptr_t)d_out | (uintptr_t)mask) & 15) == 0;
+  for (int k = 0; k < a.n; k++) {
+    if (!num[k]) return fail(CFB_ERR_INVALID, "numeric column %d is NULL", k);
+    a.cols.num[k] = num[k];
+    aligned = aligned && ((uintptr_t)num[k] & 15) == 0;
+  }
+  for (int k = 0; k < a.m; k++) {
+    if (!cat[k]) return fail(CFB_ERR_INVALID, "categorical column %d is NULL", k);
+    a.cols.cat[k] = cat[k];
+    aligned = aligned && ((uintptr_t)cat[k] & 15) == 0;
+  }
+  a.cols.group = mask;
+  a.n_rows = rows;
+  a.mode = mode;
+  a.out = d_out;
+  const int device = M->device;
+  static std::once_flag once[64];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[device & 63], [&] {
+    attr_err = cudaFuncSetAttribute(cfb::predict_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(device).smem_optin - 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(cfb::predict_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(device).smem_optin - 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const bool score4 = a.n_out == 1 && mode == CFB_PREDICT_SCORE && aligned;  // 4 rows per thread, 128-bit loads
+  const size_t units = score4 ? std::max<size_t>(1, rows / 4) : rows;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(score4 ? 4 : 2, ((size_t)dev_info(device).smem_optin - 1024) / std::max<size_t>(M->smem, 1)));
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)dev_info(device).sms * per_sm, (units + cfb::kPredictThreads - 1) / cfb::kPredictThreads));
+  if (score4) cfb::predict_score_kernel<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
+  else cfb::predict_argmax_kernel<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+// per host thread: a stream, a pinned tile and its device twin for cfb_predict_host
+struct PredictScratch {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  char *h = nullptr, *d = nullptr;
+  size_t bytes = 0;
+  ~PredictScratch() {
+    if (device < 0 || device_count_quiet() == 0) return;
+    cudaSetDevice(device);
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+thread_local PredictScratch t_predict;
+
+}  // namespace
+
+extern "C" int cfb_model_create(int device, const cfb_linear_model *M, cfb_model **out_model) {
+  if (!out_model) return fail(CFB_ERR_INVALID, "out is NULL");
+  *out_model = nullptr;
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  if (M->n_num < 0 || M->n_num > CFB_MAX_NUM || M->n_cat < 0 || M->n_cat > CFB_MAX_CAT)
+    return fail(CFB_ERR_INVALID, "model: n_num / n_cat out of range");
+  if (M->n_out < 1 || M->n_out > cfb::kPredictMaxOut) return fail(CFB_ERR_INVALID, "model: n_out must be in [1, %d]", cfb::kPredictMaxOut);
+  if (!M->bias || (M->n_num && !M->w_num) || (M->n_cat && (!M->cat_offsets || !M->cat_keys || !M->w_cat)))
+    return fail(CFB_ERR_INVALID, "model: NULL array");
+  const int K = M->n_out, n = M->n_num, m = M->n_cat;
+  const long long total = m ? M->cat_offsets[m] : 0;
+  std::unique_ptr<cfb_model> h(new cfb_model);
+  h->device = device;
+  cfb::PredictArgs &a = h->args;
+  a.n = n;
+  a.m = m;
+  a.n_out = K;
+  a.total = (int)total;
+  std::vector<int> map;  // dense key -> position maps
+  for (int c = 0; c < m; c++) {
+    const long long b = M->cat_offsets[c], e = M->cat_offsets[c + 1];
+    if (e < b) return fail(CFB_ERR_INVALID, "model: cat_offsets must be non-decreasing");
+    a.col_off[c] = (int)b;
+    a.map_off[c] = (int)map.size();
+    a.map_lo[c] = 0;
+    a.map_len[c] = 0;
+    if (e == b) continue;
+    for (long long t = b + 1; t < e; t++)
+      if (M->cat_keys[t] <= M->cat_keys[t - 1]) return fail(CFB_ERR_INVALID, "model: keys of column %d are not ascending", c);
+    const long long len = (long long)M->cat_keys[e - 1] - M->cat_keys[b] + 1;
+    if (len > (1 << 20) || (long long)map.size() + len > (4 << 20))
+      return fail(CFB_ERR_DOMAIN, "model: the key range of column %d is too wide for the dense key map", c);
+    a.map_lo[c] = M->cat_keys[b];
+    a.map_len[c] = (int)len;
+    map.resize(map.size() + len, -1);
+    for (long long t = b; t < e; t++) map[a.map_off[c] + (M->cat_keys[t] - M->cat_keys[b])] = (int)t;
+  }
+  a.map_total = (int)map.size();
+  h->smem = cfb::predict_smem_bytes(n, K, (int)total, a.map_total);
+  if (h->smem > (size_t)dev_info(device).smem_optin - 1024)
+    return fail(CFB_ERR_DOMAIN, "model too large for the device path (%zu bytes of shared memory)", h->smem);
+  std::vector<double> model((size_t)K * (1 + n + total));
+  for (int k = 0; k < K; k++) model[k] = M->bias[k];
+  for (size_t i = 0; i < (size_t)K * n; i++) model[K + i] = M->w_num[i];
+  for (size_t i = 0; i < (size_t)K * total; i++) model[(size_t)K * (1 + n) + i] = M->w_cat[i];
+  CU(cudaSetDevice(device));
+  CU(cudaMalloc((void **)&h->d_model, model.size() * 8));
+  if (cudaMalloc((void **)&h->d_map, std::max<size_t>(1, map.size()) * 4) != cudaSuccess) {
+    cudaFree(h->d_model);
+    return fail(CFB_ERR_CUDA, "cudaMalloc of the key map failed");
+  }
+  cudaError_t e = cudaMemcpy(h->d_model, model.data(), model.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !map.empty()) e = cudaMemcpy(h->d_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(h->d_model);
+    cudaFree(h->d_map);
+    return fail(CFB_ERR_CUDA, "model upload: %s", cudaGetErrorString(e));
+  }
+  a.d_model = h->d_model;
+  a.d_map = h->d_map;
+  *out_model = h.release();
+  return CFB_OK;
+}
+
+extern "C" void cfb_model_destroy(cfb_model *M) {
+  if (!M) return;
+  if (device_count_quiet() > 0) {
+    cudaSetDevice(M->device);
+    cudaFree(M->d_model);
+    cudaFree(M->d_map);
+  }
+  delete M;
+}
+
+extern "C" int cfb_predict_device(cfb_model *M, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
+                                  const int32_t *d_row_mask, size_t n_rows, int mode, void *d_out, void *stream) {
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  if (n_rows == 0) return CFB_OK;
+  if (!d_out || (M->args.n && !d_num_cols) || (M->args.m && !d_cat_cols)) return fail(CFB_ERR_INVALID, "NULL column array / output");
+  CU(cudaSetDevice(M->device));
+  return predict_launch(M, d_num_cols, d_cat_cols, d_row_mask, n_rows, mode, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int cfb_predict_host(cfb_model *M, const float *const *num_cols, const uint32_t *const *num_sel,
+                                const int32_t *const *cat_cols, const uint32_t *const *cat_sel, size_t count, int mode,
+                                void *out) {
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  if (count == 0) return CFB_OK;
+  const int n = M->args.n, m = M->args.m, device = M->device;
+  if (!out || (n && !num_cols) || (m && !cat_cols)) return fail(CFB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(device));
+  PredictScratch &sc = t_predict;
+  if (sc.device != device) {
+    if (sc.device >= 0) return fail(CFB_ERR_INVALID, "cfb_predict_host: a host thread stays on one device");
+    sc.device = device;
+    CU(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+  }
+  const size_t rows = (count + 3) & ~(size_t)3, need = (size_t)(n + m + 1) * rows * 4;
+  if (need > sc.bytes) {
+    CU(cudaStreamSynchronize(sc.stream));
+    if (sc.h) cudaFreeHost(sc.h);
+    if (sc.d) cudaFree(sc.d);
+    sc.h = sc.d = nullptr;
+    sc.bytes = std::max<size_t>(need, (size_t)1 << 20);
+    CU(cudaMallocHost((void **)&sc.h, sc.bytes));
+    CU(cudaMalloc((void **)&sc.d, sc.bytes));
+  }
+  const float *dn[CFB_MAX_NUM];
+  const int32_t *dc[CFB_MAX_CAT];
+  for (int k = 0; k < n; k++) {
+    gather((float *)(sc.h + (size_t)k * rows * 4), num_cols[k], num_sel ? num_sel[k] : nullptr, 0, count);
+    dn[k] = (const float *)(sc.d + (size_t)k * rows * 4);
+  }
+  for (int k = 0; k < m; k++) {
+    gather((int32_t *)(sc.h + (size_t)(n + k) * rows * 4), cat_cols[k], cat_sel ? cat_sel[k] : nullptr, 0, count);
+    dc[k] = (const int32_t *)(sc.d + (size_t)(n + k) * rows * 4);
+  }
+  _mm_sfence();  // the tile was filled with non-temporal stores
+  if (n + m) CU(cudaMemcpyAsync(sc.d, sc.h, (size_t)(n + m) * rows * 4, cudaMemcpyHostToDevice, sc.stream));
+  char *d_out = sc.d + (size_t)(n + m) * rows * 4, *h_out = sc.h + (size_t)(n + m) * rows * 4;
+  int rc = predict_launch(M, dn, dc, nullptr, count, mode, d_out, sc.stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_out, d_out, count * 4, cudaMemcpyDeviceToHost, sc.stream));
+  CU(cudaStreamSynchronize(sc.stream));
+  memcpy(out, h_out, count * 4);
+  return CFB_OK;
+}
 
 // ======================================================================== C ABI
 extern "C" {

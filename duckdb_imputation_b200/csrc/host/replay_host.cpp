@@ -246,6 +246,63 @@ duckdb::LogicalType RingType(bool nb) {
 }
 }  // namespace
 
+int replay_predict(const char *scalar, const float *params, size_t n_params, const int *flags, int n_flags, int n_num,
+                   int n_cat, const float *const *num, const int32_t *const *cat, const uint32_t *sel, size_t n_sel,
+                   size_t rows, void *out) {
+  using namespace duckdb;
+  try {
+    if (!scalar || !out || (!params && n_params)) throw InvalidInputException("bad arguments");
+    auto it = Catalog().scalars.find(scalar);
+    if (it == Catalog().scalars.end())
+      throw InvalidInputException(std::string("Catalog Error: scalar function ") + scalar + " does not exist");
+    ScalarFunction fun = it->second;
+    ClientContext context;
+    vector<unique_ptr<Expression>> args;
+    if (fun.bind) fun.bind(context, fun, args);
+    const idx_t out_w = fun.return_type.width();
+    // the literal arguments: a constant FLOAT[] and constant BOOLEANs, as the planner hands them over
+    Vector plist(LogicalType::LIST(LogicalType::FLOAT), 1);
+    ListVector::Reserve(plist, n_params);
+    ListVector::SetListSize(plist, n_params);
+    if (n_params) memcpy(FlatVector::GetData<float>(ListVector::GetEntry(plist)), params, n_params * sizeof(float));
+    ListVector::GetData(plist)[0] = {0, n_params};
+    plist.SetVectorType(VectorType::CONSTANT_VECTOR);
+    std::vector<Vector> lits;
+    for (int i = 0; i < n_flags; i++) {
+      lits.emplace_back(LogicalType::BOOLEAN, 1);
+      FlatVector::GetData<uint8_t>(lits.back())[0] = flags[i] ? 1 : 0;
+      lits.back().SetVectorType(VectorType::CONSTANT_VECTOR);
+    }
+    std::vector<sel_t> rel(STANDARD_VECTOR_SIZE);
+    size_t s_pos = 0, written = 0;
+    for (size_t lo = 0; lo < rows; lo += STANDARD_VECTOR_SIZE) {
+      const size_t hi = std::min(rows, lo + STANDARD_VECTOR_SIZE);
+      idx_t count = hi - lo;
+      if (sel) {
+        count = 0;
+        while (s_pos < n_sel && sel[s_pos] < hi) rel[count++] = (sel_t)(sel[s_pos++] - lo);
+        if (!count) continue;
+      }
+      DataChunk cols;
+      FillChunk(cols, n_num, n_cat, num, cat, lo, sel ? rel.data() : nullptr, count);
+      DataChunk chunk;
+      chunk.data.push_back(plist);
+      for (auto &l : lits) chunk.data.push_back(l);
+      for (auto &v : cols.data) chunk.data.push_back(v);
+      chunk.SetCardinality(count);
+      ExpressionState state;
+      Vector result(fun.return_type, count);
+      fun.function(chunk, state, result);
+      memcpy((char *)out + written * out_w, FlatVector::GetData(result), count * out_w);
+      written += count;
+    }
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out) {
   using namespace duckdb;
   try {

@@ -42,6 +42,12 @@ int replay_scalar(const char *scalar, int n_num, int n_cat, const float *const *
  * a join over aggregate results): json_args[k] is a JSON array with one STRUCT per row, in the rendering
  * of json_out (field names are ignored; nb != 0: the four-field Naive-Bayes ring).  e.g. multiply_triple. */
 int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out);
+/* Run  SELECT <scalar>(params::FLOAT[], flag..., num..., cat...) FROM t [WHERE row in sel]  -- the predict functions
+ * (linreg_predict: flags = noise, normalize; lda_predict: flags = normalize).  `out` receives one 4-byte value per
+ * (selected) row: float or int32, the function's return type.                                            */
+int replay_predict(const char *scalar, const float *params, size_t n_params, const int *flags, int n_flags, int n_num,
+                   int n_cat, const float *const *num, const int32_t *const *cat, const uint32_t *sel, size_t n_sel,
+                   size_t rows, void *out);
 void replay_free(char *p);
 const char *replay_last_error(void);
 /* Names of all registered aggregate functions, '\n'-separated (malloc'd). */

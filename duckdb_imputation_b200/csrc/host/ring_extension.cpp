@@ -52,6 +52,18 @@ void Load(duckdb::DatabaseInstance &instance) {
   mul_nb.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
   ExtensionUtil::RegisterFunction(instance, mul_nb);
 
+  // linreg_predict / lda_predict (ext.cpp:193-199, :211-217): model scores of rows on the GPU.  In the
+  // reference LDA_impute lives in the global namespace; here both sit in ML.
+  ScalarFunction linreg_predict("linreg_predict", {LogicalType::ANY}, LogicalTypeId::FLOAT, ML::linreg_impute, ML::linreg_impute_bind, nullptr,
+                                nullptr);
+  linreg_predict.varargs = LogicalType::ANY;
+  linreg_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, linreg_predict);
+  ScalarFunction lda_predict("lda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::LDA_impute, ML::LDA_impute_bind, nullptr);
+  lda_predict.varargs = LogicalType::ANY;
+  lda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, lda_predict);
+
   constexpr int kMaxCols = 20;
   for (int i = 0; i <= kMaxCols; i++)
     for (int j = 0; j <= kMaxCols; j++) {

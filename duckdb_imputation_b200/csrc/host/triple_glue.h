@@ -94,3 +94,13 @@ void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &
 void WriteResults(const std::vector<cfb_result> &res, duckdb::Vector &result, bool nb, int n_num, int n_cat);
 
 }  // namespace Triple
+
+// linreg_predict / lda_predict: the write-back step of MICE (ML/regression.h, ML/lda.h)
+namespace ML {
+void linreg_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> linreg_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                            duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void LDA_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> LDA_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+}  // namespace ML

@@ -1,0 +1,154 @@
+// predict_kernel.cuh -- model scores of rows: the write-back step of a MICE iteration.
+//
+// Replaces the per-row loops of ML::linreg_impute (ML/regression.cpp:436-506) and LDA_impute
+// (ML/lda.cpp:506-577): score_o = bias_o + SUM_i w_num[o][i] x_i + SUM_c w_cat[o][pos_c(key_c)],
+// written as the score itself (regression) or the index of the largest score (LDA).
+//
+// HBM-bound by construction: every input value is read once (4(n+m) bytes per row, coalesced:
+// consecutive threads take consecutive rows of the SoA columns) and 4 bytes are written.  The
+// model lives in shared memory: bias and weights in fp64 (the reference accumulates in double),
+// and per categorical column a dense key -> position map (int32, -1 = unknown key), so a key
+// lookup is one LDS instead of the reference's linear search (regression.cpp:471-476).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "state_layout.h"
+
+namespace cfb {
+
+constexpr int kPredictThreads = 256;
+constexpr int kPredictMaxOut = 32;
+
+struct PredictArgs {
+  ScanCols cols;            // group = row mask (nullable)
+  unsigned long long n_rows;
+  int n, m, n_out, mode;
+  int total;                // model keys over all columns
+  int map_lo[kMaxCat], map_off[kMaxCat], map_len[kMaxCat];  // dense map of column c: [map_off, map_off + map_len) covers keys [map_lo, ..)
+  int map_total;
+  int col_off[kMaxCat];     // first position of column c in w_cat
+  const double *d_model;    // [n_out] bias | [n_out][n] w_num | [n_out][total] w_cat
+  const int *d_map;         // [map_total] position within w_cat rows, or -1
+  void *out;
+};
+
+__host__ __device__ inline size_t predict_smem_bytes(int n, int n_out, int total, int map_total) {
+  return (size_t)(n_out * (1 + n + total)) * 8 + (size_t)map_total * 4;
+}
+
+// model -> shared memory (every CTA; persistent grid, so once per CTA)
+__device__ __forceinline__ void predict_load_model(const PredictArgs &a, double *smem) {
+  const int words = a.n_out * (1 + a.n + a.total);
+  for (int i = threadIdx.x; i < words; i += kPredictThreads) smem[i] = a.d_model[i];
+  int *map = reinterpret_cast<int *>(smem + words);
+  for (int i = threadIdx.x; i < a.map_total; i += kPredictThreads) map[i] = a.d_map[i];
+  __syncthreads();
+}
+
+// One output (regression): 4 consecutive rows per thread, every column one 128-bit load (columns are
+// 16-byte aligned), four independent fp64 accumulators -- the loads of a row step are independent of
+// the accumulation, which is what keeps enough bytes in flight to stream from HBM.
+__global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const __grid_constant__ PredictArgs a) {
+  extern __shared__ double predict_smem[];
+  predict_load_model(a, predict_smem);
+  const int n = a.n, m = a.m;
+  const double *w_num = predict_smem + 1, *w_cat = w_num + n;
+  const int *map = reinterpret_cast<const int *>(w_cat + a.total);
+  const double bias = predict_smem[0];
+  const unsigned long long n4 = a.n_rows / 4;
+  float *out = static_cast<float *>(a.out);
+  for (unsigned long long q = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; q < n4;
+       q += (unsigned long long)gridDim.x * kPredictThreads) {
+    int4 mk = make_int4(1, 1, 1, 1);
+    if (a.cols.group) {
+      mk = reinterpret_cast<const int4 *>(a.cols.group)[q];
+      if (!(mk.x | mk.y | mk.z | mk.w)) continue;  // no cell to fill among these rows
+    }
+    double acc0 = bias, acc1 = bias, acc2 = bias, acc3 = bias;
+#pragma unroll 4
+    for (int i = 0; i < n; i++) {
+      const float4 x = reinterpret_cast<const float4 *>(a.cols.num[i])[q];
+      const double w = w_num[i];
+      acc0 += w * (double)x.x, acc1 += w * (double)x.y, acc2 += w * (double)x.z, acc3 += w * (double)x.w;
+    }
+#pragma unroll 2
+    for (int c = 0; c < m; c++) {
+      const int4 k = reinterpret_cast<const int4 *>(a.cols.cat[c])[q];
+      const int lo = a.map_lo[c], off = a.map_off[c];
+      const unsigned len = (unsigned)a.map_len[c];
+      const unsigned d0 = (unsigned)(k.x - lo), d1 = (unsigned)(k.y - lo), d2 = (unsigned)(k.z - lo), d3 = (unsigned)(k.w - lo);
+      const int p0 = d0 < len ? map[off + d0] : -1, p1 = d1 < len ? map[off + d1] : -1;
+      const int p2 = d2 < len ? map[off + d2] : -1, p3 = d3 < len ? map[off + d3] : -1;
+      if (p0 >= 0) acc0 += w_cat[p0];
+      if (p1 >= 0) acc1 += w_cat[p1];
+      if (p2 >= 0) acc2 += w_cat[p2];
+      if (p3 >= 0) acc3 += w_cat[p3];
+    }
+    if (!a.cols.group) {
+      reinterpret_cast<float4 *>(out)[q] = make_float4((float)acc0, (float)acc1, (float)acc2, (float)acc3);
+    } else {
+      if (mk.x) out[4 * q] = (float)acc0;
+      if (mk.y) out[4 * q + 1] = (float)acc1;
+      if (mk.z) out[4 * q + 2] = (float)acc2;
+      if (mk.w) out[4 * q + 3] = (float)acc3;
+    }
+  }
+  // the last n_rows % 4 rows
+  const unsigned long long r = 4 * n4 + (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x;
+  if (r < a.n_rows && !(a.cols.group && a.cols.group[r] == 0)) {
+    double acc = bias;
+    for (int i = 0; i < n; i++) acc += w_num[i] * (double)a.cols.num[i][r];
+    for (int c = 0; c < m; c++) {
+      const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
+      const int pos = d < (unsigned)a.map_len[c] ? map[a.map_off[c] + d] : -1;
+      if (pos >= 0) acc += w_cat[pos];
+    }
+    out[r] = (float)acc;
+  }
+}
+
+// Several outputs (LDA): one row per thread, all its values loaded up front (independent loads), then the
+// scores class by class from registers; result = first index of the largest score (lda.cpp:566-573).
+__global__ void __launch_bounds__(kPredictThreads) predict_argmax_kernel(const __grid_constant__ PredictArgs a) {
+  extern __shared__ double predict_smem[];
+  predict_load_model(a, predict_smem);
+  const int K = a.n_out, n = a.n, m = a.m;
+  const double *bias = predict_smem, *w_num = bias + K, *w_cat = w_num + (size_t)K * n;
+  const int *map = reinterpret_cast<const int *>(w_cat + (size_t)K * a.total);
+  for (unsigned long long r = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
+       r += (unsigned long long)gridDim.x * kPredictThreads) {
+    if (a.cols.group && a.cols.group[r] == 0) continue;  // not a cell to fill
+    float x[32];
+    int pos[kMaxCat];
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = i < n ? a.cols.num[i][r] : 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxCat; c++) {
+      pos[c] = -1;
+      if (c < m) {
+        const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
+        if (d < (unsigned)a.map_len[c]) pos[c] = map[a.map_off[c] + d];
+      }
+    }
+    double best = 0.0;
+    int best_k = 0;
+    for (int k = 0; k < K; k++) {
+      double acc = bias[k];
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        if (i < n) acc += w_num[k * n + i] * (double)x[i];
+#pragma unroll
+      for (int c = 0; c < kMaxCat; c++)
+        if (c < m && pos[c] >= 0) acc += w_cat[(size_t)k * a.total + pos[c]];
+      if (k == 0 || acc > best) {
+        best = acc;
+        best_k = k;
+      }
+    }
+    if (a.mode == 0) static_cast<float *>(a.out)[r] = (float)best;
+    else static_cast<int *>(a.out)[r] = best_k;
+  }
+}
+
+}  // namespace cfb

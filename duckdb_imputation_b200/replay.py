@@ -41,6 +41,9 @@ class Replay:
                                     C.POINTER(P)]
         l.replay_scalar_structs.restype = C.c_int
         l.replay_scalar_structs.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(P)]
+        l.replay_predict.restype = C.c_int
+        l.replay_predict.argtypes = [C.c_char_p, P, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(P),
+                                     C.POINTER(P), P, C.c_size_t, C.c_size_t, P]
         l.replay_free.argtypes = [P]
         l.replay_last_error.restype = C.c_char_p
         l.replay_list_functions.restype = P
@@ -97,6 +100,23 @@ class Replay:
             return json.loads(C.string_at(out).decode())
         finally:
             self.lib.replay_free(out)
+
+    def predict(self, function: str, params, flags, num_cols, cat_cols, where=None):
+        """SELECT function(params::FLOAT[], flags..., cols...) FROM t [WHERE ..] -> numpy array (float32 for
+        linreg_predict, int32 for lda_predict), one value per (selected) row."""
+        kn = [np.ascontiguousarray(c, np.float32) for c in num_cols]
+        kc = [np.ascontiguousarray(c, np.int32) for c in cat_cols]
+        rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
+        s = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
+        p = np.ascontiguousarray(params, np.float32)
+        out = np.zeros(rows if s is None else len(s), np.int32 if function.startswith("lda") else np.float32)
+        fl = (C.c_int * max(1, len(flags)))(*[int(bool(f)) for f in flags])
+        rc = self.lib.replay_predict(function.encode(), p.ctypes.data, len(p), fl, len(flags), len(kn), len(kc),
+                                     ptr_array([k.ctypes.data for k in kn]), ptr_array([k.ctypes.data for k in kc]),
+                                     None if s is None else s.ctypes.data, 0 if s is None else len(s), rows, out.ctypes.data)
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        return out
 
     def scalar_structs(self, function: str, *columns):
         """SELECT function(A, B, ..) FROM j, every argument a column (list) of ring STRUCT dicts, e.g.

@@ -220,6 +220,42 @@ int cfb_ctx_import_partial(cfb_ctx *ctx, const void *d_f64, const void *d_u64, v
 int cfb_cat_minmax_device(int device, const int32_t *const *d_cat_cols, int n_cat, size_t n_rows,
                           int32_t *lo_out, int32_t *hi_out, void *stream);
 
+/* ---------------------------------------------- MICE write-back: model scores of rows */
+
+/* A linear model over n_num FLOAT and n_cat INTEGER (one-hot) columns with n_out outputs:
+ *     score_o(row) = bias[o] + SUM_i w_num[o][i] * x_i + SUM_c w_cat[o][ position of key_c in column c ]
+ * This is the arithmetic of ML::linreg_impute (ML/regression.cpp:397-509, n_out = 1) and of
+ * LDA_impute (ML/lda.cpp:421-590, n_out = #classes, result = index of the largest score); the
+ * glue (host/predict_glue.cpp) parses the reference's parameter lists into this form and folds
+ * the `normalize` centering into bias.  A key that the model does not know contributes 0.      */
+typedef struct cfb_linear_model {
+  int32_t n_num, n_cat, n_out;
+  const double *bias;         /* [n_out]                                              */
+  const double *w_num;        /* [n_out][n_num]                                       */
+  const int64_t *cat_offsets; /* [n_cat + 1] into cat_keys / the columns of w_cat     */
+  const int32_t *cat_keys;    /* [cat_offsets[n_cat]], ascending within a column      */
+  const double *w_cat;        /* [n_out][cat_offsets[n_cat]]                          */
+} cfb_linear_model;
+
+/* The model on a device (weights and dense key maps uploaded once; a MICE step scores many chunks with it). */
+typedef struct cfb_model cfb_model;
+int cfb_model_create(int device, const cfb_linear_model *model, cfb_model **out);
+void cfb_model_destroy(cfb_model *model);
+
+#define CFB_PREDICT_SCORE 0  /* out: float  [rows], score_0                              */
+#define CFB_PREDICT_ARGMAX 1 /* out: int32  [rows], first index of the largest score     */
+
+/* Device-resident columns -> d_out (device).  d_row_mask (nullable, int32 per row): only rows with a
+ * non-zero mask are written, the others keep their value -- with d_out aliasing the imputed column
+ * this is the in-place overwrite of its NULL cells (imputation_base.cpp:75-83, :133-139).
+ * Asynchronous on `stream` (cudaStream_t, NULL = the legacy default stream).                        */
+int cfb_predict_device(cfb_model *model, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
+                       const int32_t *d_row_mask, size_t n_rows, int mode, void *d_out, void *stream);
+/* Host columns (optional per-column selection vectors as in cfb_ctx_append) -> out (host); synchronous.
+ * What the DuckDB scalar functions linreg_predict / lda_predict call per chunk.                       */
+int cfb_predict_host(cfb_model *model, const float *const *num_cols, const uint32_t *const *num_sel,
+                     const int32_t *const *cat_cols, const uint32_t *const *cat_sel, size_t count, int mode, void *out);
+
 /* ------------------------------------------------------ synthetic inputs (tests, bench) */
 
 /* Counter-based generators for device-resident synthetic columns: element i of the

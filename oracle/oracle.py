@@ -156,3 +156,107 @@ def multiply(a: dict, b: dict) -> dict:
     cc += [scale(l, Na) for l in ccb]                                              # :583-597
     out["quad_cat"] = cc
     return out
+
+
+# ------------------------------------------------------------------ predict (MICE write-back step)
+def linreg_params(intercept, w_num, cat_keys, w_cat, means_num=None, means_cat=None, sigma=0.0):
+    """The FLOAT[] that linreg_train emits, in the layout linreg_impute reads (ML/regression.cpp:424-435):
+    [n_cat | idx_0..idx_{n_cat} | unique keys | intercept | w_num | w_cat | (means_num | means_cat) | sigma].
+    cat_keys / w_cat / means_cat: one list per categorical column."""
+    p = [float(len(cat_keys))]
+    if cat_keys:
+        idx = np.concatenate([[0], np.cumsum([len(k) for k in cat_keys])])
+        p += [float(i) for i in idx] + [float(k) for col in cat_keys for k in col]
+    p += [float(intercept)] + [float(w) for w in w_num] + [float(w) for col in w_cat for w in col]
+    if means_num is not None:
+        p += [float(v) for v in means_num] + [float(v) for col in (means_cat or []) for v in col]
+    p.append(float(sigma))
+    return np.asarray(p, np.float32)
+
+
+def linreg_predict(params, normalize, num_cols, cat_cols):
+    """Restatement of ML::linreg_impute (ML/regression.cpp:397-509), noise = false, row by row in fp64 like
+    the reference.  A key the parameter list does not hold raises (the reference reads past the weights)."""
+    p = np.asarray(params, np.float32)
+    n, m = len(num_cols), len(cat_cols)
+    rows = len(num_cols[0]) if n else len(cat_cols[0])
+    n_cat = int(p[0])
+    start, max_idx = 1 + n_cat, 0                                             # :428-435
+    if n_cat > 0:
+        max_idx = int(p[start])
+        start += max_idx + 1
+    out = np.full(rows, float(p[start]), np.float64)                           # :439 intercept
+    for i in range(n):                                                        # :442-453
+        x = np.asarray(num_cols[i], np.float32).astype(np.float64)
+        if normalize:
+            x = x - float(p[1 + n + max_idx + start + i])
+        out += float(p[i + start + 1]) * x
+    for i in range(m):                                                        # :455-493
+        b, e = int(p[1 + i]), int(p[2 + i])
+        keys = p[b + 2 + n_cat:e + 2 + n_cat].astype(np.int64)
+        col = np.asarray(cat_cols[i], np.int64)
+        pos = np.full(rows, -1, np.int64)
+        for j, k in enumerate(keys):
+            pos[(col == k) & (pos < 0)] = b + j
+        if (pos < 0).any():
+            raise ValueError("key not in the parameter list")
+        w = p[start + n + 1:].astype(np.float64)
+        if normalize:
+            mean = p[1 + 2 * n + max_idx + start:].astype(np.float64)
+            for j in range(b, e):
+                out += w[j] * ((pos == j).astype(np.float64) - mean[j])
+        else:
+            out += w[pos]
+    return out.astype(np.float32)                                             # FLOAT result (:366-375)
+
+
+def lda_params(labels, coef, intercept, cat_keys, means=None):
+    """The FLOAT[] that lda_train emits, in the layout LDA_impute reads (ML/lda.cpp:450-500):
+    [K | S | idx_0..idx_{S-1} | unique keys | labels | coef[K][n + total] | intercept[K] | (means[n + total])]."""
+    K = len(labels)
+    p = [float(K)]
+    if cat_keys:
+        idx = np.concatenate([[0], np.cumsum([len(k) for k in cat_keys])])
+        p += [float(len(idx))] + [float(i) for i in idx] + [float(k) for col in cat_keys for k in col]
+    else:
+        p += [0.0]
+    p += [float(l) for l in labels] + [float(v) for v in np.asarray(coef, np.float64).reshape(-1)] + [float(v) for v in intercept]
+    if means is not None:
+        p += [float(v) for v in means]
+    return np.asarray(p, np.float32)
+
+
+def lda_predict(params, normalize, num_cols, cat_cols):
+    """Restatement of LDA_impute (ML/lda.cpp:421-590): returns the INDEX of the class with the largest score
+    (:566-575), first index on ties; also returns the scores (for tie-aware comparisons)."""
+    p = np.asarray(params, np.float32)
+    n, m = len(num_cols), len(cat_cols)
+    rows = len(num_cols[0]) if n else len(cat_cols[0])
+    K, S = int(p[0]), int(p[1])
+    off = 2
+    idx = [int(v) for v in p[off:off + S]]
+    off += S
+    total = idx[-1] if S else 0
+    keys = p[off:off + total].astype(np.int64)
+    off += total + K                                                           # labels are not used (:475-480)
+    num_params = n + total
+    coef = p[off:off + K * num_params].astype(np.float64).reshape(K, num_params)  # :487-491
+    off += K * num_params
+    intercept = p[off:off + K].astype(np.float64)                              # float intercepts (:495-500)
+    off += K
+    feats = np.zeros((rows, num_params), np.float64)                           # :506-531
+    for j in range(n):
+        feats[:, j] = np.asarray(num_cols[j], np.float32).astype(np.float64)
+    for j in range(m):
+        col = np.asarray(cat_cols[j], np.int64)
+        hit = np.zeros(rows, bool)
+        for t in range(idx[j], idx[j + 1]):
+            sel = (col == keys[t]) & ~hit
+            feats[sel, n + t] = 1.0
+            hit |= sel
+        if not hit.all():
+            raise ValueError("key not in the parameter list")
+    if normalize:                                                             # :533-549
+        feats -= p[off:off + num_params].astype(np.float64)[None, :]
+    scores = feats @ coef.T + intercept[None, :]                               # dgemv (:560-562) + intercept
+    return np.argmax(scores, axis=1).astype(np.int32), scores
