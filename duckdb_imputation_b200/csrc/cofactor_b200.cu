@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -1160,20 +1161,37 @@ int predict_launch(cfb_model *M, const float *const *num, const int32_t *const *
   a.mode = mode;
   a.out = d_out;
   const int device = M->device;
-  static std::once_flag once[64];
-  cudaError_t attr_err = cudaSuccess;
-  std::call_once(once[device & 63], [&] {
-    attr_err = cudaFuncSetAttribute(cfb::predict_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(device).smem_optin - 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(cfb::predict_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(device).smem_optin - 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const bool score4 = a.n_out == 1 && mode == CFB_PREDICT_SCORE && aligned;  // 4 rows per thread, 128-bit loads
-  const size_t units = score4 ? std::max<size_t>(1, rows / 4) : rows;
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(score4 ? 4 : 2, ((size_t)dev_info(device).smem_optin - 1024) / std::max<size_t>(M->smem, 1)));
+  const int smem_max = dev_info(device).smem_optin - 1024;
+  const bool single = a.n_out == 1;
+  if (single && mode == CFB_PREDICT_ARGMAX) {  // one output: the index of the largest score is 0
+    if (mask) return fail(CFB_ERR_INVALID, "argmax of a single-output model with a row mask is not supported");
+    CU(cudaMemsetAsync(d_out, 0, rows * 4, s));
+    return CFB_OK;
+  }
+  a.vec4 = single && aligned;
+  const size_t units = a.vec4 ? std::max<size_t>(1, rows / 4) : rows;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(single ? 4 : 2, (size_t)smem_max / std::max<size_t>(M->smem, 1)));
   const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)dev_info(device).sms * per_sm, (units + cfb::kPredictThreads - 1) / cfb::kPredictThreads));
-  if (score4) cfb::predict_score_kernel<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
-  else cfb::predict_argmax_kernel<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
+  auto run = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
+    return cudaGetLastError();
+  };
+  cudaError_t e;
+  switch (a.kb) {
+    case 1: e = run(cfb::predict_score_kernel); break;
+    case 2: e = run(cfb::predict_multi_kernel<2>); break;
+    case 4: e = run(cfb::predict_multi_kernel<4>); break;
+    case 6: e = run(cfb::predict_multi_kernel<6>); break;
+    case 8: e = run(cfb::predict_multi_kernel<8>); break;
+    case 10: e = run(cfb::predict_multi_kernel<10>); break;
+    case 12: e = run(cfb::predict_multi_kernel<12>); break;
+    case 16: e = run(cfb::predict_multi_kernel<16>); break;
+    case 24: e = run(cfb::predict_multi_kernel<24>); break;
+    default: e = run(cfb::predict_multi_kernel<32>); break;
+  }
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "predict kernel launch: %s", cudaGetErrorString(e));
   g_launches++;
   CU(cudaGetLastError());
   return CFB_OK;
@@ -1236,13 +1254,24 @@ extern "C" int cfb_model_create(int device, const cfb_linear_model *M, cfb_model
     for (long long t = b; t < e; t++) map[a.map_off[c] + (M->cat_keys[t] - M->cat_keys[b])] = (int)t;
   }
   a.map_total = (int)map.size();
-  h->smem = cfb::predict_smem_bytes(n, K, (int)total, a.map_total);
+  // outputs padded to a kernel bucket; weights class-minor: [kb] bias | [n][kb] | [total][kb]
+  int KB = 1;
+  if (K > 1)
+    for (int b : {2, 4, 6, 8, 10, 12, 16, 24, 32})
+      if (b >= K) {
+        KB = b;
+        break;
+      }
+  a.kb = KB;
+  h->smem = cfb::predict_smem_bytes(n, KB, (int)total, a.map_total);
   if (h->smem > (size_t)dev_info(device).smem_optin - 1024)
     return fail(CFB_ERR_DOMAIN, "model too large for the device path (%zu bytes of shared memory)", h->smem);
-  std::vector<double> model((size_t)K * (1 + n + total));
-  for (int k = 0; k < K; k++) model[k] = M->bias[k];
-  for (size_t i = 0; i < (size_t)K * n; i++) model[K + i] = M->w_num[i];
-  for (size_t i = 0; i < (size_t)K * total; i++) model[(size_t)K * (1 + n) + i] = M->w_cat[i];
+  std::vector<double> model((size_t)KB * (1 + n + total), 0.0);
+  for (int k = 0; k < KB; k++) model[k] = k < K ? M->bias[k] : -std::numeric_limits<double>::infinity();
+  for (int k = 0; k < K; k++) {
+    for (int i = 0; i < n; i++) model[(size_t)KB * (1 + i) + k] = M->w_num[(size_t)k * n + i];
+    for (long long t = 0; t < total; t++) model[(size_t)KB * (1 + n + t) + k] = M->w_cat[(size_t)k * total + t];
+  }
   CU(cudaSetDevice(device));
   CU(cudaMalloc((void **)&h->d_model, model.size() * 8));
   if (cudaMalloc((void **)&h->d_map, std::max<size_t>(1, map.size()) * 4) != cudaSuccess) {

@@ -24,22 +24,24 @@ struct PredictArgs {
   ScanCols cols;            // group = row mask (nullable)
   unsigned long long n_rows;
   int n, m, n_out, mode;
+  int kb;                   // outputs padded to this many (class-minor weight rows of kb doubles); 1 for n_out = 1
+  int vec4;                 // score kernel: all pointers 16-byte aligned -> 4 rows per thread with 128-bit loads
   int total;                // model keys over all columns
   int map_lo[kMaxCat], map_off[kMaxCat], map_len[kMaxCat];  // dense map of column c: [map_off, map_off + map_len) covers keys [map_lo, ..)
   int map_total;
   int col_off[kMaxCat];     // first position of column c in w_cat
-  const double *d_model;    // [n_out] bias | [n_out][n] w_num | [n_out][total] w_cat
+  const double *d_model;    // [kb] bias | [n][kb] w_num | [total][kb] w_cat  (padding: weight 0, bias -inf)
   const int *d_map;         // [map_total] position within w_cat rows, or -1
   void *out;
 };
 
-__host__ __device__ inline size_t predict_smem_bytes(int n, int n_out, int total, int map_total) {
-  return (size_t)(n_out * (1 + n + total)) * 8 + (size_t)map_total * 4;
+__host__ __device__ inline size_t predict_smem_bytes(int n, int kb, int total, int map_total) {
+  return (size_t)kb * (1 + n + total) * 8 + (size_t)map_total * 4;
 }
 
 // model -> shared memory (every CTA; persistent grid, so once per CTA)
 __device__ __forceinline__ void predict_load_model(const PredictArgs &a, double *smem) {
-  const int words = a.n_out * (1 + a.n + a.total);
+  const int words = a.kb * (1 + a.n + a.total);
   for (int i = threadIdx.x; i < words; i += kPredictThreads) smem[i] = a.d_model[i];
   int *map = reinterpret_cast<int *>(smem + words);
   for (int i = threadIdx.x; i < a.map_total; i += kPredictThreads) map[i] = a.d_map[i];
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
   const double *w_num = predict_smem + 1, *w_cat = w_num + n;
   const int *map = reinterpret_cast<const int *>(w_cat + a.total);
   const double bias = predict_smem[0];
-  const unsigned long long n4 = a.n_rows / 4;
+  const unsigned long long n4 = a.vec4 ? a.n_rows / 4 : 0;  // unaligned input: every row takes the scalar path below
   float *out = static_cast<float *>(a.out);
   for (unsigned long long q = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; q < n4;
        q += (unsigned long long)gridDim.x * kPredictThreads) {
@@ -94,9 +96,10 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
       if (mk.w) out[4 * q + 3] = (float)acc3;
     }
   }
-  // the last n_rows % 4 rows
-  const unsigned long long r = 4 * n4 + (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x;
-  if (r < a.n_rows && !(a.cols.group && a.cols.group[r] == 0)) {
+  // the last n_rows % 4 rows (all rows when the input is not 16-byte aligned)
+  for (unsigned long long r = 4 * n4 + (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
+       r += (unsigned long long)gridDim.x * kPredictThreads) {
+    if (a.cols.group && a.cols.group[r] == 0) continue;
     double acc = bias;
     for (int i = 0; i < n; i++) acc += w_num[i] * (double)a.cols.num[i][r];
     for (int c = 0; c < m; c++) {
@@ -108,45 +111,56 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
   }
 }
 
-// Several outputs (LDA): one row per thread, all its values loaded up front (independent loads), then the
-// scores class by class from registers; result = first index of the largest score (lda.cpp:566-573).
-__global__ void __launch_bounds__(kPredictThreads) predict_argmax_kernel(const __grid_constant__ PredictArgs a) {
+// Several outputs (LDA): one row per thread, KB >= n_out accumulators in registers.  The weights are stored
+// class-minor ([feature][KB], padded with zeros), so the KB weights of a feature are consecutive: a uniform
+// LDS.128 per two classes for a numeric feature, and one contiguous run per thread for a (column, key).
+// Result = first index of the largest score (lda.cpp:566-573), or score_0 when mode = SCORE.
+template <int KB>
+__global__ void __launch_bounds__(kPredictThreads) predict_multi_kernel(const __grid_constant__ PredictArgs a) {
   extern __shared__ double predict_smem[];
   predict_load_model(a, predict_smem);
-  const int K = a.n_out, n = a.n, m = a.m;
-  const double *bias = predict_smem, *w_num = bias + K, *w_cat = w_num + (size_t)K * n;
-  const int *map = reinterpret_cast<const int *>(w_cat + (size_t)K * a.total);
+  const int n = a.n, m = a.m;
+  const double *bias = predict_smem, *w_num = bias + KB, *w_cat = w_num + (size_t)n * KB;
+  const int *map = reinterpret_cast<const int *>(w_cat + (size_t)a.total * KB);
   for (unsigned long long r = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
        r += (unsigned long long)gridDim.x * kPredictThreads) {
     if (a.cols.group && a.cols.group[r] == 0) continue;  // not a cell to fill
-    float x[32];
-    int pos[kMaxCat];
+    double acc[KB];
 #pragma unroll
-    for (int i = 0; i < 32; i++) x[i] = i < n ? a.cols.num[i][r] : 0.f;
+    for (int k = 0; k < KB; k++) acc[k] = bias[k];
+#pragma unroll 4
+    for (int i = 0; i < n; i++) {
+      const double x = (double)a.cols.num[i][r];
+      const double2 *w = reinterpret_cast<const double2 *>(w_num + (size_t)i * KB);
 #pragma unroll
-    for (int c = 0; c < kMaxCat; c++) {
-      pos[c] = -1;
-      if (c < m) {
-        const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
-        if (d < (unsigned)a.map_len[c]) pos[c] = map[a.map_off[c] + d];
+      for (int k = 0; k < KB / 2; k++) {
+        const double2 v = w[k];
+        acc[2 * k] += v.x * x;
+        acc[2 * k + 1] += v.y * x;
       }
     }
-    double best = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < m; c++) {
+      const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
+      const int pos = d < (unsigned)a.map_len[c] ? map[a.map_off[c] + d] : -1;
+      if (pos < 0) continue;
+      const double2 *w = reinterpret_cast<const double2 *>(w_cat + (size_t)pos * KB);
+#pragma unroll
+      for (int k = 0; k < KB / 2; k++) {
+        const double2 v = w[k];
+        acc[2 * k] += v.x;
+        acc[2 * k + 1] += v.y;
+      }
+    }
+    double best = acc[0];
     int best_k = 0;
-    for (int k = 0; k < K; k++) {
-      double acc = bias[k];
 #pragma unroll
-      for (int i = 0; i < 32; i++)
-        if (i < n) acc += w_num[k * n + i] * (double)x[i];
-#pragma unroll
-      for (int c = 0; c < kMaxCat; c++)
-        if (c < m && pos[c] >= 0) acc += w_cat[(size_t)k * a.total + pos[c]];
-      if (k == 0 || acc > best) {
-        best = acc;
+    for (int k = 1; k < KB; k++)
+      if (acc[k] > best) {  // padded classes carry bias = -inf and never win
+        best = acc[k];
         best_k = k;
       }
-    }
-    if (a.mode == 0) static_cast<float *>(a.out)[r] = (float)best;
+    if (a.mode == 0) static_cast<float *>(a.out)[r] = (float)acc[0];
     else static_cast<int *>(a.out)[r] = best_k;
   }
 }
