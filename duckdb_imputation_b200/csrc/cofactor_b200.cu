@@ -32,6 +32,7 @@
 #include "pair_hash.cuh"
 #include "predict_kernel.cuh"
 #include "slab_kernels.cuh"
+#include "slot_gram_kernel.cuh"
 #include "bucket_kernels.cuh"
 #include "bucket_launch.h"
 #include "role_kernels.cuh"
@@ -903,7 +904,79 @@ int launch_group_e(cfb_ctx *c, const cfb::GroupArgs &a, size_t smem, int grid, c
   return CFB_OK;
 }
 
+// GROUP BY / filtered numeric part with the rows bucketed by slot and the accumulators in registers
+// (slot_gram_kernel.cuh).  Returns 1 if the shape does not qualify (caller uses group_scan_kernel).
+template <int E, int TPW>
+int launch_slot_gram_e(cfb_ctx *c, const cfb::SlotGramArgs &a, size_t smem, int grid, cudaStream_t s) {
+  auto kern = cfb::slot_gram_kernel<E, TPW>;
+  static std::once_flag once[64];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[c->device & 63], [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(c->device).smem_optin - 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  kern<<<grid, cfb::kSlotThreads, smem, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (getenv("CFB_NO_SLOT_GRAM") || c->n < 1 || c->G > cfb::kSlotMaxGroups) return 1;
+  if (rows < (unsigned long long)std::max(1, env_int("CFB_SLOT_MIN_ROWS", 8192))) return 1;
+  // output entries of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows
+  const int V = cfb::slot_entries(c->n, c->kind), parts_max = cfb::kSlotWarps / c->G;
+  int parts = 1;
+  while (parts < parts_max && (V + 32 * parts - 1) / (32 * parts) > 4) parts++;
+  int E = (V + 32 * parts - 1) / (32 * parts);
+  if (E > 8) return 1;
+  E = E == 5 ? 6 : (E == 7 ? 8 : E);
+  const int smem_max = dev_info(c->device).smem_optin - 1024;
+  // two CTAs per SM when a tile of >= 2 rows per thread still fits twice, else one
+  const size_t half = (size_t)smem_max / 2 - 1024;
+  int steps = cfb::kSlotMaxSteps, per_sm = 2;
+  while (steps >= 2 && cfb::slot_smem_bytes(c->n, c->G, steps) > half) steps--;
+  if (cfb::slot_smem_bytes(c->n, c->G, steps) > half) {
+    per_sm = 1;
+    steps = cfb::kSlotMaxSteps;
+    while (steps >= 1 && cfb::slot_smem_bytes(c->n, c->G, steps) > (size_t)smem_max) steps--;
+    if (steps < 1) return 1;
+  }
+  cfb::SlotGramArgs a{};
+  a.cols = sc;
+  a.n_rows = rows;
+  a.n = c->n;
+  a.kind = c->kind;
+  a.n_groups = c->G;
+  a.steps = steps;
+  a.parts = parts;
+  // up to two tasks per warp (E <= 4: the accumulators of both fit the register budget)
+  const int tpw = E <= 4 ? 2 : 1;
+  a.splits = std::max(1, tpw * cfb::kSlotWarps / (c->G * parts));
+  const int tile = steps * cfb::kSlotThreads;
+  a.fold_tiles = std::max(1, 32768 / tile);  // an fp32 accumulator is folded into fp64 after at most ~32K rows of one CTA
+  a.F = c->lay.F;
+  a.U = c->lay.U;
+  a.f64 = c->d_f64;
+  a.u64 = c->d_u64;
+  a.err = c->d_err;
+  const size_t smem = cfb::slot_smem_bytes(c->n, c->G, steps);
+  const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm, (rows + tile - 1) / tile);
+  switch (E) {
+    case 1: return launch_slot_gram_e<1, 2>(c, a, smem, grid, s);
+    case 2: return launch_slot_gram_e<2, 2>(c, a, smem, grid, s);
+    case 3: return launch_slot_gram_e<3, 2>(c, a, smem, grid, s);
+    case 4: return launch_slot_gram_e<4, 2>(c, a, smem, grid, s);
+    case 6: return launch_slot_gram_e<6, 1>(c, a, smem, grid, s);
+    default: return launch_slot_gram_e<8, 1>(c, a, smem, grid, s);
+  }
+}
+
 int launch_group(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  {
+    const int rc = launch_slot_gram(c, sc, rows, s);
+    if (rc <= 0) return rc;
+  }
   if (getenv("CFB_NO_GROUP_KERNEL")) return 1;
   const int V = cfb::group_entries(c->n, c->kind);
   const int need = (V + 31) / 32;
