@@ -28,6 +28,7 @@
 
 #include "gram_launch.h"
 #include "group_kernel.cuh"
+#include "key_count_kernel.cuh"
 #include "key_dict.cuh"
 #include "pair_hash.cuh"
 #include "predict_kernel.cuh"
@@ -782,6 +783,41 @@ int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, 
   return CFB_OK;
 }
 
+// Key counts of the Naive-Bayes ring through a shared-memory histogram.  1 = shape does not qualify.
+int launch_key_count(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (c->kind != CFB_NB || c->m < 1 || getenv("CFB_NO_BUCKET")) return 1;
+  const long long D = c->lay.total_dom * c->G;
+  const int smem_max = dev_info(c->device).smem_optin - 1024;
+  if (D * 4 > smem_max) return 1;
+  cfb::KeyCountArgs a{};
+  a.cols = sc;
+  a.n_rows = rows;
+  a.m = c->m;
+  a.total_dom = (int)c->lay.total_dom;
+  a.n_groups = c->G;
+  a.U = c->lay.U;
+  for (int k = 0; k < cfb::kMaxCat; k++) {
+    a.lo[k] = c->lay.lo[k];
+    a.dom[k] = c->lay.dom[k];
+  }
+  for (int k = 0; k <= cfb::kMaxCat; k++) a.cat_off[k] = (int)c->lay.cat_off[k];
+  a.u64 = c->d_u64;
+  a.err = c->d_err;
+  static std::once_flag once[64];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[c->device & 63], [&] {
+    attr_err = cudaFuncSetAttribute(cfb::key_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  });
+  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const int per_sm = (int)std::max<long long>(1, std::min<long long>(2, smem_max / std::max<long long>(D * 4, 1)));
+  const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm,
+                                                                                 (rows + cfb::kBucketThreads - 1) / cfb::kBucketThreads));
+  cfb::key_count_kernel<<<grid, cfb::kBucketThreads, (size_t)D * 4, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
 // Is the role kernel usable for this scan?  Builds / refreshes the plan.  1 = no, 0 = yes.
 int role_prepare(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows) {
   if (c->kind != CFB_TRIPLE || c->m < 2 || c->lay.pairs_hashed || getenv("CFB_NO_ROLE")) return 1;
@@ -1065,6 +1101,11 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         const unsigned long long worst = std::min<unsigned long long>(cnt * npairs, (unsigned long long)dense_pair_entries(c->lay));
         int rc = hash_reserve(c, worst);
         if (rc) return rc;
+      }
+      if (!slab_numeric && c->kind == CFB_NB && cnt >= (unsigned long long)std::max(1, env_int("CFB_ROLE_MIN_ROWS", 16384))) {
+        const int rc = launch_key_count(c, part, cnt, s);  // the NB ring keeps key counts only
+        if (rc < 0) return rc;
+        if (rc == 0) continue;
       }
       if (!slab_numeric && cnt >= (unsigned long long)std::max(1, env_int("CFB_ROLE_MIN_ROWS", 16384))) {
         // dense small domains: pair counts in shared-memory tables, per-key sums by tile bucketing
