@@ -1,27 +1,28 @@
-// role_kernels.cuh -- kernel family K3 (categorical aggregates), v3: shared-memory pair tables.
+// role_kernels.cuh -- kernel family K3 (categorical aggregates): (key1,key2) pair counts in shared-memory tables.
 //
-// Replaces the per-row std::map updates of Triple::SumNoLift (sum_no_lift.cpp:158-214) for the
-// common case of dense, small categorical domains (e.g. BASELINE config 3: 10 columns of domain 100).
+// Replaces the per-row std::map updates of Triple::SumNoLift (sum_no_lift.cpp:195-214, and :158-189 when
+// bucket_sum_kernel does not apply) for the common case of dense, small categorical domains (e.g. BASELINE
+// config 3: 10 columns of domain 100).
 //
-// The categorical part is bound by the NUMBER of scattered updates a row makes (C3: 45 pair counts +
-// 10 x [count, 10 sums]), and the chip has two independent units that can execute them
-// (csrc/micro/cat_probe.cu, profiles/r01_cat_probe.txt, measured on the B200):
-//     L2 reductions (REDG)              ~200 G ops/s chip-wide, any width up to 128 bit
-//     shared-memory atomics (ATOMS)     ~420 G ops/s chip-wide (1.5 / clk / SM with 32 warps per SM)
-// match.any de-duplication + plain LDS/STS and warp-private plain read-modify-write tables were both
-// measured slower than ATOMS.  So this kernel uses BOTH units at once:
-//   * (key1,key2) pair counts go to shared-memory tables with ATOMS.  All pair tables do not fit one SM
-//     (C3: 45 x 10^4 cells), so they are cut into ROLES (RolePlan, built on the host): a CTA of role r
-//     holds that role's tables and scans ALL rows of its chunks for them; roles x replicas CTAs cover
-//     the grid.  Cells are 32-bit, or 16-bit packed two per word when that needs fewer roles (a chunk
-//     is at most 65 024 rows, so a 16-bit cell cannot overflow between folds);
-//   * per-key [count, x_0..x_{n-1}] payloads go out as 128-bit vector reductions into per-CTA fp32
-//     slabs in L2 (as in slab_kernels.cuh); every row is seen by all roles, so column c's payload is
-//     issued by role (c + chunk) mod n_roles only -- the L2 work is spread evenly over the CTAs and
-//     overlaps the ATOMS of the same instruction stream;
-//   * at the end of a chunk the CTA folds its tables / slab cells into the u64 / fp64 state.
-// Shapes this kernel does not take (GROUP BY slots, hashed pairs, tables larger than shared memory,
-// too many roles) stay on slab_scan_kernel.
+// The categorical part is bound by the NUMBER of scattered updates a row makes (C3: 45 pair counts + 10 x
+// [count, 10 sums]); csrc/micro/cat_probe.cu (profiles/r01_cat_probe.txt) measured the units that can execute
+// them on the B200: L2 reductions ~200 G ops/s chip-wide whatever their width, shared-memory atomics 2-4x that;
+// match.any de-duplication + plain LDS/STS and warp-private plain read-modify-write tables are slower than
+// ATOMS; L2 reductions and ATOMS issued together do not overlap.  So:
+//   * pair counts go to shared-memory tables with ATOMS.  All pair tables do not fit one SM (C3: 45 x 10^4
+//     cells), so they are cut into ROLES (RolePlan, built on the host, passed by value in the kernel
+//     parameters): a CTA of role r holds that role's tables (one sub-table per GROUP BY slot) and scans ALL
+//     rows of its chunks for them; roles x replicas CTAs cover the grid.  Cells are 32-bit, or 16-bit packed
+//     two per word when 32-bit cells would need too many roles (16-bit tables are folded at least every
+//     65 024 rows, so a cell cannot overflow);
+//   * every thread takes 4 consecutive rows per step, each key column as one 128-bit load: the loop over the
+//     tables is data dependent, and only wide loads keep enough bytes in flight to hide the L2 / HBM latency;
+//   * the per-key payloads [count, x_0..x_{n-1}] are normally done by bucket_sum_kernel (no float atomics).
+//     When that kernel does not apply (sum of domains > 4096) they go out from here as 128-bit vector
+//     reductions into per-CTA fp32 slabs in L2, every 4096-row tile by ONE role (rotating), all columns;
+//   * at the end of a chunk the CTA folds its tables / slab into the u64 / fp64 state.
+// Shapes this kernel does not take (hashed pairs, tables larger than shared memory, more roles than SMs / 8)
+// stay on slab_scan_kernel.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -132,3 +132,24 @@ def test_shapes_the_tables_do_not_fit_stay_on_the_l2_path():
     num, cat = _table(17, 60_000, 2, [2000, 700])  # 1.4 M cells: no shared-memory table
     got = _scan(num, cat)[0]
     assert_parity(got, oracle.aggregate_arrays(oracle.TRIPLE, num, cat)[0], what="wide pair table")
+
+
+def test_skewed_keys_and_nb_key_counts():
+    """Zipf-like keys (one hot bucket / hot cells: the worst case for bucket owners and for same-address atomics)
+    and the Naive-Bayes ring's shared-memory key histogram, with GROUP BY slots."""
+    from duckdb_imputation_b200 import CFB_NB
+    rng = np.random.default_rng(23)
+    rows = 200_000
+    num = [rng.random(rows).astype(np.float32) for _ in range(5)]
+    cat = [np.minimum(rng.zipf(1.2, rows) - 1, 99).astype(np.int32) for _ in range(4)]
+    ref = oracle.aggregate_arrays(oracle.TRIPLE, num, cat)[0]
+    assert ref["cat_counts"].max() > rows // 5  # really skewed
+    assert_parity(_scan(num, cat)[0], ref, what="zipf keys")
+    slots = rng.integers(-1, 3, rows).astype(np.int32)
+    dn, dc = _dev(num, np.float32), _dev(cat, np.int32)
+    with CofactorContext(CFB_NB, 5, 4, 3) as ctx:
+        ctx.scan_device(dn, dc, rows, d_group=torch.from_numpy(slots).cuda())
+        got = [ctx.finalize_arrays(g) for g in range(3)]
+    for g in range(3):
+        ref = oracle.aggregate_arrays(oracle.NB, num, cat, sel=np.nonzero(slots == g)[0].astype(np.uint32))[0]
+        assert_parity(got[g], ref, what=f"nb slot {g}")

@@ -15,6 +15,8 @@ CONFIGS = [
     ("C1", "sum_to_triple_5_0", CFB_TRIPLE, 5, 0, 0, 1, 1_000_000),
     ("C2", "sum_to_triple_20_0", CFB_TRIPLE, 20, 0, 0, 1, 1_000_000_000),
     ("C3", "sum_to_triple_10_10 (domain 100)", CFB_TRIPLE, 10, 10, 100, 1, 500_000_000),
+    ("C3z", "sum_to_triple_10_10, Zipf(1.2) keys in [0,100) (hot keys / hot cells)", CFB_TRIPLE, 10, 10, 100, 1, 50_000_000),
+    ("C3w", "sum_to_triple_10_2, domain 100 000 (pair counts in the hashed table)", CFB_TRIPLE, 10, 2, 100_000, 1, 50_000_000),
     ("C4a", "sum_to_nb_agg_12_4 GROUP BY label(10)", CFB_NB, 12, 4, 100, 10, 500_000_000),
     ("C4b", "sum_to_triple_12_0 GROUP BY label(10) (QDA per-class triples)", CFB_TRIPLE, 12, 0, 0, 10, 500_000_000),
     ("C5", "sum_to_triple_20_10 WHERE not null (MICE scan, 2-slot filter)", CFB_TRIPLE, 20, 10, 100, 2, 100_000_000),
@@ -31,7 +33,11 @@ for tag, name, kind, n, m, dom, G, full in CONFIGS:
     for k, t in enumerate(dn):
         nat.check(lib.cfb_gen_uniform_f32(0, t.data_ptr(), rows, synth.column_seed(3, k), 0, None))
     for k, t in enumerate(dc):
-        nat.check(lib.cfb_gen_int32(0, t.data_ptr(), rows, synth.column_seed(3, 100 + k), 0, 0, dom, None))
+        if tag == "C3z":  # host-generated skew (numpy), copied over
+            import numpy as np
+            t.copy_(torch.from_numpy(np.minimum(np.random.default_rng(k).zipf(1.2, rows) - 1, dom - 1).astype(np.int32)))
+        else:
+            nat.check(lib.cfb_gen_int32(0, t.data_ptr(), rows, synth.column_seed(3, 100 + k), 0, 0, dom, None))
     dg = None
     if G > 1:
         dg = torch.empty(rows, dtype=torch.int32, device="cuda")
@@ -60,6 +66,6 @@ for tag, name, kind, n, m, dom, G, full in CONFIGS:
     bpr = 4 * (n + m + (1 if G > 1 else 0))
     print(json.dumps({"config": tag, "workload": name, "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3,
                       "bytes_per_row": bpr, "gb_per_s": rows * bpr / ms / 1e6, "frac_of_measured_hbm_peak": rows * bpr / ms / 1e6 / PEAK,
-                      "kernels": "gram_scan" if (m == 0 and G == 1) else ("gram_scan + slab_scan" if G == 1 else "slab_scan")}), flush=True)
+                      }), flush=True)
     del dn, dc, dg
     torch.cuda.empty_cache()
