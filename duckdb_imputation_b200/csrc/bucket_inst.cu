@@ -32,7 +32,9 @@ cudaError_t bucket_launch(const BucketLaunchParams &p) {
   a.u64 = p.u64;
   a.err = p.err;
   auto kern = bucket_sum_kernel<N>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  // always the device maximum: host threads launch with different sizes concurrently, and a smaller value set by
+  // one thread must not undercut another thread's launch
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_max);
   if (e != cudaSuccess) return e;
   kern<<<p.grid, kBucketThreads, p.smem_bytes, p.stream>>>(a);
   return cudaGetLastError();

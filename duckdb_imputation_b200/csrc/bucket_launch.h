@@ -12,6 +12,7 @@ struct BucketLaunchParams {
   const Layout *lay;  // host copy
   unsigned long long rows;
   int tile_rows, fold_tiles, grid;
+  int smem_max;       // cudaDevAttrMaxSharedMemoryPerBlockOptin - 1 KB
   size_t smem_bytes;
   float *slab;
   double *f64;

@@ -771,6 +771,7 @@ int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, 
   p.tile_rows = tile;
   p.fold_tiles = std::max(1, 32768 / tile);  // an fp32 slab entry is folded into fp64 after at most ~32K rows of one CTA
   p.grid = grid;
+  p.smem_max = dev_info(c->device).smem_optin - 1024;
   p.smem_bytes = cfb::bucket_smem_bytes(c->n, c->m, D, tile);
   p.slab = c->d_slab;
   p.f64 = c->d_f64;
@@ -879,6 +880,7 @@ int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, bo
   p.pair_fold_chunks = c->role_bits == 16 ? std::max(1, cfb::kRoleFoldRows16 / (int)chunk) : (1 << 30) / (int)chunk;
   p.n_roles = c->role_roles;
   p.n_reps = n_reps;
+  p.smem_max = dev_info(c->device).smem_optin - 1024;
   p.smem_bytes = c->role_smem;
   p.skip = env_int("CFB_ROLE_DEBUG", 0) | (do_sums ? 0 : 2);
   p.n_sub = n_sub;

@@ -36,7 +36,9 @@ cudaError_t role_launch(const RoleLaunchParams &p) {
   a.u64 = p.u64;
   a.err = p.err;
   auto kern = role_scan_kernel<N, BITS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  // always the device maximum: host threads launch with different sizes concurrently, and a smaller value set by
+  // one thread must not undercut another thread's launch
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_max);
   if (e != cudaSuccess) return e;
   kern<<<p.n_roles * p.n_reps, kRoleThreads, p.smem_bytes, p.stream>>>(a);
   return cudaGetLastError();

@@ -16,6 +16,7 @@ struct RoleLaunchParams {
   unsigned long long rows;
   int chunk_rows, pair_fold_chunks, n_roles, n_reps;
   int skip, n_sub;
+  int smem_max;       // cudaDevAttrMaxSharedMemoryPerBlockOptin - 1 KB
   size_t smem_bytes;  // dynamic shared memory: the largest role's tables + the slot scratch
   float *slab;
   double *f64;

@@ -36,4 +36,12 @@ with CofactorContext(CFB_TRIPLE, 2, 2) as ctx:
 g = replay.glue()                                                                        # callbacks incl. lifted sums
 assert_struct_parity(g.query(0, num[:4], cat, group_by=grp, threads=2, lifted=True)[1],
                      oracle.aggregate(0, num[:4], cat, group_by=grp)[1], what="lifted")
+from duckdb_imputation_b200 import predict                                               # predict kernels
+model = predict.LinearModel([0.5], rng.standard_normal((1, 5)), [np.arange(-2, 9)] * 3, rng.standard_normal((1, 33)))
+out = torch.zeros(rows, dtype=torch.float32, device="cuda")
+predict.predict_device(model, dn[:5], dc, rows, predict.SCORE, out, d_mask=(dg > 1).to(torch.int32))
+lda = predict.LinearModel(rng.standard_normal(3), rng.standard_normal((3, 5)), [np.arange(-2, 9)] * 3, rng.standard_normal((3, 33)))
+cls = predict.predict_host(lda, num[:5], cat, predict.ARGMAX)
+torch.cuda.synchronize()
+assert cls.min() >= 0 and cls.max() <= 2
 print("sanitize smoke ok")
