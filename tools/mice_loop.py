@@ -1,0 +1,232 @@
+"""A GPU-resident MICE loop over a synthetic table (BASELINE config 5) -- what run_MICE_baseline
+(imputation/algorithms/imputation_base.cpp:4-145) does with SQL, done here with the C ABI:
+
+    for every iteration, for every column c with NULLs:
+        cofactor = sum_to_triple(all columns) over the rows where c is observed       (cfb_triple_device, row filter)
+        model    = train(cofactor, label = c)                                         (host, small matrices)
+        c[NULL rows] = predict(model, the other columns)                              (cfb_predict_device, in place)
+
+The trainers are out of scope of this repository (the small solves stay on the host): the tool closes
+the loop with closed-form numpy solvers on the cofactor -- least squares for FLOAT columns, LDA (pooled covariance)
+for INTEGER columns -- NOT the reference's gradient-descent linreg_train / LAPACK lda_train, and without the
+stochastic noise term.  `mice_cpu` is the same loop on the host (oracle cofactors + numpy predictions): the checker.
+
+    python tools/mice_loop.py [rows] [iterations]        one JSON line per iteration + a summary line
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+
+# ------------------------------------------------------------------ host side: moments -> models
+def moment_matrix(res):
+    """Cofactor (struct_result.result_arrays form) -> the moment matrix over z = [1 | x_0..x_{n-1} | one-hot keys]
+    (what ML/utils.cpp:176-310 builds as `sigma`), plus the feature layout."""
+    n, m = res["n"], res["m"]
+    offs, keys = res["cat_offsets"], res["cat_keys"]
+    tk = len(keys)
+    d = 1 + n + tk
+    M = np.zeros((d, d))
+    M[0, 0] = res["N"]
+    M[0, 1:1 + n] = M[1:1 + n, 0] = res["lin"]
+    iu = np.triu_indices(n)
+    Q = np.zeros((n, n))
+    Q[iu] = res["quad"]
+    Q = Q + Q.T - np.diag(np.diag(Q))
+    M[1:1 + n, 1:1 + n] = Q
+    M[0, 1 + n:] = M[1 + n:, 0] = res["cat_counts"]
+    if n:
+        M[1:1 + n, 1 + n:] = res["numcat"]
+        M[1 + n:, 1:1 + n] = res["numcat"].T
+    p = 0
+    for k in range(m):
+        for l in range(k, m):
+            lo, hi = res["pair_offsets"][p], res["pair_offsets"][p + 1]
+            k1, k2, cnt = res["pair_key1"][lo:hi], res["pair_key2"][lo:hi], res["pair_counts"][lo:hi]
+            r = 1 + n + offs[k] + np.searchsorted(keys[offs[k]:offs[k + 1]], k1)
+            c = 1 + n + offs[l] + np.searchsorted(keys[offs[l]:offs[l + 1]], k2)
+            M[r, c] = cnt
+            M[c, r] = cnt
+            p += 1
+    return M
+
+
+def train_linreg(res, label):
+    """Least squares of numeric column `label` on [1 | other numerics | one-hot of every categorical column]."""
+    n = res["n"]
+    M = moment_matrix(res)
+    feat = [i for i in range(M.shape[0]) if i != 1 + label]
+    w = np.linalg.pinv(M[np.ix_(feat, feat)], rcond=1e-10, hermitian=True) @ M[feat, 1 + label]
+    offs, keys = res["cat_offsets"], res["cat_keys"]
+    return {"bias": np.array([w[0]]), "w_num": w[1:n][None, :], "keys": [keys[offs[c]:offs[c + 1]] for c in range(res["m"])],
+            "w_cat": w[n:][None, :]}
+
+
+def train_lda(res, label):
+    """LDA (pooled covariance, class priors) of categorical column `label` on [numerics | one-hot of the other
+    categorical columns]; scores are linear: w_k = Sigma^-1 mu_k, b_k = -mu_k.w_k / 2 + log prior."""
+    n, m = res["n"], res["m"]
+    M = moment_matrix(res)
+    offs, keys = res["cat_offsets"], res["cat_keys"]
+    lab = np.arange(1 + n + offs[label], 1 + n + offs[label + 1])
+    feat = np.array([i for i in range(1, M.shape[0]) if i not in set(lab)])
+    nk = M[0, lab]
+    mu = M[np.ix_(lab, feat)] / np.maximum(nk, 1)[:, None]           # class means of the features
+    Sw = M[np.ix_(feat, feat)] - (mu * nk[:, None]).T @ mu           # within-class scatter
+    W = (np.linalg.pinv(Sw / max(res["N"] - len(lab), 1), rcond=1e-10, hermitian=True) @ mu.T).T
+    b = -0.5 * np.einsum("kf,kf->k", mu, W) + np.log(np.maximum(nk, 1e-300) / res["N"])
+    other = [c for c in range(m) if c != label]
+    cat_w = W[:, n:]                                                  # columns follow `feat`: numerics, then the other cat columns in order
+    return {"bias": b, "w_num": W[:, :n], "keys": [keys[offs[c]:offs[c + 1]] for c in other], "w_cat": cat_w,
+            "classes": keys[offs[label]:offs[label + 1]]}
+
+
+def predict_np(model, num_cols, cat_cols):
+    """numpy scores of rows (fp64) -- the checker for cfb_predict_*."""
+    rows = len(num_cols[0]) if num_cols else len(cat_cols[0])
+    s = np.tile(model["bias"][None, :], (rows, 1))
+    for i, x in enumerate(num_cols):
+        s += np.asarray(x, np.float64)[:, None] * model["w_num"][:, i][None, :]
+    off = 0
+    for c, col in enumerate(cat_cols):
+        k = model["keys"][c]
+        pos = np.searchsorted(k, col)
+        hit = (pos < len(k)) & (k[np.minimum(pos, len(k) - 1)] == col)
+        s[hit] += model["w_cat"][:, off + pos[hit]].T
+        off += len(k)
+    return s
+
+
+# ------------------------------------------------------------------ the two loops
+def mice_cpu(num, cat, null_num, null_cat, iters):
+    """Host loop (oracle cofactors + numpy predictions).  num / cat: lists of numpy columns (modified in place);
+    null_num / null_cat: {column index: boolean NULL mask}."""
+    from oracle import oracle
+    for _ in range(iters):
+        for c, mask in null_cat.items():
+            res = oracle.aggregate_arrays(oracle.TRIPLE, num, cat, sel=np.nonzero(~mask)[0].astype(np.uint32))[0]
+            model = train_lda(res, c)
+            s = predict_np(model, [x[mask] for x in num], [x[mask] for k, x in enumerate(cat) if k != c])
+            cat[c][mask] = np.argmax(s, axis=1).astype(np.int32)      # the class INDEX, as LDA_impute (lda.cpp:575)
+        for c, mask in null_num.items():
+            res = oracle.aggregate_arrays(oracle.TRIPLE, num, cat, sel=np.nonzero(~mask)[0].astype(np.uint32))[0]
+            model = train_linreg(res, c)
+            s = predict_np(model, [x[mask] for k, x in enumerate(num) if k != c], [x[mask] for x in cat])
+            num[c][mask] = s[:, 0].astype(np.float32)
+    return num, cat
+
+
+def mice_gpu(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None):
+    """Device loop.  d_num / d_cat: lists of torch CUDA tensors (modified in place); d_null_*: {column: int32 mask
+    tensor, 1 = NULL}.  Returns per-iteration timings (ms): scan / train / predict."""
+    import torch
+    from duckdb_imputation_b200 import CFB_TRIPLE, CofactorContext, predict
+    n, m = len(d_num), len(d_cat)
+    slots = {("c", c): torch.where(msk != 0, -1, 0).to(torch.int32) for c, msk in d_null_cat.items()}
+    slots.update({("n", c): torch.where(msk != 0, -1, 0).to(torch.int32) for c, msk in d_null_num.items()})
+    out = []
+    for it in range(iters):
+        t = {"scan": 0.0, "train": 0.0, "predict": 0.0}
+        for kind, cols in (("c", d_null_cat), ("n", d_null_num)):
+            for c, msk in cols.items():
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with CofactorContext(CFB_TRIPLE, n, m) as ctx:
+                    if domains is not None:
+                        ctx.set_cat_domain([d[0] for d in domains], [d[1] for d in domains])
+                    ctx.scan_device(d_num, d_cat, rows, d_group=slots[(kind, c)])
+                    res = ctx.finalize_arrays()
+                t1 = time.perf_counter()
+                if kind == "c":
+                    mdl = train_lda(res, c)
+                    lm = predict.LinearModel(mdl["bias"], mdl["w_num"], mdl["keys"], mdl["w_cat"])
+                    t2 = time.perf_counter()
+                    predict.predict_device(lm, d_num, [x for k, x in enumerate(d_cat) if k != c], rows, predict.ARGMAX, d_cat[c], d_mask=msk)
+                else:
+                    mdl = train_linreg(res, c)
+                    lm = predict.LinearModel(mdl["bias"], mdl["w_num"], mdl["keys"], mdl["w_cat"])
+                    t2 = time.perf_counter()
+                    predict.predict_device(lm, [x for k, x in enumerate(d_num) if k != c], d_cat, rows, predict.SCORE, d_num[c], d_mask=msk)
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+                lm.close()
+                t["scan"] += (t1 - t0) * 1e3
+                t["train"] += (t2 - t1) * 1e3
+                t["predict"] += (t3 - t2) * 1e3
+        out.append(t)
+        if log:
+            log(it, t)
+    return out
+
+
+def synthetic_table(rows, n=20, m=10, dom=10, null_num=(0, 1), null_cat=(0,), null_frac=0.2, seed=5):
+    """Correlated columns (so that there is something to impute), NULL cells pre-filled with the column mean / mode
+    as init_baseline does (partition.cpp:700-712)."""
+    rng = np.random.default_rng(seed)
+    latent = rng.standard_normal((rows, 3)).astype(np.float32)
+    num = [(latent @ rng.standard_normal(3).astype(np.float32) + 0.3 * rng.standard_normal(rows).astype(np.float32)).astype(np.float32)
+           for _ in range(n)]
+    cat = []
+    for _ in range(m):
+        z = latent @ rng.standard_normal(3).astype(np.float32) + 0.5 * rng.standard_normal(rows).astype(np.float32)
+        cat.append(np.clip(((z - z.min()) / (z.max() - z.min() + 1e-9) * dom).astype(np.int32), 0, dom - 1))
+    masks_num = {c: rng.random(rows) < null_frac for c in null_num}
+    masks_cat = {c: rng.random(rows) < null_frac for c in null_cat}
+    truth = {("n", c): num[c].copy() for c in null_num}
+    truth.update({("c", c): cat[c].copy() for c in null_cat})
+    for c, msk in masks_num.items():
+        num[c][msk] = num[c][~msk].mean()
+    for c, msk in masks_cat.items():
+        cat[c][msk] = np.bincount(cat[c][~msk]).argmax()
+    return num, cat, masks_num, masks_cat, truth
+
+
+def main():
+    import torch
+    rows = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    rows -= rows % 4
+    n, m, dom = 20, 10, 10
+    # the table is generated in slices on the host (numpy) and moved over; 100 M rows x 30 columns = 12 GB
+    d_num = [torch.empty(rows, dtype=torch.float32, device="cuda") for _ in range(n)]
+    d_cat = [torch.empty(rows, dtype=torch.int32, device="cuda") for _ in range(m)]
+    null_num, null_cat = (0, 1), (0,)
+    d_nn = {c: torch.empty(rows, dtype=torch.int32, device="cuda") for c in null_num}
+    d_nc = {c: torch.empty(rows, dtype=torch.int32, device="cuda") for c in null_cat}
+    step = 5_000_000
+    for lo in range(0, rows, step):
+        k = min(step, rows - lo)
+        num, cat, mn, mc, _ = synthetic_table(k, n, m, dom, null_num, null_cat, seed=5 + lo // step)
+        for i in range(n):
+            d_num[i][lo:lo + k] = torch.from_numpy(num[i])
+        for i in range(m):
+            d_cat[i][lo:lo + k] = torch.from_numpy(cat[i])
+        for c in null_num:
+            d_nn[c][lo:lo + k] = torch.from_numpy(mn[c].astype(np.int32))
+        for c in null_cat:
+            d_nc[c][lo:lo + k] = torch.from_numpy(mc[c].astype(np.int32))
+    torch.cuda.synchronize()
+    mice_gpu(d_num, d_cat, d_nn, d_nc, 1, rows, domains=[(0, dom - 1)] * m)  # warm-up iteration (also a real one)
+
+    def log(it, t):
+        print(json.dumps({"mice_iteration": it, "rows": rows, "columns": f"{n} FLOAT + {m} INT (domain {dom})",
+                          "null_columns": len(null_num) + len(null_cat), "ms": {k: round(v, 2) for k, v in t.items()},
+                          "ms_total": round(sum(t.values()), 2)}), flush=True)
+
+    ts = mice_gpu(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m, log=log)
+    tot = sum(sum(t.values()) for t in ts)
+    scans = iters * (len(null_num) + len(null_cat))
+    print(json.dumps({"summary": "MICE loop on one B200, table resident in HBM", "rows": rows, "iterations": iters,
+                      "ms_per_iteration": round(tot / iters, 2), "cofactor_scans": scans,
+                      "ms_per_scan": round(sum(t["scan"] for t in ts) / scans, 2),
+                      "scan_rows_per_s": round(rows * scans / (sum(t["scan"] for t in ts) * 1e-3)),
+                      "ms_per_predict": round(sum(t["predict"] for t in ts) / scans, 2),
+                      "ms_per_train_host": round(sum(t["train"] for t in ts) / scans, 2)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
