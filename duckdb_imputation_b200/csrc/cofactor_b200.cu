@@ -962,13 +962,23 @@ int launch_slot_gram_e(cfb_ctx *c, const cfb::SlotGramArgs &a, size_t smem, int 
 int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
   if (getenv("CFB_NO_SLOT_GRAM") || c->n < 1 || c->G > cfb::kSlotMaxGroups) return 1;
   if (rows < (unsigned long long)std::max(1, env_int("CFB_SLOT_MIN_ROWS", 8192))) return 1;
-  // output entries of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows
-  const int V = cfb::slot_entries(c->n, c->kind), parts_max = cfb::kSlotWarps / c->G;
-  int parts = 1;
-  while (parts < parts_max && (V + 32 * parts - 1) / (32 * parts) > 4) parts++;
-  int E = (V + 32 * parts - 1) / (32 * parts);
-  if (E > 8) return 1;
-  E = E == 5 ? 6 : (E == 7 ? 8 : E);
+  // output entries of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows.  A warp
+  // carries up to two tasks when E <= 4 (the accumulators of both fit the register budget).
+  const int V = cfb::slot_entries(c->n, c->kind);
+  int parts = 0, E = 0, tpw = 0;
+  for (int t : {2, 1}) {
+    const int parts_max = t * cfb::kSlotWarps / c->G, e_max = t == 2 ? 4 : 8;
+    if (parts_max < 1) continue;
+    int p = 1;
+    while (p < parts_max && (V + 32 * p - 1) / (32 * p) > 4) p++;
+    const int e = (V + 32 * p - 1) / (32 * p);
+    if (e > e_max) continue;
+    parts = p;
+    E = e == 5 ? 6 : (e == 7 ? 8 : e);
+    tpw = t;
+    break;
+  }
+  if (!parts) return 1;
   const int smem_max = dev_info(c->device).smem_optin - 1024;
   // two CTAs per SM when a tile of >= 2 rows per thread still fits twice, else one
   const size_t half = (size_t)smem_max / 2 - 1024;
@@ -988,8 +998,6 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   a.n_groups = c->G;
   a.steps = steps;
   a.parts = parts;
-  // up to two tasks per warp (E <= 4: the accumulators of both fit the register budget)
-  const int tpw = E <= 4 ? 2 : 1;
   a.splits = std::max(1, tpw * cfb::kSlotWarps / (c->G * parts));
   const int tile = steps * cfb::kSlotThreads;
   a.fold_tiles = std::max(1, 32768 / tile);  // an fp32 accumulator is folded into fp64 after at most ~32K rows of one CTA
@@ -1001,10 +1009,10 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   const size_t smem = cfb::slot_smem_bytes(c->n, c->G, steps);
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm, (rows + tile - 1) / tile);
   switch (E) {
-    case 1: return launch_slot_gram_e<1, 2>(c, a, smem, grid, s);
-    case 2: return launch_slot_gram_e<2, 2>(c, a, smem, grid, s);
-    case 3: return launch_slot_gram_e<3, 2>(c, a, smem, grid, s);
-    case 4: return launch_slot_gram_e<4, 2>(c, a, smem, grid, s);
+    case 1: return tpw == 2 ? launch_slot_gram_e<1, 2>(c, a, smem, grid, s) : launch_slot_gram_e<1, 1>(c, a, smem, grid, s);
+    case 2: return tpw == 2 ? launch_slot_gram_e<2, 2>(c, a, smem, grid, s) : launch_slot_gram_e<2, 1>(c, a, smem, grid, s);
+    case 3: return tpw == 2 ? launch_slot_gram_e<3, 2>(c, a, smem, grid, s) : launch_slot_gram_e<3, 1>(c, a, smem, grid, s);
+    case 4: return tpw == 2 ? launch_slot_gram_e<4, 2>(c, a, smem, grid, s) : launch_slot_gram_e<4, 1>(c, a, smem, grid, s);
     case 6: return launch_slot_gram_e<6, 1>(c, a, smem, grid, s);
     default: return launch_slot_gram_e<8, 1>(c, a, smem, grid, s);
   }

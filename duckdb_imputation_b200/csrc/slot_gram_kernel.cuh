@@ -28,7 +28,7 @@ namespace cfb {
 constexpr int kSlotThreads = 512;  // two CTAs per SM: one loads and sorts its tile while the other adds up
 constexpr int kSlotWarps = kSlotThreads / 32;
 constexpr int kSlotMaxSteps = 4;   // rows per thread and tile
-constexpr int kSlotMaxGroups = 16;
+constexpr int kSlotMaxGroups = 32;
 
 struct SlotGramArgs {
   ScanCols cols;
