@@ -8,6 +8,7 @@ import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 import mice_loop  # noqa: E402
+from tests import mice_host  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -21,7 +22,7 @@ def test_device_loop_matches_host_loop():
     d_nn = {c: torch.from_numpy(m.astype(np.int32)).cuda() for c, m in mn.items()}
     d_nc = {c: torch.from_numpy(m.astype(np.int32)).cuda() for c, m in mc.items()}
     mice_loop.mice_gpu(d_num, d_cat, d_nn, d_nc, 2, rows)
-    h_num, h_cat = mice_loop.mice_cpu([c.copy() for c in num], [c.copy() for c in cat], mn, mc, 2)
+    h_num, h_cat = mice_host.mice_cpu([c.copy() for c in num], [c.copy() for c in cat], mn, mc, 2)
     for c, msk in mn.items():
         got = d_num[c].cpu().numpy()
         assert np.array_equal(got[~msk], num[c][~msk])  # observed cells untouched

@@ -8,6 +8,7 @@ import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 import mice_loop  # noqa: E402
+from tests import mice_host  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 pytest.importorskip("sklearn")
@@ -43,7 +44,7 @@ def test_lda_from_cofactor_equals_sklearn_lda():
 def test_cpu_mice_loop_imputes_better_than_the_mean():
     num, cat, mn, mc, truth = mice_loop.synthetic_table(6000, n=5, m=3, dom=5, null_num=(0,), null_cat=(1,), seed=3)
     before = np.abs(num[0][mn[0]] - truth[("n", 0)][mn[0]]).mean()
-    num, cat = mice_loop.mice_cpu(num, cat, mn, mc, 2)
+    num, cat = mice_host.mice_cpu(num, cat, mn, mc, 2)
     after = np.abs(num[0][mn[0]] - truth[("n", 0)][mn[0]]).mean()
     assert after < 0.6 * before
     assert (cat[1][mc[1]] == truth[("c", 1)][mc[1]]).mean() > 0.35  # 5 classes: chance is 0.2

@@ -1,7 +1,7 @@
 """Host-fed (DuckDB callbacks) throughput of the categorical / GROUP BY configs, next to the
 reference's own callbacks on the same columns (oracle/_ref) -- both through the replay host."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from duckdb_imputation_b200 import replay
 from oracle import ref_replay

@@ -1,6 +1,6 @@
 """Small end-to-end exercise of every kernel, meant to run under compute-sanitizer."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from duckdb_imputation_b200 import CFB_NB, CFB_TRIPLE, CofactorContext, replay

@@ -9,7 +9,8 @@
 The trainers are out of scope of this repository (the small solves stay on the host): the tool closes
 the loop with closed-form numpy solvers on the cofactor -- least squares for FLOAT columns, LDA (pooled covariance)
 for INTEGER columns -- NOT the reference's gradient-descent linreg_train / LAPACK lda_train, and without the
-stochastic noise term.  `mice_cpu` is the same loop on the host (oracle cofactors + numpy predictions): the checker.
+stochastic noise term.  tests/mice_host.py holds the same loop on the host (oracle cofactors + numpy predictions):
+the checker.
 
     python tools/mice_loop.py [rows] [iterations]        one JSON line per iteration + a summary line
 """
@@ -101,25 +102,7 @@ def predict_np(model, num_cols, cat_cols):
     return s
 
 
-# ------------------------------------------------------------------ the two loops
-def mice_cpu(num, cat, null_num, null_cat, iters):
-    """Host loop (oracle cofactors + numpy predictions).  num / cat: lists of numpy columns (modified in place);
-    null_num / null_cat: {column index: boolean NULL mask}."""
-    from oracle import oracle
-    for _ in range(iters):
-        for c, mask in null_cat.items():
-            res = oracle.aggregate_arrays(oracle.TRIPLE, num, cat, sel=np.nonzero(~mask)[0].astype(np.uint32))[0]
-            model = train_lda(res, c)
-            s = predict_np(model, [x[mask] for x in num], [x[mask] for k, x in enumerate(cat) if k != c])
-            cat[c][mask] = np.argmax(s, axis=1).astype(np.int32)      # the class INDEX, as LDA_impute (lda.cpp:575)
-        for c, mask in null_num.items():
-            res = oracle.aggregate_arrays(oracle.TRIPLE, num, cat, sel=np.nonzero(~mask)[0].astype(np.uint32))[0]
-            model = train_linreg(res, c)
-            s = predict_np(model, [x[mask] for k, x in enumerate(num) if k != c], [x[mask] for x in cat])
-            num[c][mask] = s[:, 0].astype(np.float32)
-    return num, cat
-
-
+# ------------------------------------------------------------------ the device loop
 def mice_gpu(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None):
     """Device loop.  d_num / d_cat: lists of torch CUDA tensors (modified in place); d_null_*: {column: int32 mask
     tensor, 1 = NULL}.  Returns per-iteration timings (ms): scan / train / predict."""
