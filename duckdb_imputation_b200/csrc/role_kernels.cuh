@@ -97,23 +97,29 @@ __device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, u
     if constexpr (TAIL) return load_rows4<int4>(col, r, hi);
     else return *reinterpret_cast<const int4 *>(col + r);
   };
-  bool on[4] = {true, !TAIL || r + 1 < hi, !TAIL || r + 2 < hi, !TAIL || r + 3 < hi};
+  // bit i of a mask = row r + i
+  unsigned on = 1u | (!TAIL || r + 1 < hi ? 2u : 0u) | (!TAIL || r + 2 < hi ? 4u : 0u) | (!TAIL || r + 3 < hi ? 8u : 0u);
   int gv[4] = {0, 0, 0, 0};  // GROUP BY slot of the row
-  bool bad = false;
+  unsigned bad = 0;
   if (a.cols.group) {
     const int4 g = rows4(a.cols.group);
     gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+    unsigned in = 0, over = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (on[i] && gv[i] >= a.n_groups) atomicExch(a.err, 2);
-      on[i] = on[i] && gv[i] >= 0 && gv[i] < a.n_groups;  // < 0: filtered row
+      in |= ((unsigned)gv[i] < (unsigned)a.n_groups ? 1u : 0u) << i;  // < 0: filtered row
+      over |= (gv[i] >= a.n_groups ? 1u : 0u) << i;
     }
+    if (on & over) atomicExch(a.err, 2);
+    on &= in;
   }
   // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the first
   // column (and whether the row counts at all) are refreshed only when k changes (a CTA-uniform branch).
+  // The reductions are predicated, not branched around (red.shared has no result to wait for).
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(role_smem);
   int prev_k = -1;
   unsigned sk[4] = {0, 0, 0, 0};
-  bool ok[4] = {false, false, false, false};
+  unsigned ok = 0;
   for (int t = 0; t < ((a.skip & 1) ? 0 : nt); t++) {
     const RoleTable &d = a.plan.tbl[role][t];
     if (d.k != prev_k) {
@@ -122,28 +128,29 @@ __device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, u
       const int lo_k = a.lo[d.k];
       const unsigned dom_k = (unsigned)a.dom[d.k];
       sk[0] = (unsigned)(v.x - lo_k), sk[1] = (unsigned)(v.y - lo_k), sk[2] = (unsigned)(v.z - lo_k), sk[3] = (unsigned)(v.w - lo_k);
+      ok = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        ok[i] = on[i] && sk[i] < dom_k;
-        bad |= on[i] && !ok[i];
-      }
+      for (int i = 0; i < 4; i++) ok |= (sk[i] < dom_k ? 1u : 0u) << i;
+      bad |= on & ~ok;
+      ok &= on;
     }
     const int4 v = rows4(a.cols.cat[d.l]);
     const int lo_l = a.lo[d.l];
     const unsigned sl[4] = {(unsigned)(v.x - lo_l), (unsigned)(v.y - lo_l), (unsigned)(v.z - lo_l), (unsigned)(v.w - lo_l)};
     const unsigned dom_l = (unsigned)d.dom_l;
-    unsigned *tbl = role_smem + d.word_off;
+    const unsigned tbl = smem_base + 4u * (unsigned)d.word_off;
+    unsigned hit = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) hit |= (sl[i] < dom_l ? 1u : 0u) << i;
+    bad |= ok & ~hit;
+    hit &= ok;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const bool hit = ok[i] && sl[i] < dom_l;
-      bad |= ok[i] && !hit;
-      if (!hit) continue;
       unsigned cell = sk[i] * dom_l + sl[i];
       if (a.n_groups > 1) cell += (unsigned)gv[i] * (unsigned)d.gwords * (BITS == 32 ? 1u : 2u);
-      if constexpr (BITS == 32)
-        atomicAdd(tbl + cell, 1u);
-      else
-        atomicAdd(tbl + (cell >> 1), 1u << ((cell & 1u) * 16));
+      const unsigned addr = tbl + (BITS == 32 ? 4u * cell : 4u * (cell >> 1));
+      const unsigned inc = BITS == 32 ? 1u : 1u << ((cell & 1u) * 16);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(inc), "r"(hit & (1u << i)) : "memory");
     }
   }
   // per-key payload [1, x_0..x_{N-1}] of all columns when this tile is this role's: L2 vector reductions,
@@ -168,9 +175,9 @@ __device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, u
                                 {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (!on[i]) continue;
+          if (!(on & (1u << i))) continue;
           if (sc[i] >= (unsigned)a.dom[c]) {
-            bad = true;
+            bad |= 1u;
             continue;
           }
           red_v4(slab + (size_t)(a.cat_off[c] + (int)sc[i]) * P + 4 * q, xr[i][0], xr[i][1], xr[i][2], xr[i][3]);
