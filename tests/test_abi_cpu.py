@@ -47,6 +47,19 @@ def test_no_device_means_error_not_fallback():
         sum_to_triple([np.ones(4, np.float32)], [])
 
 
+def test_predict_entry_points_without_device():
+    """The write-back entry points fail loudly too: no model upload, no scoring on the host."""
+    l = nat.lib()
+    if l.cfb_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    from duckdb_imputation_b200 import predict
+    with pytest.raises(nat.CofactorError, match="no CPU fallback"):
+        predict.LinearModel([0.0], [[1.0, 2.0]])
+    assert l.cfb_predict_device(None, None, None, None, 4, 0, None, None) == nat.CFB_ERR_INVALID
+    assert l.cfb_predict_host(None, None, None, None, None, 4, 0, None) == nat.CFB_ERR_INVALID
+    l.cfb_model_destroy(None)
+
+
 def test_argument_validation_without_device():
     l = nat.lib()
     h = C.c_void_p()
