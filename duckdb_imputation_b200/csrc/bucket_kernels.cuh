@@ -36,7 +36,7 @@ struct BucketArgs {
   int m, total_dom;
   int n_groups;    // GROUP BY slots: bucket = (slot, column, key); n_groups * total_dom <= kBucketMaxDom
   long long F, U;  // per-slot strides of the f64 / u64 state
-  int tile_rows;   // multiple of kBucketThreads
+  int tile_rows;   // rows per tile (<= 65536: row ids are 16-bit)
   int fold_tiles;  // fold the slab into the state every this many tiles of a CTA
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];
   long long numcat_base;

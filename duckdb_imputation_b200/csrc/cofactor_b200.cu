@@ -757,7 +757,7 @@ int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, 
   if (c->lay.total_dom * c->G > cfb::kBucketMaxDom) return 1;
   const int P = cfb::pad4(1 + c->n), D = (int)c->lay.total_dom * c->G;  // buckets
   const long long budget = (long long)dev_info(c->device).smem_optin - 1024 - 8ll * D;
-  int tile = (int)(budget / (4 * P + 2 * c->m)) / cfb::kBucketThreads * cfb::kBucketThreads;
+  int tile = (int)(budget / (4 * P + 2 * c->m)) / 256 * 256;  // any multiple of 4 rows works; 256 keeps the passes even
   tile = std::min(tile, 4096);
   if (tile < cfb::kBucketThreads) return 1;
   const unsigned long long n_tiles = (rows + tile - 1) / tile;
