@@ -80,6 +80,7 @@ int device_count_quiet() {
 struct DeviceInfo {
   int sms = 0;
   int smem_optin = 0;
+  int smem_sm = 0;  // shared memory of one SM (all resident CTAs together)
 };
 DeviceInfo g_dev[64];
 std::once_flag g_dev_once[64];
@@ -88,6 +89,7 @@ const DeviceInfo &dev_info(int d) {
   std::call_once(g_dev_once[d], [d] {
     cudaDeviceGetAttribute(&g_dev[d].sms, cudaDevAttrMultiProcessorCount, d);
     cudaDeviceGetAttribute(&g_dev[d].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d);
+    cudaDeviceGetAttribute(&g_dev[d].smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d);
   });
   return g_dev[d];
 }
@@ -966,11 +968,11 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   // carries up to two tasks when E <= 4 (the accumulators of both fit the register budget).
   const int V = cfb::slot_entries(c->n, c->kind);
   int parts = 0, E = 0, tpw = 0;
-  for (int t : {2, 1}) {
+  for (int t : {2, 1}) {  // tasks per warp (4 tasks of 3 entries spill at the 64-register budget and measured slower)
     const int parts_max = t * cfb::kSlotWarps / c->G, e_max = t == 2 ? 4 : 8;
     if (parts_max < 1) continue;
     int p = 1;
-    while (p < parts_max && (V + 32 * p - 1) / (32 * p) > 4) p++;
+    while (p < parts_max && (V + 32 * p - 1) / (32 * p) > e_max) p++;
     const int e = (V + 32 * p - 1) / (32 * p);
     if (e > e_max) continue;
     parts = p;
@@ -980,16 +982,20 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   }
   if (!parts) return 1;
   const int smem_max = dev_info(c->device).smem_optin - 1024;
-  // two CTAs per SM when a tile of >= 2 rows per thread still fits twice, else one
-  const size_t half = (size_t)smem_max / 2 - 1024;
-  int steps = cfb::kSlotMaxSteps, per_sm = 2;
-  while (steps >= 2 && cfb::slot_smem_bytes(c->n, c->G, steps) > half) steps--;
-  if (cfb::slot_smem_bytes(c->n, c->G, steps) > half) {
-    per_sm = 1;
-    steps = cfb::kSlotMaxSteps;
-    while (steps >= 1 && cfb::slot_smem_bytes(c->n, c->G, steps) > (size_t)smem_max) steps--;
-    if (steps < 1) return 1;
+  // as many CTAs per SM (up to 4) as still leave a tile of >= 2 rows per thread
+  int steps = 0, per_sm = 1;
+  for (int want : {4, 3, 2, 1}) {
+    if (want > 2 && (E * tpw > 6 || E > 3)) continue;  // those instantiations take 128 registers (launch bounds)
+    const size_t budget = want == 1 ? (size_t)smem_max : (size_t)(dev_info(c->device).smem_sm - 1024 * want) / want - 512;
+    int st = cfb::kSlotMaxSteps;
+    while (st >= 1 && cfb::slot_smem_bytes(c->n, c->G, st) > budget) st--;
+    if (st >= (want == 1 ? 1 : 2)) {
+      steps = st;
+      per_sm = want;
+      break;
+    }
   }
+  if (steps < 1) return 1;
   cfb::SlotGramArgs a{};
   a.cols = sc;
   a.n_rows = rows;

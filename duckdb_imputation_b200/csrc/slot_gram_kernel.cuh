@@ -25,7 +25,7 @@
 
 namespace cfb {
 
-constexpr int kSlotThreads = 512;  // two CTAs per SM: one loads and sorts its tile while the other adds up
+constexpr int kSlotThreads = 256;  // several CTAs per SM: some load and sort their tiles while others add up
 constexpr int kSlotWarps = kSlotThreads / 32;
 constexpr int kSlotMaxSteps = 4;   // rows per thread and tile
 constexpr int kSlotMaxGroups = 32;
@@ -55,7 +55,7 @@ __host__ __device__ inline size_t slot_smem_bytes(int n, int n_groups, int steps
 }
 
 template <int E, int TPW>
-__global__ void __launch_bounds__(kSlotThreads, 2) slot_gram_kernel(const __grid_constant__ SlotGramArgs a) {
+__global__ void __launch_bounds__(kSlotThreads, E * TPW > 6 || E > 3 ? 2 : 4) slot_gram_kernel(const __grid_constant__ SlotGramArgs a) {
   extern __shared__ __align__(16) float slot_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = a.n, G = a.n_groups, U = a.steps, P = slot_pitch(G, U);
