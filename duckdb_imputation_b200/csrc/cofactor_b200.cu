@@ -964,19 +964,19 @@ int launch_slot_gram_e(cfb_ctx *c, const cfb::SlotGramArgs &a, size_t smem, int 
 int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
   if (getenv("CFB_NO_SLOT_GRAM") || c->n < 1 || c->G > cfb::kSlotMaxGroups) return 1;
   if (rows < (unsigned long long)std::max(1, env_int("CFB_SLOT_MIN_ROWS", 8192))) return 1;
-  // output entries of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows.  A warp
-  // carries up to two tasks when E <= 4 (the accumulators of both fit the register budget).
-  const int V = cfb::slot_entries(c->n, c->kind);
+  // 2x2 blocks of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows.  A warp carries
+  // two tasks when E == 1 (8 accumulators per block and task).
+  const int V = cfb::slot_blocks(c->n, c->kind);
   int parts = 0, E = 0, tpw = 0;
-  for (int t : {2, 1}) {  // tasks per warp (4 tasks of 3 entries spill at the 64-register budget and measured slower)
-    const int parts_max = t * cfb::kSlotWarps / c->G, e_max = t == 2 ? 4 : 8;
+  for (int t : {2, 1}) {
+    const int parts_max = t * cfb::kSlotWarps / c->G, e_max = t == 2 ? 1 : 4;
     if (parts_max < 1) continue;
     int p = 1;
     while (p < parts_max && (V + 32 * p - 1) / (32 * p) > e_max) p++;
     const int e = (V + 32 * p - 1) / (32 * p);
     if (e > e_max) continue;
     parts = p;
-    E = e == 5 ? 6 : (e == 7 ? 8 : e);
+    E = e == 3 ? 4 : e;
     tpw = t;
     break;
   }
@@ -985,7 +985,7 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   // as many CTAs per SM (up to 4) as still leave a tile of >= 2 rows per thread
   int steps = 0, per_sm = 1;
   for (int want : {4, 3, 2, 1}) {
-    if (want > 2 && (E * tpw > 6 || E > 3)) continue;  // those instantiations take 128 registers (launch bounds)
+    if (want > 2 && E > 1) continue;  // those instantiations take 128 registers (launch bounds)
     const size_t budget = want == 1 ? (size_t)smem_max : (size_t)(dev_info(c->device).smem_sm - 1024 * want) / want - 512;
     int st = cfb::kSlotMaxSteps;
     while (st >= 1 && cfb::slot_smem_bytes(c->n, c->G, st) > budget) st--;
@@ -1016,11 +1016,8 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm, (rows + tile - 1) / tile);
   switch (E) {
     case 1: return tpw == 2 ? launch_slot_gram_e<1, 2>(c, a, smem, grid, s) : launch_slot_gram_e<1, 1>(c, a, smem, grid, s);
-    case 2: return tpw == 2 ? launch_slot_gram_e<2, 2>(c, a, smem, grid, s) : launch_slot_gram_e<2, 1>(c, a, smem, grid, s);
-    case 3: return tpw == 2 ? launch_slot_gram_e<3, 2>(c, a, smem, grid, s) : launch_slot_gram_e<3, 1>(c, a, smem, grid, s);
-    case 4: return tpw == 2 ? launch_slot_gram_e<4, 2>(c, a, smem, grid, s) : launch_slot_gram_e<4, 1>(c, a, smem, grid, s);
-    case 6: return launch_slot_gram_e<6, 1>(c, a, smem, grid, s);
-    default: return launch_slot_gram_e<8, 1>(c, a, smem, grid, s);
+    case 2: return launch_slot_gram_e<2, 1>(c, a, smem, grid, s);
+    default: return launch_slot_gram_e<4, 1>(c, a, smem, grid, s);
   }
 }
 

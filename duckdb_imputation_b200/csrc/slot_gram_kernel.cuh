@@ -11,10 +11,12 @@
 //      positions; every slot's segment starts at a multiple of 4 rows and is padded with zero rows;
 //   2. the tile is written to shared memory COLUMN-major in sorted order (plus a column of ones: lin_i is
 //      the product x_i * 1), so 4 consecutive rows of a column and slot are one 16-byte word;
-//   3. warp task (slot, part, split) walks its share of the slot's 4-row groups; a lane owns E output
-//      entries and does, per entry and 4 rows, two LDS.128 and four FFMA into two registers.  The task ->
-//      warp assignment is static (up to TPW tasks per warp), so the accumulators persist across tiles and are folded into the fp64 state
-//      every `fold_tiles` tiles only (bounds every fp32 run); N is the exact segment size.
+//   3. warp task (slot, part, split) walks its share of the slot's 4-row groups; a lane owns E 2x2 BLOCKS of the
+//      upper triangle over the columns [x_0..x_{n-1}, 1] -- (i0,i1) x (j0,j1) -- and does, per block and 4 rows,
+//      four LDS.128 and sixteen FFMA (half the operand reads per FFMA of one-entry-per-lane; the shared-memory
+//      pipe is what bounds this kernel).  The task -> warp assignment is static (up to TPW tasks per warp), so
+//      the accumulators persist across tiles and are folded into the fp64 state every `fold_tiles` tiles only
+//      (bounds every fp32 run); N is the exact segment size.
 // Rows with slot < 0 are filtered out (WHERE / MICE NULL filters); slot >= n_groups is an error.
 #pragma once
 #include <cstdint>
@@ -44,68 +46,89 @@ struct SlotGramArgs {
   int *err;
 };
 
-__host__ __device__ inline int slot_entries(int n, int kind) { return n + (kind == 0 ? n * (n + 1) / 2 : n); }
+// Work items of a slot: 2x2 blocks over the block-columns of [x_0..x_{n-1}, 1, (0)], the whole upper triangle (triple
+// ring); or one item per column (NB ring: only sum x and sum x^2 of every column)
+__host__ __device__ inline int slot_block_cols(int n) { return (n + 2) / 2; }
+__host__ __device__ inline int slot_blocks(int n, int kind) {
+  const int nbk = slot_block_cols(n);
+  return kind == 0 ? nbk * (nbk + 1) / 2 : n;
+}
 // column pitch in floats: the tile, the padding of every segment to 4 rows, and 4 more so that pitch % 32 == 4
 __host__ __device__ inline int slot_pitch(int n_groups, int steps) {
   const int need = steps * kSlotThreads + 4 * n_groups;
   return (need + 31) / 32 * 32 + 4;
 }
 __host__ __device__ inline size_t slot_smem_bytes(int n, int n_groups, int steps) {
-  return (size_t)(n + 1) * slot_pitch(n_groups, steps) * 4 + (size_t)n_groups * steps * kSlotWarps * 4 + 256;
+  return (size_t)(n + 2) * slot_pitch(n_groups, steps) * 4 + (size_t)n_groups * steps * kSlotWarps * 4 + 256;
 }
 
 template <int E, int TPW>
-__global__ void __launch_bounds__(kSlotThreads, E * TPW > 6 || E > 3 ? 2 : 4) slot_gram_kernel(const __grid_constant__ SlotGramArgs a) {
+__global__ void __launch_bounds__(kSlotThreads, E > 1 ? 2 : 4) slot_gram_kernel(const __grid_constant__ SlotGramArgs a) {
   extern __shared__ __align__(16) float slot_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = a.n, G = a.n_groups, U = a.steps, P = slot_pitch(G, U);
-  float *xs = slot_smem;                                            // [n + 1][P], column n = ones
-  unsigned *wc = reinterpret_cast<unsigned *>(xs + (size_t)(n + 1) * P);  // [G][U][warps] counts -> positions
+  float *xs = slot_smem;                                            // [n + 2][P], column n = ones, column n + 1 = zeros
+  unsigned *wc = reinterpret_cast<unsigned *>(xs + (size_t)(n + 2) * P);  // [G][U][warps] counts -> positions
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned raw_off[kSlotMaxGroups + 1];  // first sorted position of the slot before padding
   __shared__ unsigned seg_start[kSlotMaxGroups], seg_rows[kSlotMaxGroups], seg_size[kSlotMaxGroups];
   const int ES = G * U * kSlotWarps;  // scan entries, slot-major
 
   // this warp's tasks (task t = warp + k * warps, k < TPW; task -> (slot, part, split), split fastest); the
-  // operand columns of this lane's entries, packed ia | ib << 8 (column n is the constant 1; -1 = no entry)
+  // block columns of this lane's blocks, packed bi | bj << 8 (-1 = no block)
   const int per_slot = a.parts * a.splits, n_tasks = G * per_slot;
-  const int V = slot_entries(n, a.kind);
+  const int nbk = slot_block_cols(n), NB = slot_blocks(n, a.kind);
   int ops[TPW][E];
-  float acc[TPW][E][2];
+  float acc[TPW][E][4][2];  // [di * 2 + dj][half of the 4-row group]
 #pragma unroll
   for (int k = 0; k < TPW; k++) {
     const int t = warp + k * kSlotWarps, tpart = (t % per_slot) / a.splits;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-      acc[k][e][0] = acc[k][e][1] = 0.f;
-      const int v = (tpart * E + e) * 32 + lane;
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[k][e][v][0] = acc[k][e][v][1] = 0.f;
+      const int b = (tpart * E + e) * 32 + lane;
       ops[k][e] = -1;
-      if (t >= n_tasks || v >= V) continue;
-      if (v < n) {
-        ops[k][e] = v | (n << 8);
-      } else if (a.kind == 0) {
-        int p = v - n, i = 0;
-        while (p >= n - i) {
-          p -= n - i;
-          i++;
+      if (t >= n_tasks || b >= NB) continue;
+      if (a.kind == 0) {
+        int p = b, bi = 0;
+        while (p >= nbk - bi) {
+          p -= nbk - bi;
+          bi++;
         }
-        ops[k][e] = i | ((i + p) << 8);
+        ops[k][e] = bi | ((bi + p) << 8);
       } else {
-        ops[k][e] = (v - n) | ((v - n) << 8);
+        ops[k][e] = b;  // NB ring: the column
       }
     }
   }
+  // zero column n + 1 once: it pads an odd number of columns to whole blocks and is never written again
+  for (int i = tid; i < P; i += kSlotThreads) xs[(size_t)(n + 1) * P + i] = 0.f;
   auto fold = [&]() {
 #pragma unroll
     for (int k = 0; k < TPW; k++) {
-      const int t = warp + k * kSlotWarps, tg = t / per_slot, tpart = (t % per_slot) / a.splits;
+      const int t = warp + k * kSlotWarps, tg = t / per_slot;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const float sum = acc[k][e][0] + acc[k][e][1];
-        if (ops[k][e] < 0 || sum == 0.f) continue;
-        const int v = (tpart * E + e) * 32 + lane;
-        atomicAdd(a.f64 + tg * a.F + v, (double)sum);  // the f64 state starts with [lin n | quad nq]
-        acc[k][e][0] = acc[k][e][1] = 0.f;
+        if (ops[k][e] < 0) continue;
+        double *f = a.f64 + tg * a.F;  // the f64 state starts with [lin n | quad nq]
+        if (a.kind != 0) {  // NB ring: [0] = sum x^2, [1] = sum x of column ops
+          const float q2 = acc[k][e][0][0] + acc[k][e][0][1], l1 = acc[k][e][1][0] + acc[k][e][1][1];
+          if (q2 != 0.f) atomicAdd(f + n + ops[k][e], (double)q2);
+          if (l1 != 0.f) atomicAdd(f + ops[k][e], (double)l1);
+          acc[k][e][0][0] = acc[k][e][0][1] = acc[k][e][1][0] = acc[k][e][1][1] = 0.f;
+          continue;
+        }
+        const int bi = ops[k][e] & 255, bj = ops[k][e] >> 8;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const float sum = acc[k][e][v][0] + acc[k][e][v][1];
+          acc[k][e][v][0] = acc[k][e][v][1] = 0.f;
+          const int i = 2 * bi + (v >> 1), j = 2 * bj + (v & 1);
+          if (sum == 0.f || i > j || j > n || i >= n) continue;  // below the diagonal, padding, or the count (1 x 1)
+          if (j == n) atomicAdd(f + i, (double)sum);  // x_i * 1
+          else atomicAdd(f + n + ((long long)i * n - (long long)i * (i + 1) / 2 + j), (double)sum);
+        }
       }
     }
   };
@@ -222,20 +245,40 @@ __global__ void __launch_bounds__(kSlotThreads, E * TPW > 6 || E > 3 ? 2 : 4) sl
       const unsigned groups = seg_rows[tg] / 4;
       const float4 *base = reinterpret_cast<const float4 *>(xs + seg_start[tg]);
       const int P4 = P / 4;
-      const float4 *xa[E], *xb[E];  // operand columns of the entries, at the first row of the segment
+      const float4 *xi[E], *xj[E];  // first column of the block's column pairs, at the first row of the segment
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const int o = ops[k][e] < 0 ? (n | (n << 8)) : ops[k][e];  // no entry: the ones column (result never folded)
-        xa[e] = base + (size_t)(o & 255) * P4;
-        xb[e] = base + (size_t)(o >> 8) * P4;
+        const int o = ops[k][e] < 0 ? 0 : ops[k][e];  // no block: block (0,0), never folded
+        xi[e] = base + (size_t)(a.kind == 0 ? 2 * (o & 255) : o) * P4;
+        xj[e] = base + (size_t)(2 * (o >> 8)) * P4;
+      }
+      if (a.kind != 0) {  // NB ring: one load per column and 4 rows
+#pragma unroll 2
+        for (unsigned q = tsplit; q < groups; q += a.splits) {
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            const float4 x = xi[e][q];
+            acc[k][e][0][0] = fmaf(x.x, x.x, fmaf(x.y, x.y, acc[k][e][0][0]));
+            acc[k][e][0][1] = fmaf(x.z, x.z, fmaf(x.w, x.w, acc[k][e][0][1]));
+            acc[k][e][1][0] += x.x + x.y;
+            acc[k][e][1][1] += x.z + x.w;
+          }
+        }
+        continue;
       }
 #pragma unroll 2
       for (unsigned q = tsplit; q < groups; q += a.splits) {
 #pragma unroll
         for (int e = 0; e < E; e++) {
-          const float4 x = xa[e][q], y = xb[e][q];
-          acc[k][e][0] = fmaf(x.x, y.x, fmaf(x.y, y.y, acc[k][e][0]));
-          acc[k][e][1] = fmaf(x.z, y.z, fmaf(x.w, y.w, acc[k][e][1]));
+          const float4 i0 = xi[e][q], i1 = xi[e][P4 + q], j0 = xj[e][q], j1 = xj[e][P4 + q];
+          acc[k][e][0][0] = fmaf(i0.x, j0.x, fmaf(i0.y, j0.y, acc[k][e][0][0]));
+          acc[k][e][0][1] = fmaf(i0.z, j0.z, fmaf(i0.w, j0.w, acc[k][e][0][1]));
+          acc[k][e][1][0] = fmaf(i0.x, j1.x, fmaf(i0.y, j1.y, acc[k][e][1][0]));
+          acc[k][e][1][1] = fmaf(i0.z, j1.z, fmaf(i0.w, j1.w, acc[k][e][1][1]));
+          acc[k][e][2][0] = fmaf(i1.x, j0.x, fmaf(i1.y, j0.y, acc[k][e][2][0]));
+          acc[k][e][2][1] = fmaf(i1.z, j0.z, fmaf(i1.w, j0.w, acc[k][e][2][1]));
+          acc[k][e][3][0] = fmaf(i1.x, j1.x, fmaf(i1.y, j1.y, acc[k][e][3][0]));
+          acc[k][e][3][1] = fmaf(i1.z, j1.z, fmaf(i1.w, j1.w, acc[k][e][3][1]));
         }
       }
     }
