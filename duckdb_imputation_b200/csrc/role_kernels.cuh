@@ -15,8 +15,10 @@
 //     rows of its chunks for them; roles x replicas CTAs cover the grid.  Cells are 32-bit, or 16-bit packed
 //     two per word when 32-bit cells would need too many roles (16-bit tables are folded at least every
 //     65 024 rows, so a cell cannot overflow);
-//   * every thread takes 4 consecutive rows per step, each key column as one 128-bit load: the loop over the
-//     tables is data dependent, and only wide loads keep enough bytes in flight to hide the L2 / HBM latency;
+//   * a chunk is scanned once per table of the role, with the table's descriptor in registers (a loop over the
+//     tables inside the row loop is instruction bound); every thread takes 4 consecutive rows per step, each key
+//     column as one 128-bit load (only wide loads keep enough bytes in flight to hide the L2 / HBM latency), and
+//     the increments are predicated red.shared, not branches around atomics;
 //   * the per-key payloads [count, x_0..x_{n-1}] are normally done by bucket_sum_kernel (no float atomics).
 //     When that kernel does not apply (sum of domains > 4096) they go out from here as 128-bit vector
 //     reductions into per-CTA fp32 slabs in L2, every 4096-row tile by ONE role (rotating), all columns;
@@ -87,8 +89,55 @@ __device__ __forceinline__ T4 load_rows4(const T *col, unsigned long long r, uns
   return v;
 }
 
-// One step of a thread: 4 consecutive rows [r, r+4) against the pair tables of the CTA's role (and, when
-// `sums_mine`, their per-key payloads).  TAIL: the rows may run past `hi`.
+// Pair counts of ONE table over the rows [lo, hi) of a chunk: the table's descriptor lives in registers for the
+// whole pass (a loop over the tables inside the row loop re-reads it from the constant bank per row step and is
+// instruction bound).  4 consecutive rows per thread and step, keys as 128-bit loads, predicated red.shared.
+template <int BITS, bool TAIL>
+__device__ __forceinline__ unsigned role_table_pass(const RoleArgs &a, const RoleTable &d, unsigned smem_base,
+                                                    unsigned long long lo, unsigned long long hi) {
+  const int *ck = a.cols.cat[d.k], *cl = a.cols.cat[d.l], *grp = a.cols.group;
+  const int lo_k = a.lo[d.k], lo_l = a.lo[d.l], G = a.n_groups;
+  const unsigned dom_k = (unsigned)a.dom[d.k], dom_l = (unsigned)d.dom_l;
+  const unsigned tbl = smem_base + 4u * (unsigned)d.word_off, gcells = (unsigned)d.gwords * (BITS == 32 ? 1u : 2u);
+  unsigned bad = 0;
+  for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+    unsigned on = 1u | (!TAIL || r + 1 < hi ? 2u : 0u) | (!TAIL || r + 2 < hi ? 4u : 0u) | (!TAIL || r + 3 < hi ? 8u : 0u);
+    int4 kv, lv, gv = make_int4(0, 0, 0, 0);
+    if constexpr (TAIL) {
+      kv = load_rows4<int4>(ck, r, hi);
+      lv = load_rows4<int4>(cl, r, hi);
+      if (grp) gv = load_rows4<int4>(grp, r, hi);
+    } else {
+      kv = *reinterpret_cast<const int4 *>(ck + r);
+      lv = *reinterpret_cast<const int4 *>(cl + r);
+      if (grp) gv = *reinterpret_cast<const int4 *>(grp + r);
+    }
+    const int g[4] = {gv.x, gv.y, gv.z, gv.w};
+    const unsigned sk[4] = {(unsigned)(kv.x - lo_k), (unsigned)(kv.y - lo_k), (unsigned)(kv.z - lo_k), (unsigned)(kv.w - lo_k)};
+    const unsigned sl[4] = {(unsigned)(lv.x - lo_l), (unsigned)(lv.y - lo_l), (unsigned)(lv.z - lo_l), (unsigned)(lv.w - lo_l)};
+    unsigned in = 0, hit = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      in |= ((unsigned)g[i] < (unsigned)G ? 1u : 0u) << i;  // slot < 0: filtered row (>= G is reported by the payload pass / bucket_sum_kernel)
+      hit |= (sk[i] < dom_k && sl[i] < dom_l ? 1u : 0u) << i;
+    }
+    on &= in;
+    bad |= on & ~hit;
+    hit &= on;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      unsigned cell = sk[i] * dom_l + sl[i];
+      if (G > 1) cell += (unsigned)g[i] * gcells;
+      const unsigned addr = tbl + (BITS == 32 ? 4u * cell : 4u * (cell >> 1));
+      const unsigned inc = BITS == 32 ? 1u : 1u << ((cell & 1u) * 16);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(inc), "r"(hit & (1u << i)) : "memory");
+    }
+  }
+  return bad;
+}
+
+// Payload step of a thread (only when bucket_sum_kernel does not apply): the per-key payloads of 4 consecutive rows
+// [r, r+4) when this tile is this role's; also reports GROUP BY slots >= n_groups.  TAIL: the rows may run past `hi`.
 template <int N, int BITS, bool TAIL>
 __device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, unsigned *role_smem, float *slab,
                                           unsigned long long r, unsigned long long hi, bool sums_mine) {
@@ -112,46 +161,6 @@ __device__ __forceinline__ void role_step(const RoleArgs &a, int role, int nt, u
     }
     if (on & over) atomicExch(a.err, 2);
     on &= in;
-  }
-  // pair counts of this role: shared-memory atomics.  Tables come in (k,l) order: the slots of the first
-  // column (and whether the row counts at all) are refreshed only when k changes (a CTA-uniform branch).
-  // The reductions are predicated, not branched around (red.shared has no result to wait for).
-  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(role_smem);
-  int prev_k = -1;
-  unsigned sk[4] = {0, 0, 0, 0};
-  unsigned ok = 0;
-  for (int t = 0; t < ((a.skip & 1) ? 0 : nt); t++) {
-    const RoleTable &d = a.plan.tbl[role][t];
-    if (d.k != prev_k) {
-      prev_k = d.k;
-      const int4 v = rows4(a.cols.cat[d.k]);
-      const int lo_k = a.lo[d.k];
-      const unsigned dom_k = (unsigned)a.dom[d.k];
-      sk[0] = (unsigned)(v.x - lo_k), sk[1] = (unsigned)(v.y - lo_k), sk[2] = (unsigned)(v.z - lo_k), sk[3] = (unsigned)(v.w - lo_k);
-      ok = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) ok |= (sk[i] < dom_k ? 1u : 0u) << i;
-      bad |= on & ~ok;
-      ok &= on;
-    }
-    const int4 v = rows4(a.cols.cat[d.l]);
-    const int lo_l = a.lo[d.l];
-    const unsigned sl[4] = {(unsigned)(v.x - lo_l), (unsigned)(v.y - lo_l), (unsigned)(v.z - lo_l), (unsigned)(v.w - lo_l)};
-    const unsigned dom_l = (unsigned)d.dom_l;
-    const unsigned tbl = smem_base + 4u * (unsigned)d.word_off;
-    unsigned hit = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) hit |= (sl[i] < dom_l ? 1u : 0u) << i;
-    bad |= ok & ~hit;
-    hit &= ok;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      unsigned cell = sk[i] * dom_l + sl[i];
-      if (a.n_groups > 1) cell += (unsigned)gv[i] * (unsigned)d.gwords * (BITS == 32 ? 1u : 2u);
-      const unsigned addr = tbl + (BITS == 32 ? 4u * cell : 4u * (cell >> 1));
-      const unsigned inc = BITS == 32 ? 1u : 1u << ((cell & 1u) * 16);
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(inc), "r"(hit & (1u << i)) : "memory");
-    }
   }
   // per-key payload [1, x_0..x_{N-1}] of all columns when this tile is this role's: L2 vector reductions,
   // one quad of the payload at a time (4 rows x 4 values in registers)
@@ -210,18 +219,28 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_scan_kernel(const __grid
     // columns: the reductions of a CTA then spread over all keys of all columns, which matters because
     // L2 serialises reductions to one address), rotating over the roles tile by tile.
     int tile = (int)(ch % n_roles);
-    // every thread takes 4 consecutive rows per step: keys and values arrive as 128-bit loads, which is
-    // what hides the L2 / HBM latency (the loop over tables is data dependent and cannot be unrolled)
-    // the last chunk of a table whose row count is not a multiple of 4 takes the variant with tail checks
-    if ((hi - lo) % 4 == 0) {
-      for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
-        role_step<N, BITS, false>(a, role, nt, role_smem, slab, r, hi, tile == role);
-        tile = tile + 1 == n_roles ? 0 : tile + 1;
+    // the last chunk of a table whose row count is not a multiple of 4 takes the variants with tail checks
+    const bool tail = (hi - lo) % 4 != 0;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(role_smem);
+    if (!(a.skip & 1)) {
+      unsigned bad = 0;
+      for (int t = 0; t < nt; t++) {
+        const RoleTable d = a.plan.tbl[role][t];
+        bad |= tail ? role_table_pass<BITS, true>(a, d, smem_base, lo, hi) : role_table_pass<BITS, false>(a, d, smem_base, lo, hi);
       }
-    } else {
-      for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
-        role_step<N, BITS, true>(a, role, nt, role_smem, slab, r, hi, tile == role);
-        tile = tile + 1 == n_roles ? 0 : tile + 1;
+      if (bad) atomicExch(a.err, 1);  // a key outside the declared domain: the scan reports CFB_ERR_DOMAIN
+    }
+    if (!(a.skip & 2)) {  // payloads, when bucket_sum_kernel does not do them
+      if (!tail) {
+        for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+          role_step<N, BITS, false>(a, role, nt, role_smem, slab, r, hi, tile == role);
+          tile = tile + 1 == n_roles ? 0 : tile + 1;
+        }
+      } else {
+        for (unsigned long long r = lo + 4ull * threadIdx.x; r < hi; r += 4ull * kRoleThreads) {
+          role_step<N, BITS, true>(a, role, nt, role_smem, slab, r, hi, tile == role);
+          tile = tile + 1 == n_roles ? 0 : tile + 1;
+        }
       }
     }
     __threadfence();
