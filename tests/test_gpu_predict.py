@@ -98,3 +98,27 @@ def test_noise_and_bad_parameter_lists_are_query_errors():
         replay.glue().predict("linreg_predict", p[:2], [False, False], x, [])
     with pytest.raises(replay.ReplayError, match="categorical"):
         replay.glue().predict("linreg_predict", p, [False, False], x, [np.ones(10, np.int32)])
+
+
+def test_less_common_predict_paths():
+    """Unaligned device columns (scalar path of the score kernel), score_0 of a multi-output model, argmax of a
+    single-output model (always index 0)."""
+    rng = np.random.default_rng(77)
+    rows, n = 50_003, 5
+    keys, w_num, w_cat, bias = _random_model(rng, n, [9], 3)
+    num, cat = _rows(rng, rows + 1, n, keys)
+    d_num = [torch.from_numpy(c).cuda()[1:] for c in num]  # 4-byte aligned only
+    d_cat = [torch.from_numpy(c).cuda()[1:] for c in cat]
+    one = predict.LinearModel(bias[:1], w_num[:1], keys, w_cat[0][:1])
+    out = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    predict.predict_device(one, d_num, d_cat, rows, predict.SCORE, out)
+    params = oracle.linreg_params(bias[0], w_num[0], keys, [w_cat[0][0]])
+    ref = oracle.linreg_predict(params, False, [c[1:] for c in num], [c[1:] for c in cat])
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    idx = torch.full((rows,), 7, dtype=torch.int32, device="cuda")
+    predict.predict_device(one, d_num, d_cat, rows, predict.ARGMAX, idx)
+    assert int(idx.abs().sum().item()) == 0
+    multi = predict.LinearModel(bias, w_num, keys, w_cat[0])
+    predict.predict_device(multi, d_num, d_cat, rows, predict.SCORE, out)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)  # score of output 0
+    torch.cuda.synchronize()
