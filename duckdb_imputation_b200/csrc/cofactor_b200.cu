@@ -2252,6 +2252,101 @@ int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *ou
   return CFB_OK;
 }
 
+int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_result *out) {
+  if (!a || !b || !out) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (sign != 1 && sign != -1) return fail(CFB_ERR_INVALID, "sign must be +1 or -1");
+  if (a->kind != b->kind || a->n_num != b->n_num || a->n_cat != b->n_cat || a->n_quad != b->n_quad)
+    return fail(CFB_ERR_INVALID, "combine: the two results have different shapes");
+  const bool nb = a->kind == CFB_NB;
+  const int n = a->n_num, m = a->n_cat;
+  const double sg = (double)sign;
+  memset(out, 0, sizeof(*out));
+  auto dupv = [](const auto &v) {
+    using T = typename std::decay<decltype(v)>::type::value_type;
+    T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+    if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+  };
+  out->kind = a->kind;
+  out->n_num = n;
+  out->n_cat = m;
+  out->N = a->N + sign * b->N;
+  out->n_quad = a->n_quad;
+  std::vector<double> lin(n), quad(a->n_quad);
+  for (int i = 0; i < n; i++) lin[i] = a->lin[i] + sg * b->lin[i];
+  for (int64_t i = 0; i < a->n_quad; i++) quad[i] = a->quad[i] + sg * b->quad[i];
+  out->lin = dupv(lin);
+  out->quad = dupv(quad);
+  // categorical columns: merge the ascending key lists, drop keys whose count becomes 0
+  std::vector<int64_t> offs(m + 1, 0), counts;
+  std::vector<int32_t> keys;
+  std::vector<std::pair<int64_t, int64_t>> src;  // per output key: its position in a / in b (-1 = absent)
+  for (int c = 0; c < m; c++) {
+    int64_t x = a->cat_offsets[c], xe = a->cat_offsets[c + 1], y = b->cat_offsets[c], ye = b->cat_offsets[c + 1];
+    while (x < xe || y < ye) {
+      int64_t px = -1, py = -1;
+      int32_t key;
+      if (y >= ye || (x < xe && a->cat_keys[x] < b->cat_keys[y])) key = a->cat_keys[px = x++];
+      else if (x >= xe || b->cat_keys[y] < a->cat_keys[x]) key = b->cat_keys[py = y++];
+      else {
+        key = a->cat_keys[x];
+        px = x++;
+        py = y++;
+      }
+      const int64_t cnt = (px >= 0 ? a->cat_counts[px] : 0) + sign * (py >= 0 ? b->cat_counts[py] : 0);
+      if (cnt == 0) continue;
+      keys.push_back(key);
+      counts.push_back(cnt);
+      src.emplace_back(px, py);
+    }
+    offs[c + 1] = (int64_t)keys.size();
+  }
+  const int64_t tk = (int64_t)keys.size();
+  out->total_keys = tk;
+  out->cat_offsets = dupv(offs);
+  out->cat_keys = dupv(keys);
+  out->cat_counts = dupv(counts);
+  if (nb) {
+    out->n_pair_lists = 0;
+    out->pair_offsets = dupv(std::vector<int64_t>(1, 0));
+    return CFB_OK;
+  }
+  std::vector<double> nc((size_t)n * tk);
+  for (int i = 0; i < n; i++)
+    for (int64_t t = 0; t < tk; t++)
+      nc[(size_t)i * tk + t] = (src[t].first >= 0 ? a->numcat_sums[(size_t)i * a->total_keys + src[t].first] : 0.0) +
+                               sg * (src[t].second >= 0 ? b->numcat_sums[(size_t)i * b->total_keys + src[t].second] : 0.0);
+  out->numcat_sums = dupv(nc);
+  out->n_pair_lists = a->n_pair_lists;
+  std::vector<int64_t> po(a->n_pair_lists + 1, 0), pc;
+  std::vector<int32_t> k1, k2;
+  for (int64_t p = 0; p < a->n_pair_lists; p++) {
+    int64_t x = a->pair_offsets[p], xe = a->pair_offsets[p + 1], y = b->pair_offsets[p], ye = b->pair_offsets[p + 1];
+    auto less = [](int32_t a1, int32_t a2, int32_t b1, int32_t b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+    while (x < xe || y < ye) {
+      int64_t cnt;
+      int32_t u, v;
+      if (y >= ye || (x < xe && less(a->pair_key1[x], a->pair_key2[x], b->pair_key1[y], b->pair_key2[y]))) {
+        u = a->pair_key1[x], v = a->pair_key2[x], cnt = a->pair_counts[x++];
+      } else if (x >= xe || less(b->pair_key1[y], b->pair_key2[y], a->pair_key1[x], a->pair_key2[x])) {
+        u = b->pair_key1[y], v = b->pair_key2[y], cnt = sign * b->pair_counts[y++];
+      } else {
+        u = a->pair_key1[x], v = a->pair_key2[x], cnt = a->pair_counts[x++] + sign * b->pair_counts[y++];
+      }
+      if (cnt == 0) continue;
+      k1.push_back(u);
+      k2.push_back(v);
+      pc.push_back(cnt);
+    }
+    po[p + 1] = (int64_t)k1.size();
+  }
+  out->pair_offsets = dupv(po);
+  out->pair_key1 = dupv(k1);
+  out->pair_key2 = dupv(k2);
+  out->pair_counts = dupv(pc);
+  return CFB_OK;
+}
+
 void cfb_result_free(cfb_result *r) {
   if (!r) return;
   free(r->lin);

@@ -198,6 +198,15 @@ void cfb_result_free(cfb_result *res);
  * `out` is owned by the caller afterwards (cfb_result_free).                               */
 int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *out);
 
+/* Ring sum / difference of two results: out = a + sign * b, sign = +1 or -1 -- the arithmetic of the Value-level
+ * helpers sum_triple / subtract_triple of the MICE drivers (imputation/triple/sum.cpp, sub.cpp:71-219), used to
+ * maintain delta cofactors (all rows minus the rows where a column is NULL).  Shapes must match (kind, n_num,
+ * n_cat).  Categorical parts are merged by key (a missing key counts 0); keys whose count becomes 0 are dropped,
+ * as a finalize of the corresponding state would.  A host-side function on two small results; `out` is owned by
+ * the caller afterwards (cfb_result_free).  (The reference returns the non-empty operand unchanged when the
+ * other one has empty lists, even for `empty - b`; here the difference is the difference.)                  */
+int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_result *out);
+
 /* ------------------------------------------------- multi-GPU partial exchange */
 
 /* Dense partial layout for the NCCL reduce of SURVEY 8(e): the caller

@@ -63,3 +63,34 @@ def assert_struct_parity(got: dict, ref: dict, rtol: float = RTOL, abs_floor: fl
             assert [e["key"] for e in la] == [e["key"] for e in lb], f"{what}: quad_num_cat[{li}] keys"
             for a, b in zip(la, lb):
                 close(a["value"], b["value"], f"quad_num_cat[{li}][{a['key']}]")
+
+
+def to_result(a: dict):
+    """numpy form (struct_result.result_arrays) -> a ctypes cfb_result that borrows the arrays; returns (result, keepalive)."""
+    import ctypes as C
+
+    from duckdb_imputation_b200._native import Result
+    keep = []
+
+    def ptr(x, dt, ct):
+        arr = np.ascontiguousarray(x, dtype=dt)
+        keep.append(arr)
+        return arr.ctypes.data_as(C.POINTER(ct))
+
+    r = Result()
+    r.kind, r.n_num, r.n_cat, r.N = a["kind"], a["n"], a["m"], a["N"]
+    r.n_quad = len(a["quad"])
+    r.lin, r.quad = ptr(a["lin"], np.float64, C.c_double), ptr(a["quad"], np.float64, C.c_double)
+    r.total_keys = len(a["cat_keys"])
+    r.cat_offsets = ptr(a["cat_offsets"], np.int64, C.c_int64)
+    r.cat_keys = ptr(a["cat_keys"], np.int32, C.c_int32)
+    r.cat_counts = ptr(a["cat_counts"], np.int64, C.c_int64)
+    if a["kind"] == 0:
+        r.numcat_sums = ptr(a["numcat"].reshape(-1), np.float64, C.c_double)
+        r.n_pair_lists = len(a["pair_offsets"]) - 1
+        r.pair_offsets = ptr(a["pair_offsets"], np.int64, C.c_int64)
+        r.pair_key1, r.pair_key2 = ptr(a["pair_key1"], np.int32, C.c_int32), ptr(a["pair_key2"], np.int32, C.c_int32)
+        r.pair_counts = ptr(a["pair_counts"], np.int64, C.c_int64)
+    else:
+        r.pair_offsets = ptr(np.zeros(1), np.int64, C.c_int64)
+    return r, keep

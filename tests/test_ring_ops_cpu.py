@@ -1,0 +1,48 @@
+"""CPU suite: ring sum / difference of two results (cfb_result_combine, a host function of the C ABI) -- the
+arithmetic of the MICE drivers' Value-level sum_triple / subtract_triple (imputation/triple/sum.cpp, sub.cpp:71-219):
+sum(A) + sum(B) == sum(A u B) and sum(A u B) - sum(B) == sum(A), keys merged, zero-count keys dropped."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from duckdb_imputation_b200 import _native as nat
+from duckdb_imputation_b200.struct_result import result_arrays
+from oracle import oracle
+from tests.parity import assert_parity, to_result
+
+
+def _combine(a, b, sign):
+    ra, ka = to_result(a)
+    rb, kb = to_result(b)
+    out = nat.Result()
+    nat.check(nat.lib().cfb_result_combine(C.byref(ra), C.byref(rb), sign, C.byref(out)))
+    try:
+        return result_arrays(out)
+    finally:
+        nat.lib().cfb_result_free(C.byref(out))
+
+
+@pytest.mark.parametrize("kind", [oracle.TRIPLE, oracle.NB])
+@pytest.mark.parametrize("n,m", [(3, 2), (0, 3), (4, 0), (2, 1)])
+def test_sum_and_difference_of_results(kind, n, m):
+    rng = np.random.default_rng(10 * n + m + kind)
+    ra, rb = 700, 400
+    num = [rng.random(ra + rb).astype(np.float32) for _ in range(n)]
+    cat = [np.concatenate([rng.integers(0, 6, ra), rng.integers(3, 11, rb)]).astype(np.int32) for _ in range(m)]  # B has keys A lacks
+    A = oracle.aggregate_arrays(kind, [c[:ra] for c in num], [c[:ra] for c in cat])[0]
+    B = oracle.aggregate_arrays(kind, [c[ra:] for c in num], [c[ra:] for c in cat])[0]
+    W = oracle.aggregate_arrays(kind, num, cat)[0]
+    assert_parity(_combine(A, B, +1), W, what="A + B")
+    assert_parity(_combine(W, B, -1), A, what="(A u B) - B")  # the keys only B has disappear again
+    assert_parity(_combine(W, A, -1), B, what="(A u B) - A")
+
+
+def test_combine_rejects_mismatched_shapes_and_signs():
+    rng = np.random.default_rng(1)
+    A = oracle.aggregate_arrays(oracle.TRIPLE, [rng.random(10).astype(np.float32)], [])[0]
+    B = oracle.aggregate_arrays(oracle.TRIPLE, [rng.random(10).astype(np.float32)] * 2, [])[0]
+    with pytest.raises(nat.CofactorError, match="shapes"):
+        _combine(A, B, 1)
+    with pytest.raises(nat.CofactorError, match="sign"):
+        _combine(A, A, 2)
