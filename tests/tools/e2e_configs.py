@@ -12,7 +12,8 @@ rng = np.random.default_rng(0)
 CONFIGS = [("C3 sum_to_triple_10_10", "sum_to_triple_10_10", 10, 10, None),
            ("C4a sum_to_nb_agg_12_4 GROUP BY 10", "sum_to_nb_agg_12_4", 12, 4, 10),
            ("C4b sum_to_triple_12_0 GROUP BY 10", "sum_to_triple_12_0", 12, 0, 10),
-           ("C2 sum_to_triple_19_0 (reference grid)", "sum_to_triple_19_0", 19, 0, None)]
+           ("C2 sum_to_triple_19_0 (reference grid)", "sum_to_triple_19_0", 19, 0, None),
+           ("C5 sum_to_triple_19_10 (MICE scan shape, reference grid)", "sum_to_triple_19_10", 19, 10, None)]
 g, r = replay.glue(), (ref_replay.ref() if ref_replay.available() else None)
 for name, fn, n, m, G in CONFIGS:
     num = [rng.random(rows, dtype=np.float32) for _ in range(n)]
