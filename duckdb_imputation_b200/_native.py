@@ -51,6 +51,7 @@ SIGNATURES = {
     "cfb_ctx_set_cat_domain": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cfb_ctx_append": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t]),
     "cfb_ctx_append_triples": (C.c_int, [_P, C.c_size_t] + [_P] * 13),
+    "cfb_ctx_append_triples_slot": (C.c_int, [_P, C.c_int, C.c_size_t] + [_P] * 13),
     "cfb_triple_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "cfb_ctx_sync": (C.c_int, [_P]),
     "cfb_ctx_combine": (C.c_int, [_P, _P]),
@@ -66,6 +67,11 @@ SIGNATURES = {
     "cfb_ctx_partial_sizes": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cfb_ctx_export_partial": (C.c_int, [_P, _P, _P, _P]),
     "cfb_ctx_import_partial": (C.c_int, [_P, _P, _P, _P]),
+    "cfb_ctx_allreduce": (C.c_int, [_P, _P, _P]),
+    "cfb_nccl_unique_id": (C.c_int, [_P]),
+    "cfb_nccl_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "cfb_nccl_comm_destroy": (C.c_int, [_P]),
+    "cfb_nccl_agree_domain": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _P]),
     "cfb_cat_minmax_device": (C.c_int, [C.c_int, C.POINTER(_P), C.c_int, C.c_size_t,
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "cfb_gen_uniform_f32": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64, _P]),
@@ -73,6 +79,8 @@ SIGNATURES = {
     "cfb_kernel_launches": (C.c_uint64, []),
     "cfb_set_timing": (C.c_int, [C.c_int]),
     "cfb_last_scan_ms": (C.c_double, [_P]),
+    "cfb_stage_isa": (C.c_char_p, []),
+    "cfb_host_copy_ceiling": (C.c_double, [C.c_size_t, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

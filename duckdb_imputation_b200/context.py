@@ -118,6 +118,11 @@ class CofactorContext:
         return float(nat.lib().cfb_last_scan_ms(self._h))
 
     # -- multi-GPU partial exchange
+    def allreduce(self, nccl_comm: int, stream: int = 0):
+        """SUM-all-reduce the dense state in place over an ncclComm_t (cfb_ctx_allreduce): the exchange step of the
+        path, inside the library.  Stream-ordered on `stream` (0 = the context's stream, synchronous)."""
+        nat.check(nat.lib().cfb_ctx_allreduce(self._h, nccl_comm, stream or None))
+
     def partial_sizes(self):
         a, b = C.c_size_t(), C.c_size_t()
         nat.check(nat.lib().cfb_ctx_partial_sizes(self._h, C.byref(a), C.byref(b)))

@@ -24,7 +24,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <emmintrin.h>
+#include <nccl.h>
 
 #include "gram_launch.h"
 #include "group_kernel.cuh"
@@ -1225,34 +1227,19 @@ int flush_tile(cfb_ctx *c) {
   return CFB_OK;
 }
 
-// Contiguous copy into the pinned staging tile with non-temporal stores: the tile is written
-// once and next read by the DMA engine, so bypassing the cache saves the read-for-ownership
-// traffic of a plain memcpy (the host-fed path is host-memory-bandwidth bound).
-inline void copy_stream(void *dst, const void *src, size_t bytes) {
-  char *d = (char *)dst;
-  const char *s = (const char *)src;
-  if (bytes < 256 || ((uintptr_t)d & 15)) {
-    memcpy(d, s, bytes);
-    return;
-  }
-  size_t i = 0;
-  for (; i + 64 <= bytes; i += 64) {
-    const __m128i a = _mm_loadu_si128((const __m128i *)(s + i)), b = _mm_loadu_si128((const __m128i *)(s + i + 16));
-    const __m128i c = _mm_loadu_si128((const __m128i *)(s + i + 32)), e = _mm_loadu_si128((const __m128i *)(s + i + 48));
-    _mm_stream_si128((__m128i *)(d + i), a);
-    _mm_stream_si128((__m128i *)(d + i + 16), b);
-    _mm_stream_si128((__m128i *)(d + i + 32), c);
-    _mm_stream_si128((__m128i *)(d + i + 48), e);
-  }
-  if (i < bytes) memcpy(d + i, s + i, bytes - i);
-}
+// Host -> staging-tile copies live in stage_copy.cpp (host compiler: AVX-512 / AVX2 / SSE2 non-temporal stores).
+}  // namespace
+extern "C" void cfb_stage_copy(void *dst, const void *src, size_t bytes);
+extern "C" void cfb_stage_gather32(void *dst, const void *src, const uint32_t *sel, size_t count);
+namespace {
 
 template <class T>
 inline void gather(T *dst, const T *src, const uint32_t *sel, size_t first, size_t cnt) {
+  static_assert(sizeof(T) == 4, "staged columns are 4-byte values");
   if (!sel)
-    copy_stream(dst, src + first, cnt * sizeof(T));
+    cfb_stage_copy(dst, src + first, cnt * sizeof(T));
   else
-    for (size_t i = 0; i < cnt; i++) dst[i] = src[sel[first + i]];
+    cfb_stage_gather32(dst, src, sel + first, cnt);
 }
 
 }  // namespace
@@ -1630,13 +1617,22 @@ int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *con
       gather((float *)(base + (size_t)k * tr * 4) + c->fill, num_cols[k], num_sel ? num_sel[k] : nullptr, done, take);
     for (int k = 0; k < c->m; k++) {
       int32_t *dst = (int32_t *)(base + (size_t)(c->n + k) * tr * 4) + c->fill;
-      gather(dst, cat_cols[k], cat_sel ? cat_sel[k] : nullptr, done, take);
+      const uint32_t *ks = cat_sel ? cat_sel[k] : nullptr;
+      gather(dst, cat_cols[k], ks, done, take);
       if (!c->user_domain) {
+        // key range of the tile, read from the source (in cache) -- not from the tile, which was written around the cache
         int lo = c->st_lo[k], hi = c->st_hi[k];
-        for (size_t i = 0; i < take; i++) {
-          lo = std::min(lo, dst[i]);
-          hi = std::max(hi, dst[i]);
-        }
+        const int32_t *src = cat_cols[k];
+        if (!ks)
+          for (size_t i = 0; i < take; i++) {
+            lo = std::min(lo, src[done + i]);
+            hi = std::max(hi, src[done + i]);
+          }
+        else
+          for (size_t i = 0; i < take; i++) {
+            lo = std::min(lo, src[ks[done + i]]);
+            hi = std::max(hi, src[ks[done + i]]);
+          }
         c->st_lo[k] = lo;
         c->st_hi[k] = hi;
       }
@@ -1663,7 +1659,17 @@ int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const flo
                            const cfb_list_entry *num_cat_lists, const int32_t *nc_key, const float *nc_val,
                            const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
                            const float *cc_val) {
+  return cfb_ctx_append_triples_slot(c, 0, count, N, lin, quad, lin_cat_lists, lc_key, lc_val, num_cat_lists, nc_key, nc_val,
+                                     cat_cat_lists, cc_key1, cc_key2, cc_val);
+}
+
+int cfb_ctx_append_triples_slot(cfb_ctx *c, int slot, size_t count, const int32_t *N, const float *lin, const float *quad,
+                                const cfb_list_entry *lin_cat_lists, const int32_t *lc_key, const float *lc_val,
+                                const cfb_list_entry *num_cat_lists, const int32_t *nc_key, const float *nc_val,
+                                const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
+                                const float *cc_val) {
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (slot < 0 || slot >= c->G) return fail(CFB_ERR_INVALID, "slot %d out of range", slot);
   if (count == 0) return CFB_OK;
   const int n = c->n, m = c->m;
   const size_t nq = (size_t)c->lay.nq;
@@ -1765,19 +1771,22 @@ int cfb_ctx_append_triples(cfb_ctx *c, size_t count, const int32_t *N, const flo
   if (bL) CU(cudaMemcpyAsync(dL, lin, bL, cudaMemcpyHostToDevice, s));
   if (bQ) CU(cudaMemcpyAsync(dQ, quad, bQ, cudaMemcpyHostToDevice, s));
   if (bE) CU(cudaMemcpyAsync(dE, ent.data(), bE, cudaMemcpyHostToDevice, s));
-  cfb::lifted_count_kernel<<<1, 256, 0, s>>>((const int32_t *)dN, count, c->d_u64);
+  // the state of GROUP BY slot `slot` (ensure_domain above may have re-laid out the state: read the layout now)
+  double *sf64 = c->d_f64 + (long long)slot * c->lay.F;
+  unsigned long long *su64 = c->d_u64 + (long long)slot * c->lay.U;
+  cfb::lifted_count_kernel<<<1, 256, 0, s>>>((const int32_t *)dN, count, su64);
   g_launches++;
   if (n) {
-    cfb::lifted_colsum_kernel<<<std::min(n, 64), 256, 0, s>>>((const float *)dL, count, n, c->d_f64);
-    cfb::lifted_colsum_kernel<<<(int)std::min<size_t>(nq, 128), 256, 0, s>>>((const float *)dQ, count, (int)nq, c->d_f64 + n);
+    cfb::lifted_colsum_kernel<<<std::min(n, 64), 256, 0, s>>>((const float *)dL, count, n, sf64);
+    cfb::lifted_colsum_kernel<<<(int)std::min<size_t>(nq, 128), 256, 0, s>>>((const float *)dQ, count, (int)nq, sf64 + n);
     g_launches += 2;
   }
   if (bE) {
     const int blocks = (int)std::min<size_t>((ent.size() + 255) / 256, (size_t)dev_info(c->device).sms * 4);
     rc = hash_reserve(c, ent.size());
     if (rc) return rc;
-    cfb::lifted_scatter_kernel<<<blocks, 256, 0, s>>>((const cfb::LiftedEntry *)dE, ent.size(), c->d_lay, c->d_f64,
-                                                     c->d_u64, c->d_err, c->hash);
+    cfb::lifted_scatter_kernel<<<blocks, 256, 0, s>>>((const cfb::LiftedEntry *)dE, ent.size(), c->d_lay, sf64, su64, c->d_err,
+                                                     c->hash, slot);
     g_launches++;
   }
   CU(cudaGetLastError());
@@ -1833,6 +1842,52 @@ double cfb_last_scan_ms(cfb_ctx *c) {
   return (double)ms;
 }
 
+namespace {
+// dst[dst_slots[i]] += src[src_slots[i]] inside ONE context (two GROUP BY states of the same arena: DuckDB's
+// radix-partitioned hash aggregate can emit a group twice from one thread and combine the two).  A slot may
+// not be source and target in the same call: the adds run concurrently.
+int combine_within(cfb_ctx *c, size_t n_pairs, const int32_t *dst_slots, const int32_t *src_slots) {
+  if (!n_pairs) return fail(CFB_ERR_INVALID, "cannot combine a context with itself (name the slots)");
+  if (!dst_slots || !src_slots) return fail(CFB_ERR_INVALID, "slot arrays are NULL");
+  std::vector<int> gmap(c->G, -1);
+  std::vector<char> is_dst(c->G, 0);
+  for (size_t i = 0; i < n_pairs; i++) {
+    const int d = dst_slots[i], s = src_slots[i];
+    if (s < 0 || s >= c->G || d < 0 || d >= c->G) return fail(CFB_ERR_INVALID, "combine: slot out of range");
+    if (s == d) return fail(CFB_ERR_INVALID, "combine: a slot cannot be merged into itself");
+    if (gmap[s] != -1 || is_dst[d]) return fail(CFB_ERR_INVALID, "combine: a slot appears twice");
+    gmap[s] = d;
+    is_dst[d] = 1;
+  }
+  for (int g = 0; g < c->G; g++)
+    if (is_dst[g] && gmap[g] != -1) return fail(CFB_ERR_INVALID, "combine: a slot is both source and target");
+  int rc = cfb_ctx_sync(c);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  int *d_gmap = nullptr;
+  CU(cudaMalloc(&d_gmap, gmap.size() * sizeof(int)));
+  CU(cudaMemcpyAsync(d_gmap, gmap.data(), gmap.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  rc = launch_remap_add(c->d_lay, c->d_lay, c->lay, c->d_f64, c->d_u64, c->d_f64, c->d_u64, c->hash, c->d_err, c->stream,
+                        cfb::SlotTrans{}, d_gmap);
+  if (rc == CFB_OK && c->lay.pairs_hashed) {
+    // every pair of a source partition may be new to its target partition
+    unsigned long long exact = 0;
+    CU(cudaMemcpyAsync(&exact, c->hash.n_entries, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    rc = hash_reserve(c, exact);
+    if (rc == CFB_OK) {
+      cfb::pair_hash_drain_kernel<<<148 * 4, 256, 0, c->stream>>>(c->hash, c->d_lay, c->d_lay, c->d_u64, c->hash, c->d_err,
+                                                                 cfb::SlotTrans{}, d_gmap, c->G);
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) rc = fail(CFB_ERR_CUDA, "pair hash drain launch failed");
+    }
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_gmap);
+  return rc;
+}
+}  // namespace
+
 int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src) {
   if (dst && src && dst->G != src->G) return fail(CFB_ERR_INVALID, "combine: group counts differ (use cfb_ctx_combine_slots)");
   return cfb_ctx_combine_slots(dst, src, 0, nullptr, nullptr);
@@ -1842,7 +1897,7 @@ int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src_c, size_t n_pairs, co
                           const int32_t *src_slots) {
   cfb_ctx *src = const_cast<cfb_ctx *>(src_c);
   if (!dst || !src) return fail(CFB_ERR_INVALID, "ctx is NULL");
-  if (dst == src) return fail(CFB_ERR_INVALID, "cannot combine a context with itself");
+  if (dst == src) return combine_within(dst, n_pairs, dst_slots, src_slots);
   if (dst->kind != src->kind || dst->n != src->n || dst->m != src->m) return fail(CFB_ERR_INVALID, "combine: shapes differ");
   // slot map: dst slot of every src slot (-1 = not combined); identity when no pairs are given
   std::vector<int> gmap;
@@ -2460,6 +2515,168 @@ int cfb_gen_int32(int device, int32_t *d_out, size_t n, uint64_t seed, uint64_t 
   cfb::gen_int_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, n, seed, first, lo, range);
   g_launches++;
   CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ multi-GPU exchange (NCCL)
+// The library does not link NCCL: the functions are resolved from libnccl.so.2 at first use, so a host that
+// never reduces across GPUs needs no NCCL at all, and a host that already loaded one (PyTorch ships its own)
+// shares that copy.
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  std::string error;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+const NcclApi &nccl_api() {
+  std::call_once(g_nccl_once, [] {
+    NcclApi &a = g_nccl;
+    const char *names[] = {getenv("CFB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      if (!nm || !*nm) continue;
+      a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (!a.handle) {
+      a.error = std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+    auto sym = [&](const char *n) {
+      void *p = dlsym(a.handle, n);
+      if (!p && a.error.empty()) a.error = std::string("NCCL symbol missing: ") + n;
+      return p;
+    };
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.CommCount = (decltype(a.CommCount))sym("ncclCommCount");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+  });
+  return g_nccl;
+}
+
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    ncclResult_t r_ = (call);                                                                                 \
+    if (r_ != ncclSuccess) return fail(CFB_ERR_CUDA, "%s failed: %s", #call, nccl_api().GetErrorString(r_)); \
+  } while (0)
+
+int nccl_ready() {
+  const NcclApi &a = nccl_api();
+  if (!a.error.empty()) return fail(CFB_ERR_STATE, "%s", a.error.c_str());
+  return CFB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int cfb_nccl_unique_id(void *id128) {
+  if (!id128) return fail(CFB_ERR_INVALID, "id buffer is NULL");
+  int rc = nccl_ready();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == CFB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(nccl_api().GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return CFB_OK;
+}
+
+int cfb_nccl_comm_create(int device, int world, int rank, const void *id128, void **comm_out) {
+  if (!id128 || !comm_out) return fail(CFB_ERR_INVALID, "NULL argument");
+  *comm_out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(CFB_ERR_INVALID, "bad rank %d / world %d", rank, world);
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible");
+  int rc = nccl_ready();
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NC(nccl_api().CommInitRank(&comm, world, id, rank));
+  *comm_out = comm;
+  return CFB_OK;
+}
+
+int cfb_nccl_comm_destroy(void *comm) {
+  if (!comm) return CFB_OK;
+  int rc = nccl_ready();
+  if (rc) return rc;
+  NC(nccl_api().CommDestroy((ncclComm_t)comm));
+  return CFB_OK;
+}
+
+int cfb_nccl_agree_domain(void *comm, int device, int32_t *lo, int32_t *hi, int n_cat, void *stream) {
+  if (!comm || !lo || !hi || n_cat < 0 || n_cat > CFB_MAX_CAT) return fail(CFB_ERR_INVALID, "bad argument");
+  if (n_cat == 0) return CFB_OK;
+  int rc = nccl_ready();
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t *d = nullptr;
+  CU(cudaMalloc(&d, 2 * CFB_MAX_CAT * sizeof(int32_t)));
+  CU(cudaMemcpyAsync(d, lo, n_cat * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + CFB_MAX_CAT, hi, n_cat * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  const NcclApi &a = nccl_api();
+  ncclResult_t r = a.GroupStart();
+  if (r == ncclSuccess) r = a.AllReduce(d, d, n_cat, ncclInt32, ncclMin, (ncclComm_t)comm, s);
+  if (r == ncclSuccess) r = a.AllReduce(d + CFB_MAX_CAT, d + CFB_MAX_CAT, n_cat, ncclInt32, ncclMax, (ncclComm_t)comm, s);
+  const ncclResult_t r2 = a.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) {
+    cudaFree(d);
+    return fail(CFB_ERR_CUDA, "NCCL min/max all-reduce failed: %s", a.GetErrorString(r));
+  }
+  CU(cudaMemcpyAsync(lo, d, n_cat * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(hi, d + CFB_MAX_CAT, n_cat * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  cudaFree(d);
+  return CFB_OK;
+}
+
+int cfb_ctx_allreduce(cfb_ctx *c, void *comm, void *stream) {
+  if (!c || !comm) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (c->lay.pairs_hashed || any_dict(c))
+    return fail(CFB_ERR_DOMAIN, "sparse state (hashed pair counts / key dictionaries) has no dense partial: combine with cfb_ctx_combine");
+  if (c->m > 0 && !c->user_domain)
+    return fail(CFB_ERR_STATE, "all-reduce needs the same categorical domain on every rank: agree on it (cfb_nccl_agree_domain) and "
+                               "declare it with cfb_ctx_set_cat_domain before the scan");
+  int rc = nccl_ready();
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  rc = flush_tile(c);
+  if (rc) return rc;
+  c->touched = true;
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (stream) {
+    c->user_stream = s;  // finalize / sync wait for it
+    if (c->tile_rows) CU(cudaStreamSynchronize(c->stream));  // staged tiles ran on the context stream
+  }
+  // ONE fused collective, in place on the state: fp64 sums and u64 counts (exact, order-independent) inside one
+  // NCCL group -- no export / import copies, no host synchronisation between the scan and the reduce.
+  const NcclApi &a = nccl_api();
+  const size_t nf = (size_t)(c->lay.F * c->lay.n_groups), nu = (size_t)(c->lay.U * c->lay.n_groups);
+  ncclResult_t r = a.GroupStart();
+  if (r == ncclSuccess && nf) r = a.AllReduce(c->d_f64, c->d_f64, nf, ncclDouble, ncclSum, (ncclComm_t)comm, s);
+  if (r == ncclSuccess) r = a.AllReduce(c->d_u64, c->d_u64, nu, ncclUint64, ncclSum, (ncclComm_t)comm, s);
+  const ncclResult_t r2 = a.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) return fail(CFB_ERR_CUDA, "NCCL all-reduce of the partial triple failed: %s", a.GetErrorString(r));
+  if (!stream) CU(cudaStreamSynchronize(s));
   return CFB_OK;
 }
 

@@ -132,11 +132,17 @@ struct list_entry_t {
 // ------------------------------------------------------------------------- vectors
 enum class VectorType : uint8_t { FLAT_VECTOR, CONSTANT_VECTOR, DICTIONARY_VECTOR };
 
+// DuckDB 0.9.2 spelling: the index array is private (`sel_vector`) and read through data(); a null
+// array is the incremental selection (get_index(i) == i), which is what FLAT vectors report.
 struct SelectionVector {
-  SelectionVector() : sel(nullptr) {}
-  explicit SelectionVector(sel_t *s) : sel(s) {}
-  idx_t get_index(idx_t i) const { return sel ? sel[i] : i; }
-  sel_t *sel;
+  SelectionVector() : sel_vector(nullptr) {}
+  explicit SelectionVector(sel_t *s) : sel_vector(s) {}
+  idx_t get_index(idx_t i) const { return sel_vector ? sel_vector[i] : i; }
+  sel_t *data() { return sel_vector; }
+  const sel_t *data() const { return sel_vector; }
+
+ private:
+  sel_t *sel_vector;
 };
 
 struct ValidityMask {
@@ -203,6 +209,31 @@ class Vector {
         break;
     }
     f.sel = &f.owned_sel;
+  }
+
+  // Materialise a CONSTANT / DICTIONARY vector of fixed-width values as FLAT (DuckDB's Vector::Flatten); nested
+  // types keep their children (only the level's own data moves), which is all the callers here rely on.
+  void Flatten(idx_t count) {
+    if (vtype_ == VectorType::FLAT_VECTOR) return;
+    const idx_t w = type_.width();
+    if (w) {
+      auto nb = std::make_shared<VectorBuffer>();
+      nb->bytes.reset(new data_t[std::max<idx_t>(1, count * w)]());
+      for (idx_t i = 0; i < count; i++) {
+        const idx_t src = vtype_ == VectorType::CONSTANT_VECTOR ? 0 : dict_sel_.get_index(i);
+        memcpy(nb->bytes.get() + i * w, data_ + src * w, w);
+      }
+      buffer_ = nb;
+      data_ = nb->bytes.get();
+    } else if (type_.id() == LogicalTypeId::STRUCT) {
+      for (auto &c : static_cast<VectorStructBuffer &>(*aux_).children) {
+        if (vtype_ == VectorType::CONSTANT_VECTOR) c->SetVectorType(VectorType::CONSTANT_VECTOR);
+        else c->Slice(dict_sel_);
+        c->Flatten(count);
+      }
+    }
+    vtype_ = VectorType::FLAT_VECTOR;
+    dict_sel_ = SelectionVector();
   }
 
   void Resize(idx_t cur, idx_t want) {
@@ -401,6 +432,31 @@ class DatabaseInstance {
  public:
   std::map<string, AggregateFunction> aggregates;
   std::map<string, ScalarFunction> scalars;
+};
+
+// What a loadable extension's entry points touch: duckdb_<name>_init(DatabaseInstance&) wraps the instance in a
+// DuckDB object and calls LoadExtension<T>(), duckdb_<name>_version() returns DuckDB::LibraryVersion()
+// (duckdb_imputation_extension.cpp:269-279).
+#ifndef DUCKDB_EXTENSION_API
+#define DUCKDB_EXTENSION_API __attribute__((visibility("default")))
+#endif
+class DuckDB;
+class Extension {
+ public:
+  virtual ~Extension() = default;
+  virtual void Load(DuckDB &db) = 0;
+  virtual std::string Name() = 0;
+};
+class DuckDB {
+ public:
+  explicit DuckDB(DatabaseInstance &i) : instance(&i, [](DatabaseInstance *) {}) {}
+  template <class T>
+  void LoadExtension() {
+    T extension;
+    extension.Load(*this);
+  }
+  static const char *LibraryVersion() { return "v0.9.2"; }  // the DuckDB release the reference pins (README.md:35-42)
+  shared_ptr<DatabaseInstance> instance;
 };
 struct ExtensionUtil {
   static void RegisterFunction(DatabaseInstance &db, AggregateFunction f) {

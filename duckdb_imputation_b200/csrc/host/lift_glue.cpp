@@ -11,10 +11,12 @@
 //       + device scatter-add of the sparse entries); combine / finalize are the shared
 //       Triple::SumStateCombine / SumStateFinalize.
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../../include/cofactor_b200.h"
 #include "triple_glue.h"
+#include "triple_view.h"
 
 namespace Triple {
 
@@ -169,7 +171,9 @@ void Lift(bool nb, duckdb::DataChunk &args, duckdb::Vector &result) {
   }
 }
 
-// update of sum_triple / sum_nb_agg: route rows to states, hand each state its rows' children
+// update of sum_triple / sum_nb_agg: route rows to states, hand each state its rows' children.  The STRUCT
+// argument may be FLAT, CONSTANT or DICTIONARY at any nesting level (a join or a filter below the aggregate):
+// the reference flattens it first (sum.cpp:72 -> utils.cpp:3-18); TripleView reads it in place.
 void SumLifted(int kind, duckdb::Vector inputs[], idx_t input_count, duckdb::Vector &state_vector, idx_t count) {
   using namespace duckdb;
   if (input_count != 1) throw InvalidInputException("sum over lifted triples takes one STRUCT argument");
@@ -177,42 +181,25 @@ void SumLifted(int kind, duckdb::Vector inputs[], idx_t input_count, duckdb::Vec
   UnifiedVectorFormat sdata;
   state_vector.ToUnifiedFormat(count, sdata);
   auto states = (SumState **)sdata.data;
-  Vector &in = inputs[0];
-  if (in.GetType().id() != LogicalTypeId::STRUCT) throw InvalidInputException("expected a triple STRUCT");
-  if (in.GetVectorType() != VectorType::FLAT_VECTOR)
-    throw InvalidInputException("sum over lifted triples expects a flat STRUCT vector (flatten first, utils.cpp:3-18)");
-  auto &kids = StructVector::GetEntries(in);
   const bool nb = kind == CFB_NB;
-  if (kids.size() != (nb ? 4u : 6u)) throw InvalidInputException("triple STRUCT has the wrong number of fields");
-  auto N = FlatVector::GetData<int32_t>(*kids[0]);
-  auto lin_e = ListVector::GetData(*kids[1]);
-  auto quad_e = ListVector::GetData(*kids[2]);
-  auto lin_d = FlatVector::GetData<float>(ListVector::GetEntry(*kids[1]));
-  auto quad_d = FlatVector::GetData<float>(ListVector::GetEntry(*kids[2]));
-  auto lc_outer = ListVector::GetData(*kids[3]);
-  Vector &lc_in = ListVector::GetEntry(*kids[3]);
-  auto lc_inner = ListVector::GetData(lc_in);
-  auto &lc_kv = StructVector::GetEntries(ListVector::GetEntry(lc_in));
+  const TripleView in(inputs[0], count, nb);
   // shape from the first row (sum.cpp:96-106): n = |lin|, m = |lin_cat|
-  const idx_t n = lin_e[0].length, m = lc_outer[0].length;
+  const idx_t n = in.lin.Entry(in.Row(0)).length, m = in.lin_cat.Outer(in.Row(0)).length;
   const idx_t nq = nb ? n : n * (n + 1) / 2, npl = m * (m + 1) / 2;
-  list_entry_t *nc_outer = nullptr, *nc_inner = nullptr, *cc_outer = nullptr, *cc_inner = nullptr;
-  int32_t *nc_key = nullptr, *cc_k1 = nullptr, *cc_k2 = nullptr;
-  float *nc_val = nullptr, *cc_val = nullptr;
+  if (n > CFB_MAX_NUM || m > CFB_MAX_CAT) throw InvalidInputException("too many columns in a lifted triple");
+  // the sparse leaves as flat arrays (the vectors' own buffers unless something below was sliced)
+  std::vector<int32_t> s_lck, s_nck, s_cc1, s_cc2;
+  std::vector<float> s_lcv, s_ncv, s_ccv;
+  const int32_t *lc_key = in.lin_cat.FlatLeaf<int32_t>(0, s_lck);
+  const float *lc_val = in.lin_cat.FlatLeaf<float>(1, s_lcv);
+  const int32_t *nc_key = nullptr, *cc_k1 = nullptr, *cc_k2 = nullptr;
+  const float *nc_val = nullptr, *cc_val = nullptr;
   if (!nb) {
-    nc_outer = ListVector::GetData(*kids[4]);
-    Vector &nc_in = ListVector::GetEntry(*kids[4]);
-    nc_inner = ListVector::GetData(nc_in);
-    auto &nkv = StructVector::GetEntries(ListVector::GetEntry(nc_in));
-    nc_key = FlatVector::GetData<int32_t>(*nkv[0]);
-    nc_val = FlatVector::GetData<float>(*nkv[1]);
-    cc_outer = ListVector::GetData(*kids[5]);
-    Vector &cc_in = ListVector::GetEntry(*kids[5]);
-    cc_inner = ListVector::GetData(cc_in);
-    auto &ckv = StructVector::GetEntries(ListVector::GetEntry(cc_in));
-    cc_k1 = FlatVector::GetData<int32_t>(*ckv[0]);
-    cc_k2 = FlatVector::GetData<int32_t>(*ckv[1]);
-    cc_val = FlatVector::GetData<float>(*ckv[2]);
+    nc_key = in.num_cat.FlatLeaf<int32_t>(0, s_nck);
+    nc_val = in.num_cat.FlatLeaf<float>(1, s_ncv);
+    cc_k1 = in.cat_cat.FlatLeaf<int32_t>(0, s_cc1);
+    cc_k2 = in.cat_cat.FlatLeaf<int32_t>(1, s_cc2);
+    cc_val = in.cat_cat.FlatLeaf<float>(2, s_ccv);
   }
   // Gather per state: compact copies of the numeric children and the inner list entries of the
   // rows that belong to it (a chunk normally has one state, or a handful with GROUP BY).
@@ -235,33 +222,49 @@ void SumLifted(int kind, duckdb::Vector inputs[], idx_t input_count, duckdb::Vec
     const auto &rows = rows_of[b];
     gN.clear(); gl.clear(); gq.clear(); glc.clear(); gnc.clear(); gcc.clear();
     for (idx_t r : rows) {
-      if (lin_e[r].length != n || quad_e[r].length != nq || lc_outer[r].length != m)
+      const idx_t sr = in.Row(r);
+      const list_entry_t le = in.lin.Entry(sr), qe = in.quad.Entry(sr), lco = in.lin_cat.Outer(sr);
+      if (le.length != n || qe.length != nq || lco.length != m)
         throw InvalidInputException("triples of different shapes in one aggregate");
-      gN.push_back(N[r]);
-      gl.insert(gl.end(), lin_d + lin_e[r].offset, lin_d + lin_e[r].offset + n);
-      gq.insert(gq.end(), quad_d + quad_e[r].offset, quad_d + quad_e[r].offset + nq);
+      gN.push_back(in.N.At<int32_t>(sr));
+      for (idx_t k = 0; k < n; k++) gl.push_back(in.lin.elems.At<float>(le.offset + k));
+      for (idx_t k = 0; k < nq; k++) gq.push_back(in.quad.elems.At<float>(qe.offset + k));
       for (idx_t k = 0; k < m; k++) {
-        const list_entry_t e = lc_inner[lc_outer[r].offset + k];
+        const list_entry_t e = in.lin_cat.Inner(lco.offset + k);
         glc.push_back({e.offset, e.length});
       }
       if (nb) continue;
-      if (nc_outer[r].length != n * m || cc_outer[r].length != npl)
-        throw InvalidInputException("triple STRUCT lists have the wrong length");
+      const list_entry_t nco = in.num_cat.Outer(sr), cco = in.cat_cat.Outer(sr);
+      if (nco.length != n * m || cco.length != npl) throw InvalidInputException("triple STRUCT lists have the wrong length");
       for (idx_t e = 0; e < n * m; e++) {
-        const list_entry_t le = nc_inner[nc_outer[r].offset + e];
-        gnc.push_back({le.offset, le.length});
+        const list_entry_t x = in.num_cat.Inner(nco.offset + e);
+        gnc.push_back({x.offset, x.length});
       }
       for (idx_t e = 0; e < npl; e++) {
-        const list_entry_t le = cc_inner[cc_outer[r].offset + e];
-        gcc.push_back({le.offset, le.length});
+        const list_entry_t x = in.cat_cat.Inner(cco.offset + e);
+        gcc.push_back({x.offset, x.length});
       }
     }
+    // a state that is fed alone keeps a private context; GROUP BY states share their worker thread's arena
     SumState *s = order[b];
-    if (s->arena && s->arena->capacity != 1) throw InvalidInputException("sum over lifted triples: state belongs to a GROUP BY arena");
-    CheckRc(cfb_ctx_append_triples(PrivateContext(*s, kind, (int)n, (int)m), rows.size(), gN.data(), gl.data(), gq.data(), glc.data(),
-                                   FlatVector::GetData<int32_t>(*lc_kv[0]), FlatVector::GetData<float>(*lc_kv[1]),
-                                   nb ? nullptr : gnc.data(), nc_key, nc_val, nb ? nullptr : gcc.data(), cc_k1, cc_k2, cc_val));
+    if (!s->arena) {
+      if (order.size() == 1) PrivateContext(*s, kind, (int)n, (int)m);
+      else AssignSlot(*s, kind, (int)n, (int)m);
+    }
+    if (s->arena->kind != kind || s->arena->n != (int)n || s->arena->m != (int)m)
+      throw InvalidInputException("triples of different shapes in one aggregate");
+    std::lock_guard<std::mutex> g(s->arena->mu);
+    CheckRc(cfb_ctx_append_triples_slot(s->arena->ctx, s->slot, rows.size(), gN.data(), gl.data(), gq.data(), glc.data(), lc_key,
+                                        lc_val, nb ? nullptr : gnc.data(), nc_key, nc_val, nb ? nullptr : gcc.data(), cc_k1,
+                                        cc_k2, cc_val));
   }
+}
+
+// simple_update of sum_triple / sum_nb_agg: every row of the chunk belongs to the one state
+void SumLiftedSimple(int kind, duckdb::Vector inputs[], idx_t input_count, duckdb::data_ptr_t state, idx_t count) {
+  duckdb::Vector states(duckdb::LogicalType::POINTER, (duckdb::data_ptr_t)&state);
+  states.SetVectorType(duckdb::VectorType::CONSTANT_VECTOR);
+  SumLifted(kind, inputs, input_count, states, count);
 }
 
 }  // namespace
@@ -299,6 +302,13 @@ void Sum(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_coun
 void sum_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::Vector &state_vector,
                 idx_t count) {
   SumLifted(CFB_NB, inputs, input_count, state_vector, count);
+}
+void SumSimple(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::data_ptr_t state, idx_t count) {
+  SumLiftedSimple(CFB_TRIPLE, inputs, input_count, state, count);
+}
+void sum_nb_agg_simple(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::data_ptr_t state,
+                       idx_t count) {
+  SumLiftedSimple(CFB_NB, inputs, input_count, state, count);
 }
 
 }  // namespace Triple

@@ -12,6 +12,7 @@
 
 #include "../../../include/cofactor_b200.h"
 #include "triple_glue.h"
+#include "triple_view.h"
 
 namespace Triple {
 
@@ -37,69 +38,40 @@ struct OwnedResult {
   }
 };
 
-// Accessors of one triple STRUCT argument (flat vectors: the join materialises them; the
-// reference flattens first, mul.cpp:24-25).
+// One row of a triple STRUCT argument -> OwnedResult.  After a join the argument is rarely a plain flat
+// vector (a CROSS JOIN hands one side over as a CONSTANT vector; a hash join slices the STRUCT's children into
+// DICTIONARY vectors); the reference flattens both arguments first (mul.cpp:24-28), TripleView reads them in place.
 struct TripleReader {
-  bool nb;
-  const int32_t *N;
-  const duckdb::list_entry_t *lin_e, *quad_e, *lc_outer, *lc_inner, *nc_outer = nullptr, *nc_inner = nullptr,
-                             *cc_outer = nullptr, *cc_inner = nullptr;
-  const float *lin_d, *quad_d, *lc_val, *nc_val = nullptr, *cc_val = nullptr;
-  const int32_t *lc_key, *cc_k1 = nullptr, *cc_k2 = nullptr;
-
-  TripleReader(duckdb::Vector &v, bool nb_) : nb(nb_) {
-    using namespace duckdb;
-    if (v.GetType().id() != LogicalTypeId::STRUCT) throw InvalidInputException("ring product: expected a triple STRUCT");
-    if (v.GetVectorType() != VectorType::FLAT_VECTOR) throw InvalidInputException("ring product expects flat STRUCT vectors");
-    auto &kids = StructVector::GetEntries(v);
-    if (kids.size() != (nb ? 4u : 6u)) throw InvalidInputException("triple STRUCT has the wrong number of fields");
-    N = FlatVector::GetData<int32_t>(*kids[0]);
-    lin_e = ListVector::GetData(*kids[1]);
-    quad_e = ListVector::GetData(*kids[2]);
-    lin_d = FlatVector::GetData<float>(ListVector::GetEntry(*kids[1]));
-    quad_d = FlatVector::GetData<float>(ListVector::GetEntry(*kids[2]));
-    lc_outer = ListVector::GetData(*kids[3]);
-    Vector &lc_in = ListVector::GetEntry(*kids[3]);
-    lc_inner = ListVector::GetData(lc_in);
-    auto &kv = StructVector::GetEntries(ListVector::GetEntry(lc_in));
-    lc_key = FlatVector::GetData<int32_t>(*kv[0]);
-    lc_val = FlatVector::GetData<float>(*kv[1]);
-    if (nb) return;
-    nc_outer = ListVector::GetData(*kids[4]);
-    Vector &nc_in = ListVector::GetEntry(*kids[4]);
-    nc_inner = ListVector::GetData(nc_in);
-    nc_val = FlatVector::GetData<float>(*StructVector::GetEntries(ListVector::GetEntry(nc_in))[1]);
-    cc_outer = ListVector::GetData(*kids[5]);
-    Vector &cc_in = ListVector::GetEntry(*kids[5]);
-    cc_inner = ListVector::GetData(cc_in);
-    auto &kkv = StructVector::GetEntries(ListVector::GetEntry(cc_in));
-    cc_k1 = FlatVector::GetData<int32_t>(*kkv[0]);
-    cc_k2 = FlatVector::GetData<int32_t>(*kkv[1]);
-    cc_val = FlatVector::GetData<float>(*kkv[2]);
-  }
+  TripleView v;
+  TripleReader(duckdb::Vector &vec, idx_t count, bool nb) : v(vec, count, nb) {}
 
   void Row(idx_t row, OwnedResult &o) const {
     using namespace duckdb;
+    const bool nb = v.nb;
     memset(&o.r, 0, sizeof(o.r));
-    const idx_t n = lin_e[row].length, m = lc_outer[row].length;
+    const idx_t sr = v.Row(row);
+    const list_entry_t le = v.lin.Entry(sr), qe = v.quad.Entry(sr), lco = v.lin_cat.Outer(sr);
+    const idx_t n = le.length, m = lco.length;
     const idx_t nq = nb ? n : n * (n + 1) / 2;
     if (n > CFB_MAX_NUM || m > CFB_MAX_CAT) throw InvalidInputException("ring product: too many columns");
-    if (quad_e[row].length != nq) throw InvalidInputException("triple STRUCT lists have the wrong length");
+    if (qe.length != nq) throw InvalidInputException("triple STRUCT lists have the wrong length");
     o.r.kind = nb ? CFB_NB : CFB_TRIPLE;
     o.r.n_num = (int)n;
     o.r.n_cat = (int)m;
-    o.r.N = N[row];
+    o.r.N = v.N.At<int32_t>(sr);
     o.r.n_quad = (int64_t)nq;
-    o.lin.assign(lin_d + lin_e[row].offset, lin_d + lin_e[row].offset + n);
-    o.quad.assign(quad_d + quad_e[row].offset, quad_d + quad_e[row].offset + nq);
+    o.lin.resize(n);
+    o.quad.resize(nq);
+    for (idx_t k = 0; k < n; k++) o.lin[k] = v.lin.elems.At<float>(le.offset + k);
+    for (idx_t k = 0; k < nq; k++) o.quad[k] = v.quad.elems.At<float>(qe.offset + k);
     o.cat_off.assign(m + 1, 0);
     o.cat_key.clear();
     o.cat_cnt.clear();
     for (idx_t c = 0; c < m; c++) {
-      const list_entry_t e = lc_inner[lc_outer[row].offset + c];
+      const list_entry_t e = v.lin_cat.Inner(lco.offset + c);
       for (idx_t t = 0; t < e.length; t++) {
-        o.cat_key.push_back(lc_key[e.offset + t]);
-        o.cat_cnt.push_back((int64_t)lc_val[e.offset + t]);  // counts are integral floats
+        o.cat_key.push_back(v.lin_cat.Leaf<int32_t>(0, e.offset + t));
+        o.cat_cnt.push_back((int64_t)v.lin_cat.Leaf<float>(1, e.offset + t));  // counts are integral floats
       }
       o.cat_off[c + 1] = (int64_t)o.cat_key.size();
     }
@@ -111,24 +83,25 @@ struct TripleReader {
     o.k2.clear();
     o.pair_cnt.clear();
     if (!nb) {
-      if (nc_outer[row].length != n * m || cc_outer[row].length != m * (m + 1) / 2)
+      const list_entry_t nco = v.num_cat.Outer(sr), cco = v.cat_cat.Outer(sr);
+      if (nco.length != n * m || cco.length != m * (m + 1) / 2)
         throw InvalidInputException("triple STRUCT lists have the wrong length");
       o.numcat.assign(n * tk, 0.0);
       for (idx_t i = 0; i < n; i++)
         for (idx_t c = 0; c < m; c++) {  // sub-list num*m + cat, same keys / order as lin_cat[cat]
-          const list_entry_t e = nc_inner[nc_outer[row].offset + i * m + c];
+          const list_entry_t e = v.num_cat.Inner(nco.offset + i * m + c);
           if ((int64_t)e.length != o.cat_off[c + 1] - o.cat_off[c])
             throw InvalidInputException("quad_num_cat and lin_cat disagree on the keys of a column");
-          for (idx_t t = 0; t < e.length; t++) o.numcat[i * tk + o.cat_off[c] + t] = nc_val[e.offset + t];
+          for (idx_t t = 0; t < e.length; t++) o.numcat[i * tk + o.cat_off[c] + t] = v.num_cat.Leaf<float>(1, e.offset + t);
         }
       const idx_t npl = m * (m + 1) / 2;
       o.r.n_pair_lists = (int64_t)npl;
       for (idx_t p = 0; p < npl; p++) {
-        const list_entry_t e = cc_inner[cc_outer[row].offset + p];
+        const list_entry_t e = v.cat_cat.Inner(cco.offset + p);
         for (idx_t t = 0; t < e.length; t++) {
-          o.k1.push_back(cc_k1[e.offset + t]);
-          o.k2.push_back(cc_k2[e.offset + t]);
-          o.pair_cnt.push_back((int64_t)cc_val[e.offset + t]);
+          o.k1.push_back(v.cat_cat.Leaf<int32_t>(0, e.offset + t));
+          o.k2.push_back(v.cat_cat.Leaf<int32_t>(1, e.offset + t));
+          o.pair_cnt.push_back((int64_t)v.cat_cat.Leaf<float>(2, e.offset + t));
         }
         o.pair_off.push_back((int64_t)o.k1.size());
       }
@@ -142,7 +115,7 @@ void Multiply(bool nb, duckdb::DataChunk &args, duckdb::Vector &result) {
   if (args.ColumnCount() != 2) throw InvalidInputException("the ring product takes two triples");
   const idx_t rows = args.size();
   if (rows == 0) return;
-  TripleReader A(args.data[0], nb), B(args.data[1], nb);
+  TripleReader A(args.data[0], rows, nb), B(args.data[1], rows, nb);
   std::vector<cfb_result> res(rows);
   struct Guard {
     std::vector<cfb_result> &r;

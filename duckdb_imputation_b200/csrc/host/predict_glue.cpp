@@ -39,10 +39,10 @@ void Classify(duckdb::DataChunk &args, idx_t first, Columns &c) {
     if (t == LogicalType::FLOAT || t == LogicalType::DOUBLE) {
       if (!c.cat.empty()) throw InvalidInputException("numeric columns must precede categorical ones");
       c.num.push_back(UnifiedVectorFormat::GetData<float>(c.fmt[j]));
-      c.num_sel.push_back(c.fmt[j].sel->sel);
+      c.num_sel.push_back(c.fmt[j].sel->data());
     } else if (t == LogicalType::INTEGER) {
       c.cat.push_back(UnifiedVectorFormat::GetData<int32_t>(c.fmt[j]));
-      c.cat_sel.push_back(c.fmt[j].sel->sel);
+      c.cat_sel.push_back(c.fmt[j].sel->data());
     } else {
       throw InvalidInputException("feature columns must be FLOAT or INTEGER");
     }

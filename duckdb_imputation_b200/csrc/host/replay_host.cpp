@@ -18,6 +18,9 @@ namespace duckdb_ring {
 void Load(duckdb::DatabaseInstance &db);
 const char *Implementation();
 }  // namespace duckdb_ring
+// The loadable-extension entry points (our build exports them; the reference's test build does not).
+extern "C" __attribute__((weak)) void duckdb_imputation_init(duckdb::DatabaseInstance &db);
+extern "C" __attribute__((weak)) const char *duckdb_imputation_version();
 
 namespace {
 
@@ -70,15 +73,53 @@ void RenderValue(duckdb::Vector &v, idx_t row, std::ostringstream &os) {
 }
 
 struct ThreadLocalStates {
-  std::unique_ptr<duckdb::data_t[]> mem;  // n_groups * state_size, like hash-table row storage
+  std::unique_ptr<duckdb::data_t[]> mem;  // [split][n_groups] * state_size, like hash-table row storage
   std::vector<char> live;
 };
+
+// Shapes of DuckDB's protocol that a plain scan does not produce (replay_set_option).
+struct Options {
+  int no_simple = 0;          // 1: never use simple_update (force the hash-aggregate protocol)
+  int lift_shape = 0;         // lifted argument: 0 flat, 1 DICTIONARY struct (reversed rows), 2 flat struct with
+                              // DICTIONARY children and leaves, 3 CONSTANT struct (a CROSS JOIN side)
+  int split_states = 1;       // k > 1: a worker keeps k state sets per group (hash table reset when full) and
+                              // merges them itself: two states of one group from one thread
+  int parallel_finalize = 0;  // P > 1: P threads combine + finalize disjoint groups at once (radix partitions)
+};
+Options g_opt;
 
 }  // namespace
 
 extern "C" {
 
 const char *replay_last_error(void) { return g_error.c_str(); }
+
+int replay_set_option(const char *name, int value) {
+  const std::string n = name ? name : "";
+  if (n == "no_simple") g_opt.no_simple = value;
+  else if (n == "lift_shape") g_opt.lift_shape = value;
+  else if (n == "split_states") g_opt.split_states = value < 1 ? 1 : value;
+  else if (n == "parallel_finalize") g_opt.parallel_finalize = value;
+  else if (n == "reset") g_opt = Options{};
+  else {
+    g_error = "replay: unknown option " + n;
+    return -1;
+  }
+  return 0;
+}
+
+// Load a fresh catalog through the extension's exported entry points; returns the number of functions registered
+// (-1: the entry points are not exported by this build).  version_out: duckdb_imputation_version().
+int replay_load_via_entry_points(const char **version_out) {
+  if (!duckdb_imputation_init || !duckdb_imputation_version) {
+    g_error = "this build does not export duckdb_imputation_init / duckdb_imputation_version";
+    return -1;
+  }
+  duckdb::DatabaseInstance db;
+  duckdb_imputation_init(db);
+  if (version_out) *version_out = duckdb_imputation_version();
+  return (int)(db.aggregates.size() + db.scalars.size());
+}
 const char *replay_implementation(void) { return duckdb_ring::Implementation(); }
 void replay_free(char *p) { free(p); }
 
@@ -336,12 +377,26 @@ int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *co
         }
       }
       chunk.SetCardinality(count);
+      // what a join hands a scalar function (replay_set_option lift_shape): every argument behind a selection
+      // that reverses the rows (1: on the STRUCT, 2: on its children), or the LAST argument as a CONSTANT vector --
+      // its first row for every row of the chunk (3: a CROSS JOIN side).  Output row r then belongs to input row
+      // count-1-r (1, 2); the rendering below puts it back in input order.
+      std::vector<sel_t> rev(count);
+      for (idx_t r = 0; r < count; r++) rev[r] = (sel_t)(count - 1 - r);
+      const int shape = g_opt.lift_shape;
+      if (shape == 1)
+        for (auto &v : chunk.data) v.Slice(SelectionVector(rev.data()));
+      else if (shape == 2)
+        for (auto &v : chunk.data)
+          for (auto &kid : StructVector::GetEntries(v)) kid->Slice(SelectionVector(rev.data()));
+      else if (shape == 3)
+        chunk.data.back().SetVectorType(VectorType::CONSTANT_VECTOR);
       ExpressionState state;
       Vector result(fun.return_type, count);
       fun.function(chunk, state, result);
       for (idx_t r = 0; r < count; r++) {
         if (lo + r) os << ", ";
-        RenderValue(result, r, os);
+        RenderValue(result, (shape == 1 || shape == 2) ? count - 1 - r : r, os);
       }
     }
     os << "]";
@@ -380,10 +435,14 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
     const size_t n_chunks = (rows + STANDARD_VECTOR_SIZE - 1) / STANDARD_VECTOR_SIZE;
     int T = std::max(1, threads);
     if ((size_t)T > std::max<size_t>(1, n_chunks)) T = (int)std::max<size_t>(1, n_chunks);
+    const Options opt = g_opt;
+    const int K = opt.split_states;  // state sets per worker
+    // a query without GROUP BY over an aggregate with simple_update is planned as an ungrouped aggregate
+    const bool simple = !group && n_groups == 1 && fun.simple_update && !opt.no_simple && K == 1;
     std::vector<ThreadLocalStates> tls(T);
     for (auto &t : tls) {
-      t.mem.reset(new data_t[std::max<size_t>(1, ssz * n_groups)]);
-      t.live.assign(n_groups, 0);
+      t.mem.reset(new data_t[std::max<size_t>(1, ssz * n_groups * K)]);
+      t.live.assign((size_t)n_groups * K, 0);
     }
     std::string worker_error;
     std::mutex err_mu;
@@ -393,8 +452,9 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
       try {
         ThreadLocalStates &loc = tls[t];
         const size_t c_lo = n_chunks * t / T, c_hi = n_chunks * (t + 1) / T;
-        std::vector<data_ptr_t> ptrs(STANDARD_VECTOR_SIZE);
-        std::vector<sel_t> rel(STANDARD_VECTOR_SIZE);
+        std::vector<data_ptr_t> ptrs(STANDARD_VECTOR_SIZE), ptrs2(STANDARD_VECTOR_SIZE);
+        std::vector<sel_t> rel(STANDARD_VECTOR_SIZE), rev(STANDARD_VECTOR_SIZE), ident(4 * STANDARD_VECTOR_SIZE);
+        for (size_t i = 0; i < ident.size(); i++) ident[i] = (sel_t)i;
         // first selected row at or after this thread's range (sel is ascending)
         size_t s_pos = sel ? (size_t)(std::lower_bound(sel, sel + n_sel, (uint32_t)(c_lo * STANDARD_VECTOR_SIZE)) - sel) : 0;
         for (size_t c = c_lo; c < c_hi; c++) {
@@ -405,14 +465,15 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
             while (s_pos < n_sel && sel[s_pos] < hi) rel[count++] = (sel_t)(sel[s_pos++] - lo);
             if (!count) continue;
           }
+          const size_t set = K > 1 ? c % (size_t)K : 0;
           for (idx_t r = 0; r < count; r++) {
             const size_t row = lo + (sel ? rel[r] : r);
             const int g = group ? group[row] : 0;
             if (g < 0 || g >= n_groups) throw InvalidInputException("group slot out of range");
-            data_ptr_t st = loc.mem.get() + (size_t)g * ssz;
-            if (!loc.live[g]) {
+            data_ptr_t st = loc.mem.get() + (set * n_groups + (size_t)g) * ssz;
+            if (!loc.live[set * n_groups + g]) {
               fun.initialize(st);
-              loc.live[g] = 1;
+              loc.live[set * n_groups + g] = 1;
             }
             ptrs[r] = st;
           }
@@ -425,10 +486,63 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
             std::vector<Vector> one;
             one.emplace_back(lift->fun.return_type, count);
             lift->fun.function(chunk, estate, one[0]);
-            fun.update(one.data(), aggr, 1, state_vector, count);
+            if (opt.lift_shape == 1 || opt.lift_shape == 2) {
+              // rows reach the aggregate in reverse order through a selection: on the STRUCT itself (1) or on each
+              // of its children, with an explicit identity selection on every leaf below them (2)
+              for (idx_t r = 0; r < count; r++) {
+                rev[r] = (sel_t)(count - 1 - r);
+                ptrs2[r] = ptrs[count - 1 - r];
+              }
+              if (opt.lift_shape == 1) {
+                one[0].Slice(SelectionVector(rev.data()));
+              } else {
+                for (auto &kid : StructVector::GetEntries(one[0])) {
+                  kid->Slice(SelectionVector(rev.data()));
+                  if (kid->GetType().id() != LogicalTypeId::LIST) continue;
+                  Vector &el = ListVector::GetEntry(*kid);
+                  if (el.GetType().id() != LogicalTypeId::LIST) continue;
+                  if (ListVector::GetListSize(el) > ident.size()) {
+                    const size_t old = ident.size();
+                    ident.resize(ListVector::GetListSize(el));
+                    for (size_t i = old; i < ident.size(); i++) ident[i] = (sel_t)i;
+                  }
+                  for (auto &leaf : StructVector::GetEntries(ListVector::GetEntry(el))) leaf->Slice(SelectionVector(ident.data()));
+                }
+              }
+              Vector sv2(LogicalType::POINTER, (data_ptr_t)ptrs2.data());
+              fun.update(one.data(), aggr, 1, sv2, count);
+            } else if (opt.lift_shape == 3) {
+              // the chunk's first lifted row as a CONSTANT vector `count` rows long
+              one[0].SetVectorType(VectorType::CONSTANT_VECTOR);
+              fun.update(one.data(), aggr, 1, state_vector, count);
+            } else if (simple) {
+              fun.simple_update(one.data(), aggr, 1, ptrs[0], count);
+            } else {
+              fun.update(one.data(), aggr, 1, state_vector, count);
+            }
+          } else if (simple) {
+            fun.simple_update(chunk.data.data(), aggr, (idx_t)n_cols, ptrs[0], count);
           } else {
             fun.update(chunk.data.data(), aggr, (idx_t)n_cols, state_vector, count);
           }
+        }
+        // a worker that kept several state sets merges them into its first one (same thread, same arenas)
+        for (int set = 1; set < K; set++) {
+          std::vector<data_ptr_t> src_p, dst_p;
+          for (int g = 0; g < n_groups; g++)
+            if (loc.live[(size_t)set * n_groups + g]) {
+              data_ptr_t d = loc.mem.get() + (size_t)g * ssz;
+              if (!loc.live[g]) {
+                fun.initialize(d);
+                loc.live[g] = 1;
+              }
+              src_p.push_back(loc.mem.get() + ((size_t)set * n_groups + g) * ssz);
+              dst_p.push_back(d);
+            }
+          if (src_p.empty()) continue;
+          Vector sv(LogicalType::POINTER, (data_ptr_t)src_p.data()), dv(LogicalType::POINTER, (data_ptr_t)dst_p.data());
+          fun.combine(sv, dv, aggr, src_p.size());
+          if (fun.destructor) fun.destructor(sv, aggr, src_p.size());
         }
       } catch (std::exception &e) {
         std::lock_guard<std::mutex> g(err_mu);
@@ -444,48 +558,78 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
     }
     if (!worker_error.empty()) throw Exception(worker_error);
 
-    // combine the thread-local states into thread 0's, group by group, then destroy sources
+    // combine the thread-local states into thread 0's, group by group, then destroy the sources; finalize.
+    // P > 1 threads do this for disjoint sets of groups at the same time, as DuckDB finalizes radix partitions.
     ThreadLocalStates &dst = tls[0];
-    for (int t = 1; t < T; t++) {
-      std::vector<data_ptr_t> src_p, dst_p;
-      for (int g = 0; g < n_groups; g++)
-        if (tls[t].live[g]) {
-          data_ptr_t d = dst.mem.get() + (size_t)g * ssz;
-          if (!dst.live[g]) {
-            fun.initialize(d);
-            dst.live[g] = 1;
-          }
-          src_p.push_back(tls[t].mem.get() + (size_t)g * ssz);
-          dst_p.push_back(d);
+    const int P = std::max(1, std::min(opt.parallel_finalize, n_groups));
+    std::vector<std::vector<std::string>> rendered(P);  // per finalize thread: one STRUCT per live group, group order
+    std::vector<std::vector<int>> groups_of(P);
+    double secs = 0, finalize_secs = -1;
+    double *seconds_box = &finalize_secs;
+    auto finisher = [&](int p) {
+      try {
+        std::vector<int> mine;
+        for (int g = p; g < n_groups; g += P) mine.push_back(g);
+        for (int t = 1; t < T; t++) {
+          std::vector<data_ptr_t> src_p, dst_p;
+          for (int g : mine)
+            if (tls[t].live[g]) {
+              data_ptr_t d = dst.mem.get() + (size_t)g * ssz;
+              if (!dst.live[g]) {
+                fun.initialize(d);
+                dst.live[g] = 1;
+              }
+              src_p.push_back(tls[t].mem.get() + (size_t)g * ssz);
+              dst_p.push_back(d);
+            }
+          if (src_p.empty()) continue;
+          Vector sv(LogicalType::POINTER, (data_ptr_t)src_p.data()), dv(LogicalType::POINTER, (data_ptr_t)dst_p.data());
+          fun.combine(sv, dv, aggr, src_p.size());
+          if (fun.destructor) fun.destructor(sv, aggr, src_p.size());
         }
-      if (src_p.empty()) continue;
-      Vector sv(LogicalType::POINTER, (data_ptr_t)src_p.data()), dv(LogicalType::POINTER, (data_ptr_t)dst_p.data());
-      fun.combine(sv, dv, aggr, src_p.size());
-      if (fun.destructor) fun.destructor(sv, aggr, src_p.size());
+        std::vector<data_ptr_t> fin;
+        for (int g : mine)
+          if (dst.live[g]) {
+            fin.push_back(dst.mem.get() + (size_t)g * ssz);
+            groups_of[p].push_back(g);
+          }
+        if (fin.empty()) return;
+        Vector states(LogicalType::POINTER, (data_ptr_t)fin.data());
+        Vector result(fun.return_type, std::max<idx_t>(fin.size(), 1));
+        fun.finalize(states, aggr, result, fin.size(), 0);
+        if (p == 0 && P == 1) *seconds_box = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t i = 0; i < fin.size(); i++) {
+          std::ostringstream one;
+          RenderValue(result, i, one);
+          rendered[p].push_back(one.str());
+        }
+        if (fun.destructor) fun.destructor(states, aggr, fin.size());
+      } catch (std::exception &e) {
+        std::lock_guard<std::mutex> g(err_mu);
+        worker_error = e.what();
+      }
+    };
+    if (P == 1) {
+      finisher(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int p = 0; p < P; p++) pool.emplace_back(finisher, p);
+      for (auto &th : pool) th.join();
     }
-    std::vector<data_ptr_t> fin;
-    for (int g = 0; g < n_groups; g++)
-      if (dst.live[g]) fin.push_back(dst.mem.get() + (size_t)g * ssz);
+    if (!worker_error.empty()) throw Exception(worker_error);
+    secs = finalize_secs >= 0 ? finalize_secs : std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::ostringstream os;
     os << "[";
-    double secs = 0;
-    if (!fin.empty()) {
-      Vector states(LogicalType::POINTER, (data_ptr_t)fin.data());
-      Vector result(fun.return_type, std::max<idx_t>(fin.size(), 1));
-      fun.finalize(states, aggr, result, fin.size(), 0);
-      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      for (size_t i = 0; i < fin.size(); i++) {
+    {
+      // results in group order
+      std::vector<std::pair<int, const std::string *>> all;
+      for (int p = 0; p < P; p++)
+        for (size_t i = 0; i < groups_of[p].size(); i++) all.emplace_back(groups_of[p][i], &rendered[p][i]);
+      std::sort(all.begin(), all.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+      for (size_t i = 0; i < all.size(); i++) {
         if (i) os << ", ";
-        RenderValue(result, i, os);
+        os << *all[i].second;
       }
-      const auto t1 = std::chrono::steady_clock::now();
-      if (fun.destructor) fun.destructor(states, aggr, fin.size());
-      if (getenv("CFB_REPLAY_TRACE"))
-        fprintf(stderr, "[replay] update+combine+finalize %.1f ms, render %.1f ms, destroy %.1f ms\n", secs * 1e3,
-                std::chrono::duration<double>(t1 - t0).count() * 1e3 - secs * 1e3,
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count() * 1e3);
-    } else {
-      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     os << "]";
     if (seconds) *seconds = secs;

@@ -48,6 +48,17 @@ int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *co
 int replay_predict(const char *scalar, const float *params, size_t n_params, const int *flags, int n_flags, int n_num,
                    int n_cat, const float *const *num, const int32_t *const *cat, const uint32_t *sel, size_t n_sel,
                    size_t rows, void *out);
+/* Shapes of DuckDB's protocol that a plain table scan does not produce (process-wide; "reset" restores all):
+ *   no_simple = 1          never plan an ungrouped aggregate: use update() with per-row state pointers
+ *   lift_shape = 1|2|3     the lifted STRUCT reaches the aggregate as a DICTIONARY vector (1), as a flat vector with
+ *                          DICTIONARY children and leaves (2), or as a CONSTANT vector -- the chunk's first row
+ *                          repeated (3): what joins and filters below sum_triple / multiply_triple hand over
+ *   split_states = k       every worker keeps k state sets per group and merges them itself (hash table reset)
+ *   parallel_finalize = P  P threads combine + finalize disjoint groups at the same time (radix partitions)  */
+int replay_set_option(const char *name, int value);
+/* Load a fresh catalog through duckdb_imputation_init(); returns the number of registered functions, -1 if the build
+ * does not export the entry points.  *version_out = duckdb_imputation_version().                               */
+int replay_load_via_entry_points(const char **version_out);
 void replay_free(char *p);
 const char *replay_last_error(void);
 /* Names of all registered aggregate functions, '\n'-separated (malloc'd). */

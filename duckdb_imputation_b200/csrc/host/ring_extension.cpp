@@ -3,8 +3,10 @@
 // Mirrors load_ring / load_nb_ring of the reference (duckdb_imputation_extension.cpp:80-113,
 // :146-179): the same SQL names, argument types, constructor-argument order
 //   (name, arg_types, return_type, state_size, initialize, update, combine, finalize,
-//    simple_update = nullptr, bind, destructor, statistics = nullptr, window = nullptr),
-// varargs = ANY and SPECIAL null handling.  The reference's loops stop at 19 although its
+//    simple_update, bind, destructor, statistics = nullptr, window = nullptr),
+// varargs = ANY and SPECIAL null handling.  simple_update is null in the reference (ext.cpp:53,106); here it is
+// supplied, which lets DuckDB plan PhysicalUngroupedAggregate for queries without GROUP BY (one state per thread,
+// no per-row state pointers) -- the five existing callbacks keep their signatures.  The reference's loops stop at 19 although its
 // README promises 20 (README.md:136); this build registers i, j in [0, 20] -- a superset that
 // includes the headline sum_to_triple_20_0.
 #include <string>
@@ -21,13 +23,13 @@ void Load(duckdb::DatabaseInstance &instance) {
   AggregateFunction sum_triple("sum_triple", {LogicalType::ANY}, LogicalTypeId::STRUCT,
                                AggregateFunction::StateSize<Triple::SumState>,
                                AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>, Triple::Sum,
-                               Triple::SumStateCombine, Triple::SumStateFinalize, nullptr, Triple::SumBind,
+                               Triple::SumStateCombine, Triple::SumStateFinalize, Triple::SumSimple, Triple::SumBind,
                                AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
   ExtensionUtil::RegisterFunction(instance, sum_triple);
   AggregateFunction sum_nb("sum_nb_agg", {LogicalType::ANY}, LogicalTypeId::STRUCT,
                            AggregateFunction::StateSize<Triple::SumState>,
                            AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>, Triple::sum_nb_agg,
-                           Triple::SumStateCombine, Triple::SumStateFinalize, nullptr, Triple::sum_nb_agg_bind,
+                           Triple::SumStateCombine, Triple::SumStateFinalize, Triple::sum_nb_agg_simple, Triple::sum_nb_agg_bind,
                            AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
   ExtensionUtil::RegisterFunction(instance, sum_nb);
   // to_cofactor(ANY...) / to_nb_agg(ANY...): varargs scalar lifts (ext.cpp:58-64, :126-131)
@@ -75,8 +77,8 @@ void Load(duckdb::DatabaseInstance &instance) {
       AggregateFunction triple("sum_to_triple_" + xy, args, LogicalTypeId::STRUCT,
                                AggregateFunction::StateSize<Triple::SumState>,
                                AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>,
-                               Triple::SumNoLift, Triple::SumStateCombine, Triple::SumStateFinalize, nullptr,
-                               Triple::SumNoLiftBind,
+                               Triple::SumNoLift, Triple::SumStateCombine, Triple::SumStateFinalize,
+                               Triple::SumNoLiftSimple, Triple::SumNoLiftBind,
                                AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
       triple.varargs = LogicalType::ANY;
       triple.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
@@ -85,8 +87,8 @@ void Load(duckdb::DatabaseInstance &instance) {
       AggregateFunction nb("sum_to_nb_agg_" + xy, args, LogicalTypeId::STRUCT,
                            AggregateFunction::StateSize<Triple::SumState>,
                            AggregateFunction::StateInitialize<Triple::SumState, Triple::StateFunction>,
-                           Triple::sum_to_nb_agg, Triple::SumStateCombine, Triple::SumStateFinalize, nullptr,
-                           Triple::sum_to_nb_agg_bind,
+                           Triple::sum_to_nb_agg, Triple::SumStateCombine, Triple::SumStateFinalize,
+                           Triple::sum_to_nb_agg_simple, Triple::sum_to_nb_agg_bind,
                            AggregateFunction::StateDestroy<Triple::SumState, Triple::StateFunction>, nullptr, nullptr);
       nb.varargs = LogicalType::ANY;
       nb.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
@@ -95,3 +97,21 @@ void Load(duckdb::DatabaseInstance &instance) {
 }
 
 }  // namespace duckdb_ring
+
+// The loadable-extension entry points, as the reference exports them (duckdb_imputation_extension.cpp:255-279).
+namespace duckdb {
+class DuckdbImputationExtension : public Extension {
+ public:
+  void Load(DuckDB &db) override { duckdb_ring::Load(*db.instance); }
+  std::string Name() override { return "duckdb_imputation"; }
+};
+}  // namespace duckdb
+
+extern "C" {
+DUCKDB_EXTENSION_API void duckdb_imputation_init(duckdb::DatabaseInstance &db) {
+  duckdb::DuckDB db_wrapper(db);
+  db_wrapper.LoadExtension<duckdb::DuckdbImputationExtension>();
+}
+// must be the LibraryVersion() of the exact DuckDB build that loads the extension (README.md:86)
+DUCKDB_EXTENSION_API const char *duckdb_imputation_version() { return duckdb::DuckDB::LibraryVersion(); }
+}

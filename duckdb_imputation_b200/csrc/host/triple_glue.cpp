@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -122,42 +123,56 @@ duckdb::LogicalType ResultType(bool nb) {
   return duckdb::LogicalType::STRUCT(f);
 }
 
-void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state_vector, idx_t count) {
-  if (count == 0) return;
-  duckdb::UnifiedVectorFormat sdata;
-  state_vector.ToUnifiedFormat(count, sdata);
-  auto states = (SumState **)sdata.data;
-
-  // FLOAT (and DOUBLE, like the reference) columns are numeric, everything else categorical;
-  // numeric columns come first (README.md:126).
+// The chunk's columns as base pointers + selection vectors (UnifiedVectorFormat, sum_no_lift.cpp:66-73):
+// FLOAT (and DOUBLE, like the reference) columns are numeric, everything else categorical; numeric
+// columns come first (README.md:126).
+struct ChunkColumns {
   const float *num[CFB_MAX_NUM];
   const uint32_t *num_sel[CFB_MAX_NUM];
   const int32_t *cat[CFB_MAX_CAT];
   const uint32_t *cat_sel[CFB_MAX_CAT];
   duckdb::UnifiedVectorFormat fmt[CFB_MAX_NUM + CFB_MAX_CAT];
-  if (cols > CFB_MAX_NUM + CFB_MAX_CAT) throw duckdb::InvalidInputException("too many columns for a ring aggregate");
   int n = 0, m = 0;
-  for (idx_t j = 0; j < cols; j++) {
-    inputs[j].ToUnifiedFormat(count, fmt[j]);
-    const auto &t = inputs[j].GetType();
-    if (t == duckdb::LogicalType::FLOAT || t == duckdb::LogicalType::DOUBLE) {
-      if (m) throw duckdb::InvalidInputException("numeric columns must precede categorical columns");
-      if (n == CFB_MAX_NUM) throw duckdb::InvalidInputException("too many numeric columns");
-      num[n] = duckdb::UnifiedVectorFormat::GetData<float>(fmt[j]);
-      num_sel[n++] = fmt[j].sel->sel;
-    } else {
-      if (m == CFB_MAX_CAT) throw duckdb::InvalidInputException("too many categorical columns");
-      cat[m] = duckdb::UnifiedVectorFormat::GetData<int32_t>(fmt[j]);
-      cat_sel[m++] = fmt[j].sel->sel;
+  ChunkColumns(duckdb::Vector inputs[], idx_t cols, idx_t count) {
+    if (cols > CFB_MAX_NUM + CFB_MAX_CAT) throw duckdb::InvalidInputException("too many columns for a ring aggregate");
+    for (idx_t j = 0; j < cols; j++) {
+      inputs[j].ToUnifiedFormat(count, fmt[j]);
+      const auto &t = inputs[j].GetType();
+      if (t == duckdb::LogicalType::FLOAT || t == duckdb::LogicalType::DOUBLE) {
+        if (m) throw duckdb::InvalidInputException("numeric columns must precede categorical columns");
+        if (n == CFB_MAX_NUM) throw duckdb::InvalidInputException("too many numeric columns");
+        num[n] = duckdb::UnifiedVectorFormat::GetData<float>(fmt[j]);
+        num_sel[n++] = fmt[j].sel->data();
+      } else {
+        if (m == CFB_MAX_CAT) throw duckdb::InvalidInputException("too many categorical columns");
+        cat[m] = duckdb::UnifiedVectorFormat::GetData<int32_t>(fmt[j]);
+        cat_sel[m++] = fmt[j].sel->data();
+      }
     }
   }
+};
+
+void AppendPrivate(SumState &state, int kind, const ChunkColumns &c, idx_t count) {
+  // a state that is fed alone gets a private one-slot context: the ungrouped kernels apply
+  cfb_ctx *ctx = PrivateContext(state, kind, c.n, c.m);
+  std::lock_guard<std::mutex> g(state.arena->mu);
+  Check(cfb_ctx_append(ctx, c.num, c.num_sel, c.cat, c.cat_sel, nullptr, count));
+}
+
+void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state_vector, idx_t count) {
+  if (count == 0) return;
+  duckdb::UnifiedVectorFormat sdata;
+  state_vector.ToUnifiedFormat(count, sdata);
+  auto states = (SumState **)sdata.data;
+  const ChunkColumns c(inputs, cols, count);
+  const int n = c.n, m = c.m;
   // Ungrouped aggregates (and single-group chunks) send every row to one state.
   SumState *first = states[sdata.sel->get_index(0)];
   bool uniform = true;
-  for (idx_t r = 1; r < count && uniform; r++) uniform = states[sdata.sel->get_index(r)] == first;
+  if (state_vector.GetVectorType() != duckdb::VectorType::CONSTANT_VECTOR)
+    for (idx_t r = 1; r < count && uniform; r++) uniform = states[sdata.sel->get_index(r)] == first;
   if (uniform && (!first->arena || first->arena->capacity == 1)) {
-    // a state that is fed alone gets a private one-slot context: the ungrouped kernels apply
-    Check(cfb_ctx_append(PrivateContext(*first, kind, n, m), num, num_sel, cat, cat_sel, nullptr, count));
+    AppendPrivate(*first, kind, c, count);
     return;
   }
   // GROUP BY: new states get a slot in this thread's open arena; the chunk is shipped once per arena
@@ -169,12 +184,7 @@ void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state
   seen.clear();
   for (idx_t r = 0; r < count; r++) {
     SumState *s = states[sdata.sel->get_index(r)];
-    if (!s->arena) {
-      Arena *a = t_open.Get(kind, n, m);
-      s->arena = a;
-      s->slot = a->next_slot++;
-      a->refs.fetch_add(1);
-    }
+    if (!s->arena) AssignSlot(*s, kind, n, m);
     size_t b = 0;
     while (b < seen.size() && seen[b] != s->arena) b++;
     if (b == seen.size()) seen.push_back(s->arena);
@@ -186,8 +196,24 @@ void Update(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::Vector &state
       const SumState *s = states[sdata.sel->get_index(r)];
       slots[r] = s->arena == a ? (uint32_t)s->slot : 0xFFFFFFFFu;  // -1 as int32: row not for this arena
     }
-    Check(cfb_ctx_append(a->ctx, num, num_sel, cat, cat_sel, slots.data(), count));
+    std::lock_guard<std::mutex> g(a->mu);
+    Check(cfb_ctx_append(a->ctx, c.num, c.num_sel, c.cat, c.cat_sel, slots.data(), count));
   }
+}
+
+void SimpleUpdate(int kind, duckdb::Vector inputs[], idx_t cols, duckdb::data_ptr_t state, idx_t count) {
+  if (count == 0) return;
+  SumState &s = *reinterpret_cast<SumState *>(state);
+  const ChunkColumns c(inputs, cols, count);
+  if (!s.arena || s.arena->capacity == 1) {
+    AppendPrivate(s, kind, c, count);
+    return;
+  }
+  // (a state that already lives in a GROUP BY arena: every row goes to its slot)
+  static thread_local std::vector<uint32_t> slots;
+  slots.assign(count, (uint32_t)s.slot);
+  std::lock_guard<std::mutex> g(s.arena->mu);
+  Check(cfb_ctx_append(s.arena->ctx, c.num, c.num_sel, c.cat, c.cat_sel, slots.data(), count));
 }
 
 }  // namespace
@@ -199,6 +225,14 @@ cfb_ctx *PrivateContext(SumState &state, int kind, int n_num, int n_cat) {
     state.slot = 0;
   }
   return state.arena->ctx;
+}
+
+void AssignSlot(SumState &state, int kind, int n_num, int n_cat) {
+  if (state.arena) return;
+  Arena *a = t_open.Get(kind, n_num, n_cat);
+  state.arena = a;
+  state.slot = a->next_slot++;
+  a->refs.fetch_add(1);
 }
 
 template <class STATE>
@@ -230,6 +264,15 @@ void sum_to_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &, duckdb
   Update(CFB_NB, inputs, cols, state_vector, count);
 }
 
+void SumNoLiftSimple(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::data_ptr_t state,
+                     idx_t count) {
+  SimpleUpdate(CFB_TRIPLE, inputs, input_count, state, count);
+}
+void sum_to_nb_agg_simple(duckdb::Vector inputs[], duckdb::AggregateInputData &, idx_t input_count, duckdb::data_ptr_t state,
+                          idx_t count) {
+  SimpleUpdate(CFB_NB, inputs, input_count, state, count);
+}
+
 void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::AggregateInputData &, idx_t count) {
   duckdb::UnifiedVectorFormat sdata;
   state.ToUnifiedFormat(count, sdata);
@@ -259,7 +302,16 @@ void SumStateCombine(duckdb::Vector &state, duckdb::Vector &combined, duckdb::Ag
     batches[b].ss.push_back(s->slot);
   }
   for (auto &b : batches) {
-    if (b.d == b.s) throw duckdb::InternalException("ring aggregate: combine of two states of one arena");
+    if (b.d == b.s) {
+      // two states of one arena (a group the hash aggregate emitted twice from one thread): merged inside
+      // the context, one pair per call -- a slot may be the target of one pair and the source of the next
+      std::lock_guard<std::mutex> g(b.d->mu);
+      for (size_t i = 0; i < b.ds.size(); i++) Check(cfb_ctx_combine_slots(b.d->ctx, b.d->ctx, 1, &b.ds[i], &b.ss[i]));
+      continue;
+    }
+    // both contexts are entered: lock both arenas, in address order
+    std::mutex &m1 = b.d < b.s ? b.d->mu : b.s->mu, &m2 = b.d < b.s ? b.s->mu : b.d->mu;
+    std::lock_guard<std::mutex> g1(m1), g2(m2);
     Check(cfb_ctx_combine_slots(b.d->ctx, b.s->ctx, b.ds.size(), b.ds.data(), b.ss.data()));
   }
 }
@@ -400,6 +452,7 @@ void SumStateFinalize(duckdb::Vector &state_vector, duckdb::AggregateInputData &
     SumState *s = states[sdata.sel->get_index(i)];
     memset(&res[i], 0, sizeof(cfb_result));
     if (s->arena) {
+      std::lock_guard<std::mutex> g(s->arena->mu);
       Check(cfb_ctx_finalize(s->arena->ctx, s->slot, &res[i]));
       n = res[i].n_num;
       m = res[i].n_cat;

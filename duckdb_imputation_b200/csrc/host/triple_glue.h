@@ -5,6 +5,7 @@
 // bodies call the C ABI of include/cofactor_b200.h instead of looping on the CPU.
 #pragma once
 #include <atomic>
+#include <mutex>
 
 #include <duckdb.hpp>
 
@@ -22,6 +23,11 @@ struct Arena {
   int capacity = 1;          // GROUP BY slots of ctx
   int next_slot = 0;         // only the owning thread hands out slots
   std::atomic<int> refs{0};  // live states + 1 while a thread keeps it open
+  // A cfb_ctx is driven by one thread at a time, but the states of ONE arena can reach combine / finalize on
+  // different threads at once (DuckDB finalizes the radix partitions of a hash aggregate in parallel; the groups
+  // of a partition come from every worker's arena).  Every entry into the context takes this lock; combine
+  // takes both arenas' locks in address order.
+  std::mutex mu;
   void Release() {
     if (refs.fetch_sub(1) == 1) {
       cfb_ctx_destroy(ctx);
@@ -51,11 +57,19 @@ struct StateFunction {
 // The context of a state that is fed alone (ungrouped aggregates, sum_triple / sum_nb_agg): a private
 // arena with one slot, created on first use.
 cfb_ctx *PrivateContext(SumState &state, int kind, int n_num, int n_cat);
+// GROUP BY: a state that has no arena yet gets a slot in the calling thread's open arena of this shape.
+void AssignSlot(SumState &state, int kind, int n_num, int n_cat);
 
 duckdb::unique_ptr<duckdb::FunctionData> SumNoLiftBind(duckdb::ClientContext &context, duckdb::AggregateFunction &function,
                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 void SumNoLift(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
                duckdb::Vector &state_vector, idx_t count);
+// simple_update (ungrouped aggregates: one state, no per-row state pointers).  The reference leaves the slot
+// null (duckdb_imputation_extension.cpp:53,106), which forces the hash aggregate even without GROUP BY.
+void SumNoLiftSimple(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+                     duckdb::data_ptr_t state, idx_t count);
+void sum_to_nb_agg_simple(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+                          duckdb::data_ptr_t state, idx_t count);
 
 duckdb::unique_ptr<duckdb::FunctionData> sum_to_nb_agg_bind(duckdb::ClientContext &context, duckdb::AggregateFunction &function,
                                                             duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
@@ -71,6 +85,10 @@ duckdb::unique_ptr<duckdb::FunctionData> sum_nb_agg_bind(duckdb::ClientContext &
                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 void sum_nb_agg(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
                 duckdb::Vector &state_vector, idx_t count);
+void SumSimple(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+               duckdb::data_ptr_t state, idx_t count);
+void sum_nb_agg_simple(duckdb::Vector inputs[], duckdb::AggregateInputData &aggr_input_data, idx_t input_count,
+                       duckdb::data_ptr_t state, idx_t count);
 void CustomLift(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
 duckdb::unique_ptr<duckdb::FunctionData> CustomLiftBind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);

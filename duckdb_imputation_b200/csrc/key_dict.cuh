@@ -14,8 +14,11 @@
 
 namespace cfb {
 
+// An entry is (code << 32) | (uint32_t)key.  Real codes are < 2^31, so neither the free marker (code field
+// 0xFFFFFFFF) nor the pending marker (0xFFFFFFFE) can be produced by a published entry, and
+// (pending, key) differs from the free word for EVERY key, -1 included.
 constexpr unsigned long long kDictEmpty = ~0ull;
-constexpr unsigned int kDictPending = 0xFFFFFFFFu;
+constexpr unsigned int kDictPending = 0xFFFFFFFEu;
 
 struct KeyDict {
   unsigned long long *table;  // [capacity]: (code << 32) | (uint32_t)key, kDictEmpty = free
@@ -45,7 +48,7 @@ __device__ __forceinline__ void dict_insert(const KeyDict &d, int key) {
         return;
       }
     }
-    if ((int)(unsigned int)(e & 0xFFFFFFFFull) == key) return;  // present (its code may still be pending)
+    if ((int)(unsigned int)(e & 0xFFFFFFFFull) == key && (unsigned int)(e >> 32) != 0xFFFFFFFFu) return;  // present (its code may still be pending)
   }
 }
 
@@ -56,7 +59,7 @@ __device__ __forceinline__ int dict_lookup(const KeyDict &d, int key) {
   for (unsigned long long probe = 0; probe < d.capacity; probe++, i = (i + 1) & mask) {
     const unsigned long long e = d.table[i];
     if (e == kDictEmpty) return -1;
-    if ((int)(unsigned int)(e & 0xFFFFFFFFull) == key) return (int)(unsigned int)(e >> 32);
+    if ((int)(unsigned int)(e & 0xFFFFFFFFull) == key && (unsigned int)(e >> 32) != 0xFFFFFFFFu) return (int)(unsigned int)(e >> 32);
   }
   return -1;
 }

@@ -300,7 +300,8 @@ struct LiftedEntry {
 __global__ void __launch_bounds__(256)
     lifted_scatter_kernel(const LiftedEntry *__restrict__ e, unsigned long long n_entries, const Layout *__restrict__ lay_g,
                           double *__restrict__ f64, unsigned long long *__restrict__ u64, int *__restrict__ err,
-                          const PairHash hash) {
+                          const PairHash hash, int group) {
+  // f64 / u64 point at the state of GROUP BY slot `group` (the hash table is partitioned by group)
   __shared__ Layout lay;
   {
     const int *src = reinterpret_cast<const int *>(lay_g);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256)
       }
       if (!lay.pairs_hashed)
         atomicAdd(u64 + lay.pair_base + lay.pair_off[k * m + l] + sk * lay.dom[l] + sl, (unsigned long long)llrintf(x.value));
-      else if (!pair_hash_add(hash, 0, pair_key(k * m + l, sk, sl), (unsigned long long)llrintf(x.value)))
+      else if (!pair_hash_add(hash, group, pair_key(k * m + l, sk, sl), (unsigned long long)llrintf(x.value)))
         atomicExch(err, 3);
     }
   }

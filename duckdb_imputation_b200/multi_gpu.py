@@ -1,10 +1,14 @@
-"""Multi-GPU plumbing of the aggregate: one process per GPU over torch.distributed.
+"""Multi-GPU plumbing of the aggregate: one process per GPU.
 
 Rows are range-partitioned; every rank aggregates its slice into a dense state with the SAME
-categorical domain; one all-reduce (SUM) of the two state arrays (fp64 sums, int64 counts) yields the
-global triple on every rank -- the GPU twin of Triple::SumStateCombine across DuckDB threads
-(sum_state.cpp:10-114).  Works with the nccl backend on device tensors and with gloo on CPU
-tensors (the CPU tests drive the same functions with oracle-produced partials).
+categorical domain; one all-reduce (SUM) of the state (fp64 sums, u64 counts) yields the global triple on
+every rank -- the GPU twin of Triple::SumStateCombine across DuckDB threads (sum_state.cpp:10-114).
+
+On GPUs the exchange is INSIDE the C ABI: `Communicator` creates an ncclComm_t through cfb_nccl_comm_create
+(the 128-byte id travels over torch.distributed, the only thing Python contributes) and
+`allreduce_context` is one call to cfb_ctx_allreduce -- export, collective and import happen in the library,
+in place, stream-ordered.  The torch.distributed functions below (`agree_domain`, `allreduce_dense`) are the
+same host logic on CPU tensors for the gloo tests, which drive it with oracle-produced partials.
 """
 from __future__ import annotations
 
@@ -42,11 +46,58 @@ def allreduce_dense(f64: torch.Tensor, i64: torch.Tensor):
     return f64, i64
 
 
-def allreduce_context(ctx, f64_buf: torch.Tensor, i64_buf: torch.Tensor, stream: int = 0):
-    """Replace the context's state by the sum over ranks (device buffers sized by ctx.partial_sizes())."""
-    ctx.export_partial(f64_buf, i64_buf, stream=stream)
-    allreduce_dense(f64_buf, i64_buf)
-    ctx.import_partial(f64_buf, i64_buf, stream=stream)
+class Communicator:
+    """An ncclComm_t owned by the C library (one per process / GPU).  Rank 0 draws the NCCL unique id, the id is
+    broadcast over the already-initialised torch.distributed group, every rank joins."""
+
+    def __init__(self, device: int):
+        import ctypes as C
+        from . import _native as nat
+        self._nat = nat
+        self.device = device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        buf = (C.c_char * 128)()
+        if self.rank == 0:
+            nat.check(nat.lib().cfb_nccl_unique_id(buf))
+        box = [bytes(buf)]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        self._h = C.c_void_p()
+        nat.check(nat.lib().cfb_nccl_comm_create(device, self.world, self.rank, ident, C.byref(self._h)))
+
+    @property
+    def handle(self) -> int:
+        return self._h.value
+
+    def agree_domain(self, lo, hi, stream: int = 0):
+        """Element-wise global [min lo, max hi] over the ranks (cfb_nccl_agree_domain)."""
+        import ctypes as C
+        m = len(lo)
+        a = (C.c_int32 * max(1, m))(*lo)
+        b = (C.c_int32 * max(1, m))(*hi)
+        self._nat.check(self._nat.lib().cfb_nccl_agree_domain(self._h, self.device, a, b, m, stream or None))
+        return list(a)[:m], list(b)[:m]
+
+    def close(self):
+        if self._h:
+            self._nat.lib().cfb_nccl_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def allreduce_context(ctx, comm: "Communicator", stream: int = None):
+    """Replace the context's state by the sum over ranks: ONE call into the library (cfb_ctx_allreduce), stream-ordered
+    on `stream` -- default: torch's current stream, the one the caller's scans and events are on."""
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    ctx.allreduce(comm.handle, stream=stream)
 
 
 # ---- dense partial layout on the host (mirror of csrc/state_layout.h) -----------------------

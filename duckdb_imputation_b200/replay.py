@@ -44,12 +44,40 @@ class Replay:
         l.replay_predict.restype = C.c_int
         l.replay_predict.argtypes = [C.c_char_p, P, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(P),
                                      C.POINTER(P), P, C.c_size_t, C.c_size_t, P]
+        l.replay_set_option.restype = C.c_int
+        l.replay_set_option.argtypes = [C.c_char_p, C.c_int]
+        l.replay_load_via_entry_points.restype = C.c_int
+        l.replay_load_via_entry_points.argtypes = [C.POINTER(C.c_char_p)]
         l.replay_free.argtypes = [P]
         l.replay_last_error.restype = C.c_char_p
         l.replay_list_functions.restype = P
         l.replay_implementation.restype = C.c_char_p
         self.lib = l
         self.last_seconds = 0.0
+
+    def options(self, **kw):
+        """Context manager: shapes of DuckDB's protocol a plain scan does not produce (replay_host.h,
+        replay_set_option): no_simple, lift_shape, split_states, parallel_finalize."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            try:
+                for k, v in kw.items():
+                    if self.lib.replay_set_option(k.encode(), int(v)):
+                        raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+                yield self
+            finally:
+                self.lib.replay_set_option(b"reset", 0)
+        return cm()
+
+    def load_via_entry_points(self):
+        """duckdb_imputation_init() on a fresh catalog -> (number of registered functions, version string)."""
+        v = C.c_char_p()
+        n = self.lib.replay_load_via_entry_points(C.byref(v))
+        if n < 0:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        return n, (v.value or b"").decode()
 
     @property
     def implementation(self) -> str:

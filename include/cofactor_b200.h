@@ -8,7 +8,7 @@
  * aggregate callbacks -- so every entry point below cites the reference
  * callback (file:line under /root/reference/duckdb_extension/src) whose work it
  * replaces.  The DuckDB-side glue that binds them lives in
- * duckdb_imputation_b200/csrc/duckdb_glue.cpp and is described in INTEGRATION.md.
+ * duckdb_imputation_b200/csrc/host/{triple,lift,mul,predict}_glue.cpp and is described in INTEGRATION.md.
  *
  * Conventions
  *   - plain C, POD arguments, no torch / DuckDB / CUDA types in any signature
@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CFB_ABI_VERSION 1
+#define CFB_ABI_VERSION 2
 
 typedef enum cfb_status {
   CFB_OK = 0,
@@ -131,6 +131,14 @@ int cfb_ctx_append_triples(cfb_ctx *ctx, size_t count, const int32_t *N, const f
                            const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
                            const float *cc_val);
 
+/* Same, into GROUP BY slot `slot` of the context (sum_triple ... GROUP BY: the states of a worker thread share
+ * one context, like the states of the sum_to_triple aggregates).                                       */
+int cfb_ctx_append_triples_slot(cfb_ctx *ctx, int slot, size_t count, const int32_t *N, const float *lin,
+                                const float *quad, const cfb_list_entry *lin_cat_lists, const int32_t *lc_key,
+                                const float *lc_val, const cfb_list_entry *num_cat_lists, const int32_t *nc_key,
+                                const float *nc_val, const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1,
+                                const int32_t *cc_key2, const float *cc_val);
+
 /* Drain the context's streams; surfaces asynchronous kernel errors. */
 int cfb_ctx_sync(cfb_ctx *ctx);
 
@@ -141,7 +149,9 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src);
 
 /* Same for individual GROUP BY slots: dst[dst_slots[i]] += src[src_slots[i]], i < n_pairs; all other
  * slots of both contexts are untouched (n_groups may differ).  This is what the DuckDB glue calls when
- * the thread-local hash tables are merged: one context holds all groups of a worker thread.   */
+ * the thread-local hash tables are merged: one context holds all groups of a worker thread.
+ * dst == src is allowed (two states of one thread's context: a group that the radix-partitioned hash
+ * aggregate emitted twice); then no slot may be source and target in the same call.            */
 int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src, size_t n_pairs, const int32_t *dst_slots,
                           const int32_t *src_slots);
 
@@ -224,6 +234,25 @@ int cfb_ctx_partial_sizes(cfb_ctx *ctx, size_t *n_f64, size_t *n_u64);
 int cfb_ctx_export_partial(cfb_ctx *ctx, void *d_f64, void *d_u64, void *stream);
 int cfb_ctx_import_partial(cfb_ctx *ctx, const void *d_f64, const void *d_u64, void *stream);
 
+/* The exchange step itself, inside the library ("one NCCL reduce", mirroring SumStateCombine,
+ * sum_state.cpp:23-112, across GPUs): SUM-all-reduce of the context's dense state IN PLACE over `nccl_comm`
+ * (an ncclComm_t) -- the fp64 sums and the u64 counts as one fused NCCL group, stream-ordered on `stream`
+ * (cudaStream_t; NULL = the context's stream, then the call returns when done).  Every rank must have
+ * declared the same categorical domain (cfb_nccl_agree_domain + cfb_ctx_set_cat_domain) and the same
+ * n_groups.  NCCL is resolved from libnccl.so.2 at first use (CFB_NCCL_LIB overrides the name); the library
+ * itself does not link it.  CFB_ERR_STATE when NCCL cannot be loaded.                                     */
+int cfb_ctx_allreduce(cfb_ctx *ctx, void *nccl_comm, void *stream);
+
+/* Communicator plumbing for hosts that do not link NCCL themselves (one process per GPU): rank 0 asks for an
+ * id, ships the 128 bytes to the other ranks by any channel, every rank creates its communicator.         */
+#define CFB_NCCL_UNIQUE_ID_BYTES 128
+int cfb_nccl_unique_id(void *id128);
+int cfb_nccl_comm_create(int device, int world, int rank, const void *id128, void **nccl_comm_out);
+int cfb_nccl_comm_destroy(void *nccl_comm);
+/* Element-wise global [min lo, max hi] of per-rank key ranges (host arrays, in place): the domain agreement
+ * that precedes a categorical multi-GPU scan.                                                              */
+int cfb_nccl_agree_domain(void *nccl_comm, int device, int32_t *lo, int32_t *hi, int n_cat, void *stream);
+
 /* Observed [min,max] of each categorical column over device-resident input
  * (device pre-pass; used to agree domains across ranks before the scan).      */
 int cfb_cat_minmax_device(int device, const int32_t *const *d_cat_cols, int n_cat, size_t n_rows,
@@ -284,6 +313,13 @@ int cfb_gen_int32(int device, int32_t *d_out, size_t n, uint64_t seed, uint64_t 
 uint64_t cfb_kernel_launches(void);
 int cfb_set_timing(int enabled);
 double cfb_last_scan_ms(cfb_ctx *ctx);
+
+/* The host half of the feed (cfb_ctx_append stages DuckDB vectors with non-temporal stores): which vector ISA
+ * the staging copy picked on this CPU ("avx512" / "avx2" / "sse2"), and the host-memory ceiling of that copy on
+ * this box -- `threads` threads copying private `bytes_per_thread` buffers in 8 KB pieces, aggregate GB/s of
+ * payload (nt = 1: the staging copy, nt = 0: memcpy).  bench.py quotes it beside the end-to-end number.   */
+const char *cfb_stage_isa(void);
+double cfb_host_copy_ceiling(size_t bytes_per_thread, int threads, int nt, int reps);
 
 #ifdef __cplusplus
 }

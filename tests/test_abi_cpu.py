@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version_and_result_layout():
-    assert nat.lib().cfb_abi_version() == 1
+    assert nat.lib().cfb_abi_version() == 2
     # cfb_result: 3 x int32 (+pad) then 14 eight-byte fields
     assert C.sizeof(nat.Result) == 16 + 14 * 8
 

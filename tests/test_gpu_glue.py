@@ -157,3 +157,112 @@ def test_multiply_over_gpu_aggregates(goldens):
                         [np.repeat(c, rb) for c in Ac] + [np.tile(c, ra) for c in Bc])
         prod["lin_agg"], prod["quad_agg"] = prod.pop("lin_num"), prod.pop("quad_num")
         assert prod == whole
+
+
+# ---------------------------------------------------------------- protocol shapes a plain scan does not produce
+def _small_table(seed, rows, n=4, m=2):
+    rng = np.random.default_rng(seed)
+    num = [rng.integers(0, 9, rows).astype(np.float32) for _ in range(n)]  # small ints: fp sums exact in any order
+    cat = [rng.integers(-3, 9, rows).astype(np.int32) for _ in range(m)]
+    return rng, num, cat
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_simple_update_equals_the_hash_aggregate_protocol(kind):
+    """Ungrouped queries go through simple_update (PhysicalUngroupedAggregate: one state per thread, no per-row state
+    pointers), which the reference leaves null (ext.cpp:53,106); the result equals the update() protocol's."""
+    _, num, cat = _small_table(31, 70_001)
+    g = replay.glue()
+    for lifted in (False, True):
+        fast = g.query(kind, num, cat, threads=3, lifted=lifted)
+        with g.options(no_simple=1):
+            slow = g.query(kind, num, cat, threads=3, lifted=lifted)
+        assert fast == slow
+        assert_struct_parity(fast, oracle.aggregate(kind, num, cat), what=f"simple_update kind {kind} lifted {lifted}")
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_sum_triple_over_non_flat_struct_vectors(kind, shape):
+    """the reference flattens the argument of sum_triple / sum_nb_agg (sum.cpp:72 ->
+    utils.cpp:3-18) because a join or filter below the aggregate hands over DICTIONARY / CONSTANT vectors.
+    shape 1: DICTIONARY STRUCT; 2: flat STRUCT with DICTIONARY children and leaves; 3: CONSTANT STRUCT (the
+    chunk's first lifted row for every row of the chunk -- a CROSS JOIN side)."""
+    rng, num, cat = _small_table(32 + shape, 9_000)
+    gb = rng.integers(0, 3, len(num[0]))
+    g = replay.glue()
+    with g.options(lift_shape=shape, no_simple=1):
+        got = g.query(kind, num, cat, group_by=gb, threads=2, lifted=True)
+        got1 = g.query(kind, num, cat, threads=2, lifted=True)
+    if shape == 3:
+        first = (np.arange(len(num[0])) // 2048) * 2048  # every row of a chunk carries the chunk's first row
+        num, cat = [c[first] for c in num], [c[first] for c in cat]
+    ref = oracle.aggregate(kind, num, cat, group_by=gb)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert_struct_parity(a, b, what=f"kind {kind} shape {shape}")
+    assert_struct_parity(got1, oracle.aggregate(kind, num, cat), what=f"ungrouped kind {kind} shape {shape}")
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+def test_multiply_over_non_flat_struct_vectors(shape):
+    """mul.cpp:24-28 flattens both arguments; here they are read in place whatever their shape."""
+    g = replay.glue()
+    rng = np.random.default_rng(40 + shape)
+    rows = 5
+    A, B = [], []
+    for r in range(rows):
+        ra, rb = 50 + r, 20 + 3 * r
+        A.append(g.query(0, [rng.integers(0, 6, ra).astype(np.float32) for _ in range(2)], [rng.integers(0, 3 + r, ra).astype(np.int32)]))
+        B.append(g.query(0, [rng.integers(0, 6, rb).astype(np.float32)], [rng.integers(5, 7 + r, rb).astype(np.int32) for _ in range(2)]))
+    flat = g.scalar_structs("multiply_triple", A, B)
+    with g.options(lift_shape=shape):
+        got = g.scalar_structs("multiply_triple", A, B)
+    if shape == 3:  # the last argument is a CONSTANT vector: its first row for every row
+        flat = g.scalar_structs("multiply_triple", A, [B[0]] * rows)
+    assert got == flat
+
+
+@pytest.mark.parametrize("kind,n,m", [(0, 4, 2), (1, 3, 1), (0, 5, 0)])
+def test_two_states_of_one_group_in_one_thread_are_merged(kind, n, m):
+    """DuckDB's radix-partitioned hash aggregate can emit a group twice from one thread (hash table reset when
+    full) and combine the two states: both live in the SAME arena (context).  split_states = 3: every worker keeps
+    three state sets per group and merges them itself."""
+    rng, num, cat = _small_table(50 + n, 60_000, n, m)
+    gb = rng.integers(0, 5, len(num[0]))
+    g = replay.glue()
+    with g.options(split_states=3):
+        got = g.query(kind, num, cat, group_by=gb, threads=2)
+        got1 = g.query(kind, num, cat, threads=2)
+    for a, b in zip(got, oracle.aggregate(kind, num, cat, group_by=gb)):
+        assert_struct_parity(a, b, what=f"split states kind {kind}")
+    assert_struct_parity(got1, oracle.aggregate(kind, num, cat), what="split states, ungrouped")
+
+
+@pytest.mark.parametrize("kind,n,m", [(0, 4, 2), (1, 6, 2)])
+def test_parallel_combine_and_finalize_of_one_arena(kind, n, m):
+    """DuckDB finalizes the radix partitions of a hash aggregate in parallel: SumStateCombine / SumStateFinalize run
+    concurrently for DIFFERENT groups whose states share the workers' arenas (one cfb_ctx each).  Four threads
+    combine + finalize disjoint groups at once; the arena lock serialises the contexts."""
+    rng, num, cat = _small_table(60 + n, 200_000, n, m)
+    gb = rng.integers(0, 24, len(num[0]))
+    g = replay.glue()
+    ref = oracle.aggregate(kind, num, cat, group_by=gb)
+    for _ in range(3):
+        with g.options(parallel_finalize=4):
+            got = g.query(kind, num, cat, group_by=gb, threads=4)
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert_struct_parity(a, b, what=f"parallel finalize kind {kind}")
+
+
+def test_sum_triple_group_by_shares_one_arena_per_thread():
+    """sum_triple ... GROUP BY with hundreds of groups: the states of a worker thread are slots of shared contexts
+    (round 1 gave every group a private context + stream)."""
+    rng, num, cat = _small_table(70, 30_000, 3, 1)
+    gb = rng.integers(0, 300, len(num[0]))
+    got = replay.glue().query(0, num, cat, group_by=gb, threads=2, lifted=True)
+    ref = oracle.aggregate(0, num, cat, group_by=gb)
+    assert len(got) == len(ref) == 300
+    for a, b in zip(got, ref):
+        assert_struct_parity(a, b, what="sum_triple GROUP BY 300")

@@ -62,7 +62,8 @@ def test_whole_suite_with_hashed_pairs_forced():
 
 def _wide_table(rng, rows):
     num = [rng.random(rows).astype(np.float32) for _ in range(3)]
-    pool = np.array([-2_000_000_000, -7, 0, 3, 65_536, 1_999_999_999, 2_147_483_647, -2_147_483_648], np.int64)
+    # -1 is in the pool on purpose: (pending, key = -1) must not look like a free dictionary slot (key_dict.cuh)
+    pool = np.array([-2_000_000_000, -7, -1, 0, 3, 65_536, 1_999_999_999, 2_147_483_647, -2_147_483_648], np.int64)
     cat = [pool[rng.integers(0, len(pool), rows)].astype(np.int32),                     # ids all over int32
            rng.integers(0, 6, rows).astype(np.int32),                                    # ordinary small column
            (rng.integers(0, 300, rows).astype(np.int64) * 7_000_003 - 1_000_000_000).astype(np.int32)]
