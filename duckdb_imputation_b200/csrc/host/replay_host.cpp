@@ -496,16 +496,20 @@ int replay_aggregate(const char *function, const char *scalar, int n_num, int n_
               if (opt.lift_shape == 1) {
                 one[0].Slice(SelectionVector(rev.data()));
               } else {
+                size_t leaf_rows = 0;  // size the identity selection first: the slices keep pointers into it
+                for (auto &kid : StructVector::GetEntries(one[0]))
+                  if (kid->GetType().id() == LogicalTypeId::LIST && ListVector::GetEntry(*kid).GetType().id() == LogicalTypeId::LIST)
+                    leaf_rows = std::max<size_t>(leaf_rows, ListVector::GetListSize(ListVector::GetEntry(*kid)));
+                if (leaf_rows > ident.size()) {
+                  const size_t old = ident.size();
+                  ident.resize(leaf_rows);
+                  for (size_t i = old; i < ident.size(); i++) ident[i] = (sel_t)i;
+                }
                 for (auto &kid : StructVector::GetEntries(one[0])) {
                   kid->Slice(SelectionVector(rev.data()));
                   if (kid->GetType().id() != LogicalTypeId::LIST) continue;
                   Vector &el = ListVector::GetEntry(*kid);
                   if (el.GetType().id() != LogicalTypeId::LIST) continue;
-                  if (ListVector::GetListSize(el) > ident.size()) {
-                    const size_t old = ident.size();
-                    ident.resize(ListVector::GetListSize(el));
-                    for (size_t i = old; i < ident.size(); i++) ident[i] = (sel_t)i;
-                  }
                   for (auto &leaf : StructVector::GetEntries(ListVector::GetEntry(el))) leaf->Slice(SelectionVector(ident.data()));
                 }
               }
