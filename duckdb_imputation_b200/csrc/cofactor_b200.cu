@@ -38,6 +38,8 @@
 #include "slot_gram_kernel.cuh"
 #include "bucket_kernels.cuh"
 #include "bucket_launch.h"
+#include "chain_kernels.cuh"
+#include "chain_launch.h"
 #include "role_kernels.cuh"
 #include "role_launch.h"
 #include "slab_launch.h"
@@ -181,6 +183,13 @@ struct cfb_ctx {
   float *d_slab = nullptr;
   long long slab_floats = 0;  // per CTA
   int slab_grid = 0;
+  // chain_sum_kernel: per-CTA count slabs (all zero between launches) and the packed one-byte slots it hands to
+  // pair_packed_kernel
+  unsigned *d_cnt_slab = nullptr;
+  long long cnt_slab_words = 0;  // per CTA
+  int cnt_slab_grid = 0;
+  unsigned char *d_packed = nullptr;
+  size_t packed_cap = 0;
   // role plan of role_scan_kernel (shared-memory pair tables), rebuilt when the domains change
   cfb::RolePlan *role_plan = nullptr;  // host copy; travels in the kernel parameters
   int role_state = 0;  // 0: no plan for the current domains yet, 1: plan valid, -1: shape does not fit
@@ -669,6 +678,12 @@ constexpr std::array<cudaError_t (*)(const cfb::BucketLaunchParams &), sizeof...
 }
 const auto kBucket = bucket_table(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
 
+template <int... Ns>
+constexpr std::array<cudaError_t (*)(const cfb::ChainLaunchParams &), sizeof...(Ns)> chain_table(std::integer_sequence<int, Ns...>) {
+  return {{cfb::chain_launch<Ns>...}};
+}
+const auto kChain = chain_table(std::make_integer_sequence<int, CFB_MAX_NUM + 1>{});
+
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -788,6 +803,88 @@ int launch_bucket(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, 
   return CFB_OK;
 }
 
+// Key counts + per-key sums through per-bucket linked lists in shared memory (chain_kernels.cuh); with `packed` the
+// kernel also writes the validated one-byte slots of every row for pair_packed_kernel.  Returns 1 if the shape does
+// not qualify, 0 on success, <0 on error.
+int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, unsigned char *packed, unsigned long long packed_stride,
+                 cudaStream_t s) {
+  if (c->kind != CFB_TRIPLE || c->m < 1 || getenv("CFB_NO_CHAIN") || getenv("CFB_NO_BUCKET")) return 1;
+  const long long D = c->lay.total_dom * c->G;
+  if (D > cfb::kChainMaxHeads || D < 1) return 1;
+  const int QT = std::max(1, cfb::chain_quads(c->n));
+  int sub_shift = 0;
+  while ((D << (sub_shift + 1)) <= cfb::kChainMaxHeads && (D << sub_shift) * QT < 2048) sub_shift++;
+  if (const char *e = getenv("CFB_CHAIN_SUB_SHIFT")) sub_shift = std::max(0, std::min(atoi(e), 12));
+  while ((D << sub_shift) > cfb::kChainMaxHeads) sub_shift--;
+  const int heads = (int)(D << sub_shift);
+  // kChainCtasPerSm CTAs share an SM: each gets its share of the SM's shared memory (1 KB per CTA is the system's)
+  const long long cta_smem = std::min<long long>(dev_info(c->device).smem_optin - 1024,
+                                                 (long long)dev_info(c->device).smem_sm / cfb::kChainCtasPerSm - 1024 - 512);
+  const long long budget = cta_smem - 4ll * heads - ((c->lay.total_dom + 15) & ~15ll);
+  const int per_row = (c->n ? cfb::chain_quad_stride(c->n) * 16 : 0) + 2 * c->m;
+  int tile = (int)std::min<long long>(budget / per_row, 32768);
+  tile = tile >= 2 * cfb::kChainThreads ? tile / cfb::kChainThreads * cfb::kChainThreads : tile / 256 * 256;
+  if (const char *e = getenv("CFB_CHAIN_TILE")) tile = std::min(tile, std::max(256, atoi(e) / 32 * 32));
+  if (tile < 512) return 1;
+  const unsigned long long n_tiles = (rows + tile - 1) / tile;
+  const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * cfb::kChainCtasPerSm, n_tiles);
+  int rc = ensure_slab(c, D * 4 * cfb::chain_quads(c->n), grid, s);
+  if (rc) return rc;
+  if (D != c->cnt_slab_words || grid > c->cnt_slab_grid) {
+    if (c->d_cnt_slab) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
+      cudaFree(c->d_cnt_slab);
+      c->d_cnt_slab = nullptr;
+    }
+    const int alloc_grid = std::max(grid, c->cnt_slab_grid);
+    CU(cudaMalloc(&c->d_cnt_slab, (size_t)D * alloc_grid * sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->d_cnt_slab, 0, (size_t)D * alloc_grid * sizeof(unsigned), s));
+    c->cnt_slab_words = D;
+    c->cnt_slab_grid = alloc_grid;
+  }
+  cfb::ChainLaunchParams p{};
+  p.cols = sc;
+  p.lay = &c->lay;
+  p.rows = rows;
+  p.tile_rows = tile;
+  p.fold_tiles = std::max(1, 32768 / tile);  // an fp32 slab entry is folded into fp64 after at most ~32K rows of one CTA
+  p.sub_shift = sub_shift;
+  p.grid = grid;
+  p.smem_max = dev_info(c->device).smem_optin - 1024;
+  p.smem_bytes = cfb::chain_smem_bytes(c->n, c->m, heads, (int)c->lay.total_dom, tile);
+  p.slab = c->d_slab;
+  p.cnt_slab = c->d_cnt_slab;
+  p.f64 = c->d_f64;
+  p.u64 = c->d_u64;
+  p.err = c->d_err;
+  p.packed = packed;
+  p.packed_stride = packed_stride;
+  p.stream = s;
+  const cudaError_t e = kChain[c->n](p);
+  g_launches++;
+  if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "chain kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+// Room for `cols` packed one-byte columns of `rows` rows (column stride returned in *stride).
+int ensure_packed(cfb_ctx *c, int cols, unsigned long long rows, unsigned long long *stride) {
+  *stride = (rows + 255) & ~255ull;
+  const size_t need = (size_t)cols * *stride;
+  if (need > c->packed_cap) {
+    if (c->d_packed) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
+      cudaFree(c->d_packed);
+      c->d_packed = nullptr;
+      c->packed_cap = 0;
+    }
+    CU(cudaMalloc(&c->d_packed, need));
+    c->packed_cap = need;
+  }
+  return CFB_OK;
+}
+
 // Key counts of the Naive-Bayes ring through a shared-memory histogram.  1 = shape does not qualify.
 int launch_key_count(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
   if (c->kind != CFB_NB || c->m < 1 || getenv("CFB_NO_BUCKET")) return 1;
@@ -896,6 +993,39 @@ int launch_role(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, bo
   const cudaError_t e = (c->role_bits == 16 ? kRole16 : kRole32)[c->n](p);
   g_launches++;
   if (e != cudaSuccess) return fail(CFB_ERR_CUDA, "role kernel launch (n=%d): %s", c->n, cudaGetErrorString(e));
+  return CFB_OK;
+}
+
+// Pair counts from the packed slots chain_sum_kernel wrote (call role_prepare first: same plan, roles and replicas).
+int launch_pair_packed(cfb_ctx *c, unsigned long long rows, const unsigned char *packed, unsigned long long stride, bool grouped,
+                       cudaStream_t s) {
+  const int n_reps = std::max(1, dev_info(c->device).sms / c->role_roles);
+  const unsigned long long rows16 = grouped ? (rows + 15) & ~15ull : rows & ~15ull;  // rows done in 16-row groups
+  const int step = 16 * cfb::kRoleThreads;  // rows of one pass of the CTA over a chunk
+  // 16-bit cells are folded after every chunk (<= 65024 rows); 32-bit cells once, at the end of the scan
+  const int max_steps = c->role_bits == 16 ? 3 : 4;
+  long long chunk = (long long)((rows16 + n_reps - 1) / n_reps);
+  chunk = std::min<long long>((long long)max_steps * step, std::max<long long>(step, (chunk + step - 1) / step * step));
+  cfb::PackedPairArgs a{};
+  a.packed = packed;
+  a.stride = stride;
+  a.n_rows = grouped ? rows16 : rows;
+  a.chunk_rows = (int)chunk;
+  a.pair_fold_chunks = c->role_bits == 16 ? 1 : 1 << 30;
+  a.n_reps = n_reps;
+  a.m = c->m;
+  a.n_groups = c->G;
+  a.U = c->lay.U;
+  a.pair_base = c->lay.pair_base;
+  a.u64 = c->d_u64;
+  a.plan = *c->role_plan;
+  const int smem_max = dev_info(c->device).smem_optin - 1024;
+  auto kern = c->role_bits == 16 ? (grouped ? cfb::pair_packed_kernel<16, true> : cfb::pair_packed_kernel<16, false>)
+                                 : (grouped ? cfb::pair_packed_kernel<32, true> : cfb::pair_packed_kernel<32, false>);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  kern<<<c->role_roles * n_reps, cfb::kRoleThreads, c->role_smem, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
   return CFB_OK;
 }
 
@@ -1105,6 +1235,8 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     const bool hashed = c->lay.pairs_hashed && npairs > 0;
     unsigned long long slice = rows;
     if (hashed) slice = std::max<unsigned long long>(1ull << 18, ((1ull << 24) / npairs) & ~1023ull);
+    else if (c->kind == CFB_TRIPLE && c->m >= 2)  // bounds the packed-slot scratch of the pair kernel ((m+1) bytes per row)
+      slice = std::max<unsigned long long>(1ull << 20, (unsigned long long)env_int("CFB_CAT_SLICE_ROWS", 32 << 20) & ~16383ull);
     for (unsigned long long r0 = 0; r0 < rows; r0 += slice) {
       const unsigned long long cnt = std::min(slice, rows - r0);
       cfb::ScanCols part = sc;
@@ -1126,6 +1258,24 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
         // dense small domains: pair counts in shared-memory tables, per-key sums by tile bucketing
         const bool pairs_here = role_prepare(c, part, cnt) == 0;
         if (pairs_here || (c->m == 1 && c->kind == CFB_TRIPLE)) {
+          // second generation: per-bucket lists (no second ranking pass) + pair counts from packed one-byte slots
+          bool pack = pairs_here && c->G <= 255 && !getenv("CFB_NO_PACKED");
+          for (int k = 0; k < c->m && pack; k++) pack = c->lay.dom[k] <= 255;
+          unsigned long long stride = 0;
+          if (pack) {
+            const int rc = ensure_packed(c, c->m + (group ? 2 : 0), cnt, &stride);
+            if (rc) return rc;
+          }
+          const int ch = launch_chain(c, part, cnt, pack ? c->d_packed : nullptr, stride, s);
+          if (ch < 0) return ch;
+          if (ch == 0) {
+            if (pairs_here) {
+              const int rc = pack ? launch_pair_packed(c, cnt, c->d_packed, stride, group != nullptr, s)
+                                  : launch_role(c, part, cnt, /*do_sums=*/false, s);
+              if (rc < 0) return rc;
+            }
+            continue;
+          }
           const int b = launch_bucket(c, part, cnt, s);
           if (b < 0) return b;
           if (pairs_here && (b == 0 || c->G == 1)) {  // (the role kernel's own payload path has single-slot slabs)
@@ -1546,6 +1696,11 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   c->cur = 0;
   c->uses_group = false;
   c->user_stream = nullptr;
+  if (c->packed_cap > (64u << 20)) {  // a parked context keeps small scratch only
+    cudaFree(c->d_packed);
+    c->d_packed = nullptr;
+    c->packed_cap = 0;
+  }
   // recycle: zero the state (its layout, i.e. the categorical domain seen so far, is kept: keys
   // that do not occur again have count 0 and are not emitted) and park the context
   const long long state_bytes = (c->lay.F + c->lay.U) * c->lay.n_groups * 8;
@@ -1568,6 +1723,8 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);
+  cudaFree(c->d_cnt_slab);
+  cudaFree(c->d_packed);
   delete c->role_plan;
   if (c->hash.capacity) hash_free(c->hash);
   for (auto &cd : c->dict)
