@@ -36,6 +36,7 @@
 #include "predict_kernel.cuh"
 #include "slab_kernels.cuh"
 #include "slot_gram_kernel.cuh"
+#include "slot_block_kernel.cuh"
 #include "bucket_kernels.cuh"
 #include "bucket_launch.h"
 #include "chain_kernels.cuh"
@@ -1093,9 +1094,69 @@ int launch_slot_gram_e(cfb_ctx *c, const cfb::SlotGramArgs &a, size_t smem, int 
   return CFB_OK;
 }
 
+// Few slots: bulk-copy fetch, atomic-rank sort and 4x4 register blocks + FFMA2 over the slot-sorted tile
+// (slot_block_kernel.cuh).  1 = the shape does not qualify (more (slot, block) lane tasks than a CTA has lanes).
+template <bool NB>
+int launch_slot_block_k(cfb_ctx *c, const cfb::SlotBlockArgs &a, size_t smem, int grid, cudaStream_t s) {
+  auto kern = cfb::slot_block_kernel<NB>;
+  static std::once_flag once[64];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[c->device & 63], [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info(c->device).smem_optin - 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(CFB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  kern<<<grid, cfb::kSlotThreads, smem, s>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return CFB_OK;
+}
+
+int launch_slot_block(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+  if (c->n > 31 || getenv("CFB_NO_SLOT_BLOCK")) return 1;  // (n + 1 columns are fetched by one warp)
+  const bool nb_ring = c->kind == CFB_NB;
+  const int nblk = cfb::slotb_blocks(c->n, nb_ring);
+  if (c->G * nblk > cfb::kSlotThreads) return 1;
+  if (!sc.group || ((uintptr_t)sc.group & 15)) return 1;  // the tile is fetched with 16-byte bulk copies
+  int steps = 0, per_sm = 1;
+  for (int want : {2, 1}) {
+    const size_t budget = want == 1 ? (size_t)dev_info(c->device).smem_optin - 1024
+                                    : (size_t)(dev_info(c->device).smem_sm - 1024 * want) / want - 512;
+    int st = cfb::kSlotMaxSteps;
+    while (st >= 1 && cfb::slotb_smem_bytes(c->n, c->G, st) > budget) st--;
+    if (st >= (want == 1 ? 1 : 2)) {
+      steps = st;
+      per_sm = want;
+      break;
+    }
+  }
+  if (const char *e = getenv("CFB_SLOT_STEPS")) steps = std::max(1, std::min(steps, atoi(e)));
+  if (steps < 1) return 1;
+  cfb::SlotBlockArgs a{};
+  a.cols = sc;
+  a.n_rows = rows;
+  a.n = c->n;
+  a.n_groups = c->G;
+  a.steps = steps;
+  a.splits = std::max(1, cfb::kSlotThreads / (c->G * nblk));
+  const int tile = steps * cfb::kSlotThreads;
+  a.fold_tiles = std::max(1, 32768 / tile);  // an fp32 accumulator is folded into fp64 after at most ~32K rows of one CTA
+  a.F = c->lay.F;
+  a.U = c->lay.U;
+  a.f64 = c->d_f64;
+  a.u64 = c->d_u64;
+  a.err = c->d_err;
+  const size_t smem = cfb::slotb_smem_bytes(c->n, c->G, steps);
+  const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm, (rows + tile - 1) / tile);
+  return nb_ring ? launch_slot_block_k<true>(c, a, smem, grid, s) : launch_slot_block_k<false>(c, a, smem, grid, s);
+}
+
 int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
   if (getenv("CFB_NO_SLOT_GRAM") || c->n < 1 || c->G > cfb::kSlotMaxGroups) return 1;
   if (rows < (unsigned long long)std::max(1, env_int("CFB_SLOT_MIN_ROWS", 8192))) return 1;
+  {
+    const int rc = launch_slot_block(c, sc, rows, s);
+    if (rc <= 0) return rc;
+  }
   // 2x2 blocks of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows.  A warp carries
   // two tasks when E == 1 (8 accumulators per block and task).
   const int V = cfb::slot_blocks(c->n, c->kind);
