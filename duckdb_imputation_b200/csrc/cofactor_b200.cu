@@ -1111,9 +1111,18 @@ int launch_slot_block_k(cfb_ctx *c, const cfb::SlotBlockArgs &a, size_t smem, in
   return CFB_OK;
 }
 
-int launch_slot_block(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+int launch_slot_block(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s, bool *keys_done) {
+  *keys_done = false;
   if (c->n > 31 || getenv("CFB_NO_SLOT_BLOCK")) return 1;  // (n + 1 columns are fetched by one warp)
   const bool nb_ring = c->kind == CFB_NB;
+  // Naive-Bayes ring: the key counts ride along when their columns fit the fetch warp and the histogram stays small
+  int fuse_m = 0;
+  if (nb_ring && c->m > 0 && c->n + 1 + c->m <= 32 && c->lay.total_dom * c->G * 4 <= 32768 && !getenv("CFB_NO_NB_FUSE")) {
+    fuse_m = c->m;
+    for (int k = 0; k < c->m; k++)
+      if ((uintptr_t)sc.cat[k] & 15) fuse_m = 0;
+  }
+  const int td = fuse_m ? (int)c->lay.total_dom : 0;
   const int nblk = cfb::slotb_blocks(c->n, nb_ring);
   if (c->G * nblk > cfb::kSlotThreads) return 1;
   if (!sc.group || ((uintptr_t)sc.group & 15)) return 1;  // the tile is fetched with 16-byte bulk copies
@@ -1122,7 +1131,7 @@ int launch_slot_block(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long ro
     const size_t budget = want == 1 ? (size_t)dev_info(c->device).smem_optin - 1024
                                     : (size_t)(dev_info(c->device).smem_sm - 1024 * want) / want - 512;
     int st = cfb::kSlotMaxSteps;
-    while (st >= 1 && cfb::slotb_smem_bytes(c->n, c->G, st) > budget) st--;
+    while (st >= 1 && cfb::slotb_smem_bytes(c->n, c->G, st, fuse_m, td) > budget) st--;
     if (st >= (want == 1 ? 1 : 2)) {
       steps = st;
       per_sm = want;
@@ -1145,16 +1154,25 @@ int launch_slot_block(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long ro
   a.f64 = c->d_f64;
   a.u64 = c->d_u64;
   a.err = c->d_err;
-  const size_t smem = cfb::slotb_smem_bytes(c->n, c->G, steps);
+  a.m = fuse_m;
+  a.total_dom = td;
+  for (int k = 0; k < cfb::kMaxCat; k++) {
+    a.lo[k] = c->lay.lo[k];
+    a.dom[k] = c->lay.dom[k];
+  }
+  for (int k = 0; k <= cfb::kMaxCat; k++) a.cat_off[k] = (int)c->lay.cat_off[k];
+  const size_t smem = cfb::slotb_smem_bytes(c->n, c->G, steps, fuse_m, td);
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * per_sm, (rows + tile - 1) / tile);
+  *keys_done = fuse_m > 0;
   return nb_ring ? launch_slot_block_k<true>(c, a, smem, grid, s) : launch_slot_block_k<false>(c, a, smem, grid, s);
 }
 
-int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s, bool *keys_done) {
+  *keys_done = false;
   if (getenv("CFB_NO_SLOT_GRAM") || c->n < 1 || c->G > cfb::kSlotMaxGroups) return 1;
   if (rows < (unsigned long long)std::max(1, env_int("CFB_SLOT_MIN_ROWS", 8192))) return 1;
   {
-    const int rc = launch_slot_block(c, sc, rows, s);
+    const int rc = launch_slot_block(c, sc, rows, s, keys_done);
     if (rc <= 0) return rc;
   }
   // 2x2 blocks of a slot over `parts` warps, E per lane; the remaining warps split the slot's rows.  A warp carries
@@ -1214,9 +1232,9 @@ int launch_slot_gram(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long row
   }
 }
 
-int launch_group(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s) {
+int launch_group(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, cudaStream_t s, bool *keys_done) {
   {
-    const int rc = launch_slot_gram(c, sc, rows, s);
+    const int rc = launch_slot_gram(c, sc, rows, s, keys_done);
     if (rc <= 0) return rc;
   }
   if (getenv("CFB_NO_GROUP_KERNEL")) return 1;
@@ -1284,12 +1302,13 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     g_launches++;
   }
   int slab_numeric = grouped ? 1 : 0;
+  bool keys_done = false;  // the Naive-Bayes key counts went along with the numeric part
   if (grouped) {
-    const int rc = launch_group(c, sc, rows, s);  // N / lin / quad of every slot (and the row filter)
+    const int rc = launch_group(c, sc, rows, s, &keys_done);  // N / lin / quad of every slot (and the row filter)
     if (rc < 0) return rc;
     if (rc == 0) slab_numeric = 0;
   }
-  if ((grouped && slab_numeric) || c->m > 0) {
+  if ((grouped && slab_numeric) || (c->m > 0 && !keys_done)) {
     // With hashed pair counts the scan is cut into slices so that the table can be grown
     // (host-side, between launches) before it could fill up.
     const int npairs = c->kind == CFB_TRIPLE ? c->m * (c->m - 1) / 2 : 0;

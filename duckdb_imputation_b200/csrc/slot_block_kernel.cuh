@@ -42,6 +42,11 @@ struct SlotBlockArgs {
   double *f64;
   unsigned long long *u64;
   int *err;
+  // Naive-Bayes ring only: the key counts of the m categorical columns (sum_to_nb_agg.cpp:124-145) in the same pass --
+  // their columns are fetched with the tile and counted in a shared-memory histogram over (slot, column, key),
+  // folded into the u64 state when the CTA is done (m == 0: not fused, key_count_kernel does them)
+  int m, total_dom;
+  int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];
 };
 
 // columns of the sorted tile: [x_0..x_{n-1}, zero padding] in whole blocks of 4
@@ -59,9 +64,11 @@ __host__ __device__ inline int slotb_pitch_quads(int n_groups, int steps) {
 // first quad of column c: columns r, 4 + r, 8 + r, 12 + r (what the lanes of a warp read together) get the bank
 // groups r, r + 2, r + 4, r + 6
 __host__ __device__ inline int slotb_col_quad(int c, int pitch_quads) { return c * pitch_quads + (((c & 3) + 2 * (c >> 2)) & 7); }
-// dynamic shared memory: sorted tile | raw staging [n + 1][tile rows] (column n = the slot ids)
-__host__ __device__ inline size_t slotb_smem_bytes(int n, int n_groups, int steps) {
-  return (size_t)slotb_block_cols(n) * 4 * slotb_pitch_quads(n_groups, steps) * 16 + (size_t)(n + 1) * steps * kSlotThreads * 4;
+// dynamic shared memory: sorted tile | raw staging [n + 1 + m][tile rows] (column n = the slot ids, then the m key
+// columns of a fused Naive-Bayes scan) | key histogram [n_groups * total_dom]
+__host__ __device__ inline size_t slotb_smem_bytes(int n, int n_groups, int steps, int m = 0, int total_dom = 0) {
+  return (size_t)slotb_block_cols(n) * 4 * slotb_pitch_quads(n_groups, steps) * 16 +
+         (size_t)(n + 1 + m) * steps * kSlotThreads * 4 + (size_t)(m ? n_groups * total_dom : 0) * 4;
 }
 
 struct __align__(16) SlotQuad {
@@ -85,10 +92,12 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
   const int n = a.n, G = a.n_groups, U = a.steps, PQ = slotb_pitch_quads(G, U), T = U * kSlotThreads;
   const int nb = slotb_block_cols(n), NC = 4 * nb, NBLK = NB ? nb : nb * (nb + 1) / 2;
   float *xs = slotb_smem;                       // [NC] columns of PQ quads, skewed; sorted by slot
-  float *raw = xs + (size_t)NC * PQ * 4;        // [n + 1][T]: the tile as it lies in the table, column n = slot ids
+  float *raw = xs + (size_t)NC * PQ * 4;        // [n + 1 + m][T]: the tile as it lies in the table, column n = slot ids
+  const int m = NB ? a.m : 0, n_fetch = n + 1 + m;
+  unsigned *key_hist = reinterpret_cast<unsigned *>(raw + (size_t)n_fetch * T);  // [G * total_dom] (fused NB scan)
+  for (int i = tid; i < (m ? G * a.total_dom : 0); i += kSlotThreads) key_hist[i] = 0;
   __shared__ __align__(8) uint64_t full_bar;
-  __shared__ unsigned cnt[kSlotMaxGroups];      // rows of every slot in the tile (zero between tiles)
-  __shared__ unsigned seg_start[kSlotMaxGroups], seg_rows[kSlotMaxGroups];
+  __shared__ unsigned cnt[2][kSlotMaxGroups];   // rows of every slot in the tile; tiles alternate between the two sets
 
   // this lane's task: (slot, split, block), block fastest -- the lanes of a warp mostly share slot and split, i.e. rows
   const int per_slot = NBLK * a.splits;
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
   // the padding columns (n .. NC - 1) are zero and never written again
   for (int c = n; c < NC; c++)
     for (int i = tid; i < PQ * 4; i += kSlotThreads) xs[(size_t)c * PQ * 4 + i] = 0.f;
-  if (tid < kSlotMaxGroups) cnt[tid] = 0;
+  if (tid < 2 * kSlotMaxGroups) cnt[tid / kSlotMaxGroups][tid % kSlotMaxGroups] = 0;
 
   auto fold = [&]() {
     if (!active) return;
@@ -152,10 +161,11 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
   auto fetch = [&](unsigned long long tile) {
     const unsigned long long lo = tile * T;
     const int cnt_rows = (int)min((unsigned long long)T, a.n_rows - lo), whole = cnt_rows & ~3;
-    if (tid == 0) ptx::mbar_arrive_expect_tx(&full_bar, (uint32_t)(whole * 4 * (n + 1)));
+    if (tid == 0) ptx::mbar_arrive_expect_tx(&full_bar, (uint32_t)(whole * 4 * n_fetch));
     __syncwarp();
-    if (tid <= n) {
-      const void *src = tid < n ? (const void *)(a.cols.num[tid] + lo) : (const void *)(a.cols.group + lo);
+    if (tid < n_fetch) {
+      const void *src = tid < n ? (const void *)(a.cols.num[tid] + lo)
+                                : (tid == n ? (const void *)(a.cols.group + lo) : (const void *)(a.cols.cat[tid - n - 1] + lo));
       if (whole) ptx::bulk_g2s_plain(raw + (size_t)tid * T, src, (uint32_t)(whole * 4), &full_bar);
       for (int r = whole; r < cnt_rows; r++) raw[(size_t)tid * T + r] = reinterpret_cast<const float *>(src)[r];
     }
@@ -175,6 +185,7 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
     if (rows_here & 3) __syncthreads();  // ragged tail: the plain stores of warp 0 must be visible to everyone
     const int *rslot = reinterpret_cast<const int *>(raw + (size_t)n * T);
     // ---- 1. every row takes its rank within its slot from the slot's counter
+    unsigned *tile_cnt = cnt[it & 1];
     int slot[kSlotMaxSteps];
     unsigned pos[kSlotMaxSteps];
 #pragma unroll
@@ -189,34 +200,44 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
           g = -1;
         }
         slot[u] = g;
-        if (g >= 0) pos[u] = atomicAdd(&cnt[g], 1u);
+        if (g >= 0) pos[u] = atomicAdd(&tile_cnt[g], 1u);
+        if (NB && g >= 0) {
+          for (int c = 0; c < m; c++) {
+            const unsigned sl = (unsigned)(reinterpret_cast<const int *>(raw + (size_t)(n + 1 + c) * T)[row] - a.lo[c]);
+            if (sl < (unsigned)a.dom[c]) atomicAdd(&key_hist[g * a.total_dom + a.cat_off[c] + (int)sl], 1u);
+            else atomicExch(a.err, 1);  // a key outside the declared domain
+          }
+        }
       }
     }
     __syncthreads();
-    // ---- 2. segments (warp 0): every slot starts at a multiple of 4 rows and is padded with zero rows; N += size
-    if (tid < 32) {
-      const unsigned size = lane < G ? cnt[lane] : 0u, rows4 = (size + 3) & ~3u;
-      unsigned incl = rows4;
+    // ---- 2. segments: every slot starts at a multiple of 4 rows and is padded with zero rows.  Every WARP derives
+    //         them for itself (lane g holds slot g's start and size): no shared arrays, no barrier of their own.
+    const unsigned seg_size = lane < G ? tile_cnt[lane] : 0u, seg_rows4 = (seg_size + 3) & ~3u;
+    unsigned seg_begin;
+    {
+      unsigned incl = seg_rows4;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
       }
-      const unsigned start = incl - rows4;
-      if (lane < G) {
-        seg_start[lane] = start;
-        seg_rows[lane] = rows4;
-        cnt[lane] = 0;
-        if (size) red_u64(a.u64 + lane * a.U, size);
-        for (unsigned r = start + size; r < start + rows4; r++)
-          for (int i = 0; i < n; i++) xs[(size_t)slotb_col_quad(i, PQ) * 4 + r] = 0.f;
-      }
+      seg_begin = incl - seg_rows4;
     }
-    __syncthreads();
-    // ---- 3. the tile, column-major in sorted order
+    if (tid < G && seg_size) red_u64(a.u64 + tid * a.U, seg_size);  // N += size
+    cnt[(it & 1) ^ 1][lane] = 0;  // the other counter set (last read before the barrier above) serves the next tile
+    // ---- 3. the tile, column-major in sorted order; the zero rows that pad a segment to whole 4-row groups
 #pragma unroll
-    for (int u = 0; u < kSlotMaxSteps; u++)
-      if (slot[u] >= 0) pos[u] += seg_start[slot[u]];
+    for (int u = 0; u < kSlotMaxSteps; u++) {
+      const unsigned st = __shfl_sync(0xffffffffu, seg_begin, slot[u] < 0 ? 0 : slot[u]);
+      if (slot[u] >= 0) pos[u] += st;
+    }
+    for (int g = tid >> 5; g < G; g += kSlotWarps) {  // warp w pads the slots w, w + 8, ...: lane = (pad row, column)
+      const unsigned st = __shfl_sync(0xffffffffu, seg_begin, g), sz = __shfl_sync(0xffffffffu, seg_size, g);
+      const unsigned pad = ((sz + 3) & ~3u) - sz;
+      for (unsigned e = lane; e < pad * (unsigned)n; e += 32)
+        xs[(size_t)slotb_col_quad((int)(e % n), PQ) * 4 + st + sz + e / n] = 0.f;
+    }
 #pragma unroll 4
     for (int i = 0; i < n; i++) {
       float v[kSlotMaxSteps];
@@ -231,9 +252,10 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
     // the staging buffer has been read: the next tile of this CTA lands in it while this one is multiplied
     if (tile + gridDim.x < n_tiles && tid < 32) fetch(tile + gridDim.x);
     // ---- 4. this lane's block over its share of the slot's 4-row groups
+    const unsigned my_rows4 = __shfl_sync(0xffffffffu, seg_rows4, tg), my_begin = __shfl_sync(0xffffffffu, seg_begin, tg);
     if (active) {
-      const unsigned groups = seg_rows[tg] / 4;
-      const SlotQuad *base = reinterpret_cast<const SlotQuad *>(xs) + seg_start[tg] / 4;
+      const unsigned groups = my_rows4 / 4;
+      const SlotQuad *base = reinterpret_cast<const SlotQuad *>(xs) + my_begin / 4;
 #pragma unroll 1
       for (unsigned q = tsplit; q < groups; q += a.splits) {
         SlotQuad xi[4];
@@ -267,6 +289,11 @@ __global__ void __launch_bounds__(kSlotThreads, 2) slot_block_kernel(const __gri
       fold();
     }
     __syncthreads();  // the sorted tile is rewritten by the next iteration
+  }
+  // key counts of the fused Naive-Bayes scan (a CTA sees < 2^32 rows)
+  for (int i = tid; i < (m ? G * a.total_dom : 0); i += kSlotThreads) {
+    const unsigned v = key_hist[i];
+    if (v) red_u64(a.u64 + (i / a.total_dom) * a.U + 1 + i % a.total_dom, v);
   }
 }
 
