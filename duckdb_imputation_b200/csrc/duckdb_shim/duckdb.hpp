@@ -13,6 +13,9 @@
 // (Vector copies alias their buffers, as in DuckDB), ListVector::Reserve / SetListSize growth.
 #pragma once
 #include <cassert>
+#include <cfloat>
+#include <climits>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -32,6 +35,9 @@ typedef uint64_t idx_t;  // duckdb.h (C API) exposes idx_t globally; the referen
 #define D_ASSERT(x) assert(x)
 #endif
 #define STANDARD_VECTOR_SIZE 2048
+#ifndef PI
+#define PI 3.141592653589793  // duckdb/common/constants: the reference's Box-Muller uses it (regression.cpp:502)
+#endif
 
 namespace duckdb {
 
@@ -69,12 +75,25 @@ class InvalidInputException : public Exception {
 
 // --------------------------------------------------------------------------- types
 enum class LogicalTypeId : uint8_t { INVALID, ANY, BOOLEAN, INTEGER, BIGINT, FLOAT, DOUBLE, VARCHAR, POINTER, STRUCT, LIST };
+enum class PhysicalType : uint8_t { INVALID, BOOL, INT32, INT64, FLOAT, DOUBLE, VARCHAR, STRUCT, LIST };
 
 class LogicalType {
  public:
   LogicalType() : id_(LogicalTypeId::INVALID) {}
   LogicalType(LogicalTypeId id) : id_(id) {}  // NOLINT: implicit like DuckDB's
   LogicalTypeId id() const { return id_; }
+  PhysicalType InternalType() const {
+    switch (id_) {
+      case LogicalTypeId::BOOLEAN: return PhysicalType::BOOL;
+      case LogicalTypeId::INTEGER: return PhysicalType::INT32;
+      case LogicalTypeId::BIGINT: case LogicalTypeId::POINTER: return PhysicalType::INT64;
+      case LogicalTypeId::FLOAT: return PhysicalType::FLOAT;
+      case LogicalTypeId::DOUBLE: return PhysicalType::DOUBLE;
+      case LogicalTypeId::STRUCT: return PhysicalType::STRUCT;
+      case LogicalTypeId::LIST: return PhysicalType::LIST;
+      default: return PhysicalType::INVALID;
+    }
+  }
   bool operator==(const LogicalType &o) const {
     if (id_ != o.id_ || children_.size() != o.children_.size()) return false;
     for (size_t i = 0; i < children_.size(); i++)
@@ -159,6 +178,24 @@ struct UnifiedVectorFormat {
   static const T *GetData(const UnifiedVectorFormat &f) {
     return reinterpret_cast<const T *>(f.data);
   }
+};
+
+// A scalar of one of the fixed-width types (what Vector::GetValue / SetValue exchange on this path).
+class Value {
+ public:
+  Value() : v_(0.0) {}
+  Value(bool b) : v_(b ? 1.0 : 0.0) {}      // NOLINT: implicit like DuckDB's
+  Value(int32_t i) : v_((double)i) {}       // NOLINT
+  Value(int64_t i) : v_((double)i) {}       // NOLINT
+  Value(float f) : v_((double)f) {}         // NOLINT
+  Value(double d) : v_(d) {}                // NOLINT
+  template <class T>
+  T GetValue() const {
+    return static_cast<T>(v_);
+  }
+
+ private:
+  double v_;
 };
 
 class Vector;
@@ -250,6 +287,30 @@ class Vector {
   }
 
   shared_ptr<VectorBuffer> &auxiliary() { return aux_; }
+  const shared_ptr<VectorBuffer> &auxiliary() const { return aux_; }
+
+  // scalar access by row (fixed-width types only), through the vector's own selection
+  Value GetValue(idx_t i) const {
+    const idx_t r = vtype_ == VectorType::CONSTANT_VECTOR ? 0 : (vtype_ == VectorType::DICTIONARY_VECTOR ? dict_sel_.get_index(i) : i);
+    switch (type_.id()) {
+      case LogicalTypeId::BOOLEAN: return Value(reinterpret_cast<const uint8_t *>(data_)[r] != 0);
+      case LogicalTypeId::INTEGER: return Value(reinterpret_cast<const int32_t *>(data_)[r]);
+      case LogicalTypeId::BIGINT: return Value(reinterpret_cast<const int64_t *>(data_)[r]);
+      case LogicalTypeId::FLOAT: return Value(reinterpret_cast<const float *>(data_)[r]);
+      case LogicalTypeId::DOUBLE: return Value(reinterpret_cast<const double *>(data_)[r]);
+      default: throw InternalException("shim: GetValue on a nested vector");
+    }
+  }
+  void SetValue(idx_t i, const Value &v) {
+    switch (type_.id()) {
+      case LogicalTypeId::BOOLEAN: reinterpret_cast<uint8_t *>(data_)[i] = v.GetValue<bool>(); break;
+      case LogicalTypeId::INTEGER: reinterpret_cast<int32_t *>(data_)[i] = v.GetValue<int32_t>(); break;
+      case LogicalTypeId::BIGINT: reinterpret_cast<int64_t *>(data_)[i] = v.GetValue<int64_t>(); break;
+      case LogicalTypeId::FLOAT: reinterpret_cast<float *>(data_)[i] = v.GetValue<float>(); break;
+      case LogicalTypeId::DOUBLE: reinterpret_cast<double *>(data_)[i] = v.GetValue<double>(); break;
+      default: throw InternalException("shim: SetValue on a nested vector");
+    }
+  }
 
  private:
   static sel_t *ZeroSel() {
@@ -315,6 +376,9 @@ struct StructVector {
   static vector<unique_ptr<Vector>> &GetEntries(Vector &v) {
     return static_cast<VectorStructBuffer &>(*v.auxiliary()).children;
   }
+  static const vector<unique_ptr<Vector>> &GetEntries(const Vector &v) {
+    return static_cast<const VectorStructBuffer &>(*v.auxiliary()).children;
+  }
 };
 
 // --------------------------------------------------------------- function plumbing
@@ -324,10 +388,31 @@ class Expression {
  public:
   LogicalType return_type;
 };
-class Value;           // only named in declarations on this path
-class BaseStatistics;  // idem (utils.h)
+class BaseStatistics {  // only produced by the statistics callbacks, which nothing here calls
+ public:
+  unique_ptr<BaseStatistics> ToUnique() const { return make_uniq<BaseStatistics>(*this); }
+};
+struct NumericStats {
+  static BaseStatistics CreateUnknown(const LogicalType &) { return BaseStatistics(); }
+};
 struct FunctionData {
   virtual ~FunctionData() = default;
+  template <class T>
+  T &Cast() {
+    return reinterpret_cast<T &>(*this);
+  }
+};
+struct FunctionLocalState {
+  virtual ~FunctionLocalState() = default;
+  template <class T>
+  T &Cast() {
+    return reinterpret_cast<T &>(*this);
+  }
+};
+class BoundFunctionExpression : public Expression {};
+struct FunctionStatisticsInput {
+  BoundFunctionExpression &expr;
+  vector<BaseStatistics> &child_stats;
 };
 struct VariableReturnBindData : FunctionData {
   explicit VariableReturnBindData(LogicalType t) : stype(std::move(t)) {}
@@ -405,19 +490,27 @@ class DataChunk {
  private:
   idx_t count = 0;
 };
-struct ExpressionState {};
+struct ExpressionState {
+  unique_ptr<FunctionLocalState> local;  // what init_local_state returned for this executor
+};
+struct ExecuteFunctionState {
+  static FunctionLocalState *GetFunctionState(ExpressionState &state) { return state.local.get(); }
+};
 class ScalarFunction;
 typedef void (*scalar_function_t)(DataChunk &args, ExpressionState &state, Vector &result);
 typedef unique_ptr<FunctionData> (*bind_scalar_function_t)(ClientContext &, ScalarFunction &, vector<unique_ptr<Expression>> &);
+typedef unique_ptr<BaseStatistics> (*function_statistics_t)(ClientContext &, FunctionStatisticsInput &);
+typedef unique_ptr<FunctionLocalState> (*init_local_state_t)(ExpressionState &, const BoundFunctionExpression &, FunctionData *);
 class ScalarFunction {
  public:
   ScalarFunction(string name_p, vector<LogicalType> arguments_p, LogicalType return_type_p, scalar_function_t function_p,
-                 bind_scalar_function_t bind_p = nullptr, void *dependency = nullptr, void *statistics = nullptr)
+                 bind_scalar_function_t bind_p = nullptr, void *dependency = nullptr, function_statistics_t statistics_p = nullptr,
+                 init_local_state_t init_local_state_p = nullptr)
       : name(std::move(name_p)), arguments(std::move(arguments_p)), return_type(std::move(return_type_p)),
-        function(function_p), bind(bind_p) {
+        function(function_p), bind(bind_p), statistics(statistics_p), init_local_state(init_local_state_p) {
     (void)dependency;
-    (void)statistics;
   }
+
   string name;
   vector<LogicalType> arguments;
   LogicalType return_type;
@@ -425,6 +518,8 @@ class ScalarFunction {
   FunctionNullHandling null_handling = FunctionNullHandling::DEFAULT_NULL_HANDLING;
   scalar_function_t function;
   bind_scalar_function_t bind;
+  function_statistics_t statistics;
+  init_local_state_t init_local_state;
 };
 
 // The catalog an extension registers into (ExtensionUtil::RegisterFunction).

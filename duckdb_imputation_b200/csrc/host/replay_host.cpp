@@ -299,8 +299,11 @@ int replay_predict(const char *scalar, const float *params, size_t n_params, con
     ScalarFunction fun = it->second;
     ClientContext context;
     vector<unique_ptr<Expression>> args;
-    if (fun.bind) fun.bind(context, fun, args);
+    unique_ptr<FunctionData> bind_data;
+    if (fun.bind) bind_data = fun.bind(context, fun, args);
     const idx_t out_w = fun.return_type.width();
+    ExpressionState state;  // one executor: its local state lives as long as the query
+    if (fun.init_local_state) state.local = fun.init_local_state(state, BoundFunctionExpression(), bind_data.get());
     // the literal arguments: a constant FLOAT[] and constant BOOLEANs, as the planner hands them over
     Vector plist(LogicalType::LIST(LogicalType::FLOAT), 1);
     ListVector::Reserve(plist, n_params);
@@ -331,7 +334,6 @@ int replay_predict(const char *scalar, const float *params, size_t n_params, con
       for (auto &l : lits) chunk.data.push_back(l);
       for (auto &v : cols.data) chunk.data.push_back(v);
       chunk.SetCardinality(count);
-      ExpressionState state;
       Vector result(fun.return_type, count);
       fun.function(chunk, state, result);
       memcpy((char *)out + written * out_w, FlatVector::GetData(result), count * out_w);

@@ -131,13 +131,13 @@ class Replay:
 
     def predict(self, function: str, params, flags, num_cols, cat_cols, where=None):
         """SELECT function(params::FLOAT[], flags..., cols...) FROM t [WHERE ..] -> numpy array (float32 for
-        linreg_predict, int32 for lda_predict), one value per (selected) row."""
+        linreg_predict, int32 for lda_predict / nb_predict / qda_predict), one value per (selected) row."""
         kn = [np.ascontiguousarray(c, np.float32) for c in num_cols]
         kc = [np.ascontiguousarray(c, np.int32) for c in cat_cols]
         rows = len(kn[0]) if kn else (len(kc[0]) if kc else 0)
         s = None if where is None else np.nonzero(np.asarray(where))[0].astype(np.uint32)
         p = np.ascontiguousarray(params, np.float32)
-        out = np.zeros(rows if s is None else len(s), np.int32 if function.startswith("lda") else np.float32)
+        out = np.zeros(rows if s is None else len(s), np.float32 if function.startswith("linreg") else np.int32)
         fl = (C.c_int * max(1, len(flags)))(*[int(bool(f)) for f in flags])
         rc = self.lib.replay_predict(function.encode(), p.ctypes.data, len(p), fl, len(flags), len(kn), len(kc),
                                      ptr_array([k.ctypes.data for k in kn]), ptr_array([k.ctypes.data for k in kc]),

@@ -200,13 +200,15 @@ def linreg_predict(params, normalize, num_cols, cat_cols):
             pos[(col == k) & (pos < 0)] = b + j
         if (pos < 0).any():
             raise ValueError("key not in the parameter list")
-        w = p[start + n + 1:].astype(np.float64)
+        w = p[start + n + 1:]
         if normalize:
-            mean = p[1 + 2 * n + max_idx + start:].astype(np.float64)
+            # (double)(w_j * (onehot_j - mean_j)): the product is a FLOAT product (regression.cpp:478-491), added in
+            # key order
+            mean = p[1 + 2 * n + max_idx + start:]
             for j in range(b, e):
-                out += w[j] * ((pos == j).astype(np.float64) - mean[j])
+                out += (w[j] * ((pos == j).astype(np.float32) - mean[j])).astype(np.float64)
         else:
-            out += w[pos]
+            out += w[pos].astype(np.float64)
     return out.astype(np.float32)                                             # FLOAT result (:366-375)
 
 
@@ -260,3 +262,132 @@ def lda_predict(params, normalize, num_cols, cat_cols):
         feats -= p[off:off + num_params].astype(np.float64)[None, :]
     scores = feats @ coef.T + intercept[None, :]                               # dgemv (:560-562) + intercept
     return np.argmax(scores, axis=1).astype(np.int32), scores
+
+
+def nb_params(labels, priors, means, variances, cat_keys, cat_probs):
+    """The FLOAT[] that nb_train emits, in the layout ML::nb_impute reads (ML/naive_bayes.cpp:186-210):
+    [K | S | idx_0..idx_{S-1} | unique keys | labels[K] | priors[K] | per class: (mean, variance) per numeric column,
+    then one probability per (column, key)].  means / variances: [K][n]; cat_probs: [K][total keys]."""
+    K = len(labels)
+    p = [float(K)]
+    if cat_keys:
+        idx = np.concatenate([[0], np.cumsum([len(k) for k in cat_keys])])
+        p += [float(len(idx))] + [float(i) for i in idx] + [float(k) for col in cat_keys for k in col]
+    else:
+        p += [0.0]
+    p += [float(l) for l in labels] + [float(v) for v in priors]
+    for k in range(K):
+        for j in range(len(means[k]) if len(means) else 0):
+            p += [float(means[k][j]), float(variances[k][j])]
+        if cat_keys:
+            p += [float(v) for v in cat_probs[k]]
+    return np.asarray(p, np.float32)
+
+
+def nb_predict(params, num_cols, cat_cols):
+    """Restatement of ML::nb_impute (ML/naive_bayes.cpp:153-263): per row and class the product of the prior, one
+    Gaussian density per numeric column (variance + 1e-9) and one probability per categorical column (0 for a key
+    the model does not hold); the LABEL of the first class with the largest product (class 0 when every product is
+    0).  fp64 like the reference; also returns the products."""
+    p = np.asarray(params, np.float32)
+    n, m = len(num_cols), len(cat_cols)
+    rows = len(num_cols[0]) if n else len(cat_cols[0])
+    K, S = int(p[0]), int(p[1])
+    idx, keys, total = [], np.zeros(0, np.int64), 0
+    if S > 0:
+        idx = [int(v) for v in p[2:2 + S]]
+        total = idx[-1]
+        keys = p[2 + S:2 + S + total].astype(np.uint64).astype(np.int64)       # uint64_t cat_vars (:196-202)
+    label_off = 2 + (S + total if S > 0 else 0)
+    prior_off = label_off + K
+    k0 = prior_off + K
+    per_class = 2 * n + (idx[m] if S > 0 else 0)
+    prob = np.zeros((rows, K), np.float64)
+    for c in range(K):
+        base = k0 + c * per_class
+        tot = np.full(rows, np.float64(p[prior_off + c]))
+        for j in range(n):
+            var = np.float64(p[base + 2 * j + 1]) + 0.000000001
+            mean = np.float64(p[base + 2 * j])
+            x = np.asarray(num_cols[j], np.float32)
+            # (in_cont_data - mean): float - double -> double
+            tot = tot * ((1.0 / np.sqrt(2 * np.pi * var)) * np.exp(-np.power(x.astype(np.float64) - mean, 2) / (2.0 * var)))
+        if S > 0:
+            cb = base + 2 * n
+            for j in range(m):
+                col = np.asarray(cat_cols[j], np.int64)
+                f = np.zeros(rows, np.float64)
+                seen = np.zeros(rows, bool)
+                for t in range(idx[j], idx[j + 1]):
+                    sel = (col == keys[t]) & ~seen
+                    f[sel] = np.float64(p[cb + t])
+                    seen |= sel
+                tot = tot * f
+        prob[:, c] = tot
+    best = np.zeros(rows, np.int64)
+    mx = np.zeros(rows, np.float64)
+    for c in range(K):                                                        # strict '>' from 0 (:247-250)
+        better = prob[:, c] > mx
+        best[better] = c
+        mx[better] = prob[better, c]
+    return p[label_off + best].astype(np.int32), prob
+
+
+def qda_params(labels, quad, lin, intercept, cat_keys, means=None):
+    """The FLOAT[] that qda_train emits, in the layout ML::qda_impute reads (ML/qda.cpp:367-400, :437-448):
+    [K | S | idx | unique keys | labels[K] | per class: Q[p x p] column-major, l[p], intercept | (means[p])],
+    p = n + total keys."""
+    K = len(labels)
+    out = [float(K)]
+    if cat_keys:
+        idx = np.concatenate([[0], np.cumsum([len(k) for k in cat_keys])])
+        out += [float(len(idx))] + [float(i) for i in idx] + [float(k) for col in cat_keys for k in col]
+    else:
+        out += [0.0]
+    out += [float(l) for l in labels]
+    for k in range(K):
+        out += [float(v) for v in np.asarray(quad[k], np.float64).reshape(-1, order="F")]
+        out += [float(v) for v in lin[k]] + [float(intercept[k])]
+    if means is not None:
+        out += [float(v) for v in means]
+    return np.asarray(out, np.float32)
+
+
+def qda_predict(params, normalize, num_cols, cat_cols):
+    """Restatement of ML::qda_impute (ML/qda.cpp:338-498): score_k = intercept_k + f^T Q_k f + l_k . f over the
+    features f = [numeric | one-hot] (centred when normalize; a key the model does not hold leaves its one-hot
+    block zero); the LABEL of the first class with the largest score.  PARITY UNPINNED: ML/qda.cpp does not compile
+    with g++ (qda.cpp:209), so this restatement could not be run against the reference."""
+    p = np.asarray(params, np.float32)
+    n, m = len(num_cols), len(cat_cols)
+    rows = len(num_cols[0]) if n else len(cat_cols[0])
+    K, S = int(p[0]), int(p[1])
+    idx, keys, total, start = [], np.zeros(0, np.int64), 0, 2
+    if S > 0:
+        idx = [int(v) for v in p[2:2 + S]]
+        total = idx[-1]
+        keys = p[2 + S:2 + S + total].astype(np.uint64).astype(np.int64)
+        start = 2 + total + S
+    label_off = start
+    start += K
+    P = n + total
+    feats = np.zeros((rows, P), np.float64)
+    for j in range(n):
+        feats[:, j] = np.asarray(num_cols[j], np.float32).astype(np.float64)
+    for j in range(m):
+        col = np.asarray(cat_cols[j], np.int64)
+        seen = np.zeros(rows, bool)
+        for t in range(idx[j], idx[j + 1]):
+            sel = (col == keys[t]) & ~seen
+            feats[sel, n + t] = 1.0
+            seen |= sel
+    if normalize:
+        off = start + (P * P + P + 1) * K
+        feats = feats - p[off:off + P].astype(np.float64)[None, :]
+    scores = np.zeros((rows, K), np.float64)
+    for k in range(K):
+        base = start + k * (P * P + P + 1)
+        Q = p[base:base + P * P].astype(np.float64).reshape(P, P, order="F")
+        l = p[base + P * P:base + P * P + P].astype(np.float64)
+        scores[:, k] = np.float64(p[base + P * P + P]) + np.einsum("ri,ij,rj->r", feats, Q, feats) + feats @ l
+    return p[label_off + np.argmax(scores, axis=1)].astype(np.int32), scores

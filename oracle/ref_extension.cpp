@@ -9,12 +9,44 @@
 #include <triple/sum/sum_state.h>
 #include <triple/sum/sum_to_nb_agg.h>
 
+#include <ML/lda.h>
+#include <ML/naive_bayes.h>
+#include <ML/regression.h>
+
+namespace {
+// The local state ML::linreg_impute expects (regression.cpp:399).  The reference's own init function
+// (regression.cpp:377-394) casts the BIND data to RegressionState and seeds libc random() from /dev/urandom; here the
+// state is simply constructed -- the generator is seeded by the test that asks for noise.
+duckdb::unique_ptr<duckdb::FunctionLocalState> FreshRegressionState(duckdb::ExpressionState &, const duckdb::BoundFunctionExpression &,
+                                                                  duckdb::FunctionData *) {
+  return duckdb::make_uniq<RegressionState>();
+}
+}  // namespace
+
 namespace duckdb_ring {
 
 const char *Implementation() { return "reference"; }
 
 void Load(duckdb::DatabaseInstance &db) {
   using namespace duckdb;
+  // the predict side of the write-back step, as load_ml registers it (duckdb_imputation_extension.cpp:193-249); the
+  // trainers are not registered (no BLAS / LAPACK here), qda_predict neither (ML/qda.cpp does not compile with g++:
+  // `new double[wkopt]` with a double, qda.cpp:209)
+  {
+    ScalarFunction lda_predict("lda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, LDA_impute, LDA_impute_bind, nullptr, LDA_impute_stats);
+    lda_predict.varargs = LogicalType::ANY;
+    lda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, lda_predict);
+    ScalarFunction linreg_predict("linreg_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::linreg_impute, ML::linreg_impute_bind, nullptr,
+                                  nullptr, FreshRegressionState);
+    linreg_predict.varargs = LogicalType::ANY;
+    linreg_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, linreg_predict);
+    ScalarFunction nb_predict("nb_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::nb_impute, ML::nb_impute_bind, nullptr);
+    nb_predict.varargs = LogicalType::ANY;
+    nb_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, nb_predict);
+  }
   for (int i = 0; i < 20; i++)
     for (int j = 0; j < 20; j++) {
       if (i == 0 && j == 0) continue;

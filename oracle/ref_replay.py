@@ -34,3 +34,35 @@ def time_sum_to_triple(num_cols, cat_cols, threads: int) -> float:
     name = "ref_sum_to_triple_20_0" if (n, m) == (20, 0) else "sum_to_triple_%d_%d" % (n, m)
     r.aggregate(name, num_cols, cat_cols, threads=threads)
     return r.last_seconds
+
+
+class _quiet_stdout:
+    """The reference's predict functions print per-row debug lines to std::cout (regression.cpp:440, :466, lda.cpp:525):
+    file descriptor 1 points at /dev/null while they run."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        os.close(self._null)
+
+
+def predict(function: str, params, flags, num_cols, cat_cols, where=None):
+    """The reference's own linreg_predict / lda_predict / nb_predict (ML::linreg_impute, LDA_impute, ML::nb_impute compiled
+    from /root/reference into oracle/_ref) on these columns: one value per (selected) row."""
+    with _quiet_stdout():
+        return ref().predict(function, params, flags, num_cols, cat_cols, where=where)
+
+
+def seed_libc_random(seed: int):
+    """linreg_predict(noise = true) draws from libc random() (regression.cpp:495-505)."""
+    import ctypes
+    ctypes.CDLL(None).srandom(ctypes.c_uint(seed))
