@@ -62,6 +62,9 @@ SIGNATURES = {
     "cfb_result_multiply": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.POINTER(Result)]),
     "cfb_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "cfb_model_destroy": (None, [_P]),
+    "cfb_model_set_noise": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64]),
+    "cfb_model_create_nb": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "cfb_model_create_qda": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "cfb_predict_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int, _P, _P]),
     "cfb_predict_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),
     "cfb_ctx_partial_sizes": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

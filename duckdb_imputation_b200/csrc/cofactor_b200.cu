@@ -1477,9 +1477,13 @@ inline void gather(T *dst, const T *src, const uint32_t *sel, size_t first, size
 // ------------------------------------------------------------------ model scores (MICE write-back)
 struct cfb_model {
   int device = 0;
+  int type = 0;  // 0: linear scores (linreg / LDA), 1: Gaussian naive Bayes, 2: QDA
   double *d_model = nullptr;
   int *d_map = nullptr;
+  int *d_labels = nullptr;  // naive Bayes / QDA
   cfb::PredictArgs args{};
+  cfb::NbArgs nb{};
+  cfb::QdaArgs qda{};
   size_t smem = 0;
 };
 
@@ -1487,6 +1491,38 @@ namespace {
 
 int predict_launch(cfb_model *M, const float *const *num, const int32_t *const *cat, const int32_t *mask, size_t rows,
                    int mode, void *d_out, cudaStream_t s) {
+  if (M->type != 0) {
+    // naive Bayes / QDA: one row per thread, the model read from global memory, the class label out
+    if (mode != CFB_PREDICT_LABEL) return fail(CFB_ERR_INVALID, "a naive-Bayes / QDA model predicts labels (CFB_PREDICT_LABEL)");
+    const int n = M->type == 1 ? M->nb.n : M->qda.n, m = M->type == 1 ? M->nb.m : M->qda.m;
+    cfb::ScanCols cols{};
+    for (int k = 0; k < n; k++) {
+      if (!num[k]) return fail(CFB_ERR_INVALID, "numeric column %d is NULL", k);
+      cols.num[k] = num[k];
+    }
+    for (int k = 0; k < m; k++) {
+      if (!cat[k]) return fail(CFB_ERR_INVALID, "categorical column %d is NULL", k);
+      cols.cat[k] = cat[k];
+    }
+    cols.group = mask;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)dev_info(M->device).sms * 8, (rows + cfb::kPredictThreads - 1) / cfb::kPredictThreads));
+    if (M->type == 1) {
+      cfb::NbArgs a = M->nb;
+      a.cols = cols;
+      a.n_rows = rows;
+      a.out = (int *)d_out;
+      cfb::predict_nb_kernel<<<grid, cfb::kPredictThreads, 0, s>>>(a);
+    } else {
+      cfb::QdaArgs a = M->qda;
+      a.cols = cols;
+      a.n_rows = rows;
+      a.out = (int *)d_out;
+      cfb::predict_qda_kernel<<<grid, cfb::kPredictThreads, 0, s>>>(a);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    return CFB_OK;
+  }
   if (mode != CFB_PREDICT_SCORE && mode != CFB_PREDICT_ARGMAX) return fail(CFB_ERR_INVALID, "unknown predict mode %d", mode);
   cfb::PredictArgs a = M->args;
   bool aligned = (((uintptr_t)d_out | (uintptr_t)mask) & 15) == 0;
@@ -1641,15 +1677,170 @@ extern "C" void cfb_model_destroy(cfb_model *M) {
     cudaSetDevice(M->device);
     cudaFree(M->d_model);
     cudaFree(M->d_map);
+    cudaFree(M->d_labels);
   }
   delete M;
+}
+
+namespace {
+// Dense key -> position maps of a model's categorical columns (shared by the three model kinds).
+int build_key_maps(int m, const int64_t *offs, const int32_t *keys, int *map_lo, int *map_off, int *map_len, std::vector<int> *map) {
+  for (int c = 0; c < m; c++) {
+    const long long b = offs[c], e = offs[c + 1];
+    if (e < b) return fail(CFB_ERR_INVALID, "model: cat_offsets must be non-decreasing");
+    map_off[c] = (int)map->size();
+    map_lo[c] = 0;
+    map_len[c] = 0;
+    if (e == b) continue;
+    for (long long t = b + 1; t < e; t++)
+      if (keys[t] <= keys[t - 1]) return fail(CFB_ERR_INVALID, "model: keys of column %d are not ascending", c);
+    const long long len = (long long)keys[e - 1] - keys[b] + 1;
+    if (len > (1 << 20) || (long long)map->size() + len > (4 << 20))
+      return fail(CFB_ERR_DOMAIN, "model: the key range of column %d is too wide for the dense key map", c);
+    map_lo[c] = keys[b];
+    map_len[c] = (int)len;
+    map->resize(map->size() + len, -1);
+    for (long long t = b; t < e; t++) (*map)[map_off[c] + (keys[t] - keys[b])] = (int)t;
+  }
+  return CFB_OK;
+}
+
+// doubles | key map | labels of a naive-Bayes / QDA model -> device
+int upload_label_model(cfb_model *h, const std::vector<double> &vals, const std::vector<int> &map, const int32_t *labels, int K) {
+  CU(cudaSetDevice(h->device));
+  CU(cudaMalloc((void **)&h->d_model, std::max<size_t>(1, vals.size()) * 8));
+  CU(cudaMalloc((void **)&h->d_map, std::max<size_t>(1, map.size()) * 4));
+  CU(cudaMalloc((void **)&h->d_labels, (size_t)K * 4));
+  if (!vals.empty()) CU(cudaMemcpy(h->d_model, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice));
+  if (!map.empty()) CU(cudaMemcpy(h->d_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_labels, labels, (size_t)K * 4, cudaMemcpyHostToDevice));
+  return CFB_OK;
+}
+}  // namespace
+
+extern "C" int cfb_model_set_noise(cfb_model *M, double sigma, uint64_t seed, uint64_t first_row) {
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  if (M->type != 0 || M->args.n_out != 1) return fail(CFB_ERR_INVALID, "noise applies to a single-output linear model");
+  if (!(sigma >= 0.0)) return fail(CFB_ERR_INVALID, "sigma must be >= 0");
+  M->args.noise_sigma = sigma;
+  M->args.noise_seed = seed;
+  M->args.noise_first = first_row;
+  return CFB_OK;
+}
+
+extern "C" int cfb_model_create_nb(int device, const cfb_nb_model *M, cfb_model **out_model) {
+  if (!out_model) return fail(CFB_ERR_INVALID, "out is NULL");
+  *out_model = nullptr;
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  const int K = M->n_classes, n = M->n_num, m = M->n_cat;
+  if (n < 0 || n > CFB_MAX_NUM || m < 0 || m > CFB_MAX_CAT || K < 1) return fail(CFB_ERR_INVALID, "model: shape out of range");
+  if (!M->labels || !M->prior || (n && (!M->mean || !M->var)) || (m && (!M->cat_offsets || !M->cat_keys || !M->cat_prob)))
+    return fail(CFB_ERR_INVALID, "model: NULL array");
+  const long long total = m ? M->cat_offsets[m] : 0;
+  std::unique_ptr<cfb_model> h(new cfb_model);
+  h->device = device;
+  h->type = 1;
+  cfb::NbArgs &a = h->nb;
+  a.n = n;
+  a.m = m;
+  a.n_classes = K;
+  a.total = (int)total;
+  std::vector<int> map;
+  int rc = build_key_maps(m, M->cat_offsets, M->cat_keys, a.map_lo, a.map_off, a.map_len, &map);
+  if (rc) return rc;
+  // [K] prior | [K][n] norm | [K][n] mean | [K][n] 2 var | [K][total] probabilities: the row-independent factors of the
+  // reference's expression, evaluated once with the same operations (naive_bayes.cpp:222-227)
+  std::vector<double> v((size_t)K * (1 + 3 * n + total));
+  double *prior = v.data(), *norm = prior + K, *mean = norm + (size_t)K * n, *two_var = mean + (size_t)K * n, *prob = two_var + (size_t)K * n;
+  for (int k = 0; k < K; k++) {
+    prior[k] = M->prior[k];
+    for (int j = 0; j < n; j++) {
+      double variance = M->var[(size_t)k * n + j];
+      variance += 0.000000001;  // avoid division by 0 (naive_bayes.cpp:223)
+      norm[(size_t)k * n + j] = (double)1 / sqrt(2 * M_PI * variance);
+      mean[(size_t)k * n + j] = M->mean[(size_t)k * n + j];
+      two_var[(size_t)k * n + j] = (double)2 * variance;
+    }
+    for (long long t = 0; t < total; t++) prob[(size_t)k * total + t] = M->cat_prob[(size_t)k * total + t];
+  }
+  rc = upload_label_model(h.get(), v, map, M->labels, K);
+  if (rc) {
+    cfb_model_destroy(h.release());
+    return rc;
+  }
+  a.d_map = h->d_map;
+  a.labels = h->d_labels;
+  a.prior = h->d_model;
+  a.norm = a.prior + K;
+  a.mean = a.norm + (size_t)K * n;
+  a.two_var = a.mean + (size_t)K * n;
+  a.cat_prob = a.two_var + (size_t)K * n;
+  *out_model = h.release();
+  return CFB_OK;
+}
+
+extern "C" int cfb_model_create_qda(int device, const cfb_qda_model *M, cfb_model **out_model) {
+  if (!out_model) return fail(CFB_ERR_INVALID, "out is NULL");
+  *out_model = nullptr;
+  if (device_count_quiet() == 0) return fail(CFB_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+  if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
+  const int K = M->n_classes, n = M->n_num, m = M->n_cat;
+  if (n < 0 || n > CFB_MAX_NUM || m < 0 || m > CFB_MAX_CAT || K < 1) return fail(CFB_ERR_INVALID, "model: shape out of range");
+  if (!M->labels || !M->quad || !M->lin || !M->intercept || (m && (!M->cat_offsets || !M->cat_keys))) return fail(CFB_ERR_INVALID, "model: NULL array");
+  const long long total = m ? M->cat_offsets[m] : 0, P = n + total;
+  if (P < 1 || (double)K * P * P * 8 > 4e9) return fail(CFB_ERR_DOMAIN, "model: QDA matrices of %lld x %lld per class are too large", P, P);
+  std::unique_ptr<cfb_model> h(new cfb_model);
+  h->device = device;
+  h->type = 2;
+  cfb::QdaArgs &a = h->qda;
+  a.n = n;
+  a.m = m;
+  a.n_classes = K;
+  a.total = (int)total;
+  a.p = (int)P;
+  std::vector<int> map;
+  int rc = build_key_maps(m, M->cat_offsets, M->cat_keys, a.map_lo, a.map_off, a.map_len, &map);
+  if (rc) return rc;
+  // [K][P][P] Q | [K][P] g | [K] b with the centre folded in: g = lin - (Q + Q^T) c, b = intercept + c^T Q c - lin . c
+  std::vector<double> v((size_t)K * (P * P + P + 1));
+  double *Q = v.data(), *g = Q + (size_t)K * P * P, *b = g + (size_t)K * P;
+  memcpy(Q, M->quad, (size_t)K * P * P * 8);
+  for (int k = 0; k < K; k++) {
+    const double *Qk = M->quad + (size_t)k * P * P, *lk = M->lin + (size_t)k * P;
+    double bk = M->intercept[k];
+    for (long long i = 0; i < P; i++) {
+      double gi = lk[i];
+      if (M->center) {
+        for (long long j = 0; j < P; j++) gi -= (Qk[i + j * P] + Qk[j + i * P]) * M->center[j];
+        double row = 0.0;
+        for (long long j = 0; j < P; j++) row += Qk[i + j * P] * M->center[j];
+        bk += M->center[i] * row - lk[i] * M->center[i];
+      }
+      g[(size_t)k * P + i] = gi;
+    }
+    b[k] = bk;
+  }
+  rc = upload_label_model(h.get(), v, map, M->labels, K);
+  if (rc) {
+    cfb_model_destroy(h.release());
+    return rc;
+  }
+  a.d_map = h->d_map;
+  a.labels = h->d_labels;
+  a.Q = h->d_model;
+  a.g = a.Q + (size_t)K * P * P;
+  a.b = a.g + (size_t)K * P;
+  *out_model = h.release();
+  return CFB_OK;
 }
 
 extern "C" int cfb_predict_device(cfb_model *M, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                                   const int32_t *d_row_mask, size_t n_rows, int mode, void *d_out, void *stream) {
   if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
   if (n_rows == 0) return CFB_OK;
-  if (!d_out || (M->args.n && !d_num_cols) || (M->args.m && !d_cat_cols)) return fail(CFB_ERR_INVALID, "NULL column array / output");
+  const int mn = M->type == 0 ? M->args.n : (M->type == 1 ? M->nb.n : M->qda.n), mm = M->type == 0 ? M->args.m : (M->type == 1 ? M->nb.m : M->qda.m);
+  if (!d_out || (mn && !d_num_cols) || (mm && !d_cat_cols)) return fail(CFB_ERR_INVALID, "NULL column array / output");
   CU(cudaSetDevice(M->device));
   return predict_launch(M, d_num_cols, d_cat_cols, d_row_mask, n_rows, mode, d_out, (cudaStream_t)stream);
 }
@@ -1659,7 +1850,8 @@ extern "C" int cfb_predict_host(cfb_model *M, const float *const *num_cols, cons
                                 void *out) {
   if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
   if (count == 0) return CFB_OK;
-  const int n = M->args.n, m = M->args.m, device = M->device;
+  const int n = M->type == 0 ? M->args.n : (M->type == 1 ? M->nb.n : M->qda.n), m = M->type == 0 ? M->args.m : (M->type == 1 ? M->nb.m : M->qda.m);
+  const int device = M->device;
   if (!out || (n && !num_cols) || (m && !cat_cols)) return fail(CFB_ERR_INVALID, "NULL argument");
   CU(cudaSetDevice(device));
   PredictScratch &sc = t_predict;

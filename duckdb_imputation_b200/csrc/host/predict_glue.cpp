@@ -6,11 +6,19 @@
 // turns them into a cfb_linear_model -- bias, numeric weights, per-(column,key) weights, with the
 // `normalize` centering folded into the bias -- and scores the chunk on the GPU (cfb_predict_host).
 //
+//   nb_predict(params FLOAT[], normalize BOOL, cols...)                  ML::nb_impute      reference: ML/naive_bayes.cpp:153-263
+//   qda_predict(params FLOAT[], normalize BOOL, cols...)                 ML::qda_impute     reference: ML/qda.cpp:338-498
+//
 // Deliberate differences: a key the model does not know contributes 0 (the reference reads
-// past the column's weights, regression.cpp:471-498, or asserts, lda.cpp:528); `noise = true` is refused:
-// the reference draws from libc random() seeded from /dev/urandom (regression.cpp:376-393, :495-505), which
-// no test can pin -- a counter-based device generator is the planned replacement.
+// past the column's weights, regression.cpp:471-498, or asserts, lda.cpp:528).  `noise = true` adds
+// sigma * N(0, 1) like the reference (regression.cpp:495-505), but the normals come from a counter-based
+// generator on the device (Philox + Box-Muller keyed by a per-executor seed and the row's position in the
+// stream) instead of libc random() seeded from /dev/urandom: same distribution, reproducible with CFB_NOISE_SEED.
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -97,6 +105,7 @@ struct ModelCache {
   std::vector<float> params;
   int tag = -1;  // function | flags | n | m
   cfb_model *model = nullptr;
+  uint64_t noise_seed = 0, rows_done = 0;  // this executor's noise stream and its position
   ~ModelCache() { cfb_model_destroy(model); }
 };
 thread_local ModelCache t_cache;
@@ -111,7 +120,21 @@ cfb_model *Upload(Model &M, const std::vector<float> &p, int tag) {
   Check(cfb_model_create(Device(), &M.m, &t_cache.model));
   t_cache.params = p;
   t_cache.tag = tag;
+  // a fresh noise stream per uploaded model and executor thread: CFB_NOISE_SEED pins it (tests), else the system's
+  // entropy source, as the reference seeds from /dev/urandom (regression.cpp:380-391)
+  static std::atomic<uint64_t> executor{0};
+  const uint64_t lane = executor.fetch_add(1);
+  if (const char *e = getenv("CFB_NOISE_SEED")) t_cache.noise_seed = strtoull(e, nullptr, 10) + 0x9E3779B97F4A7C15ull * lane;
+  else t_cache.noise_seed = ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}() ^ lane;
+  t_cache.rows_done = 0;
   return t_cache.model;
+}
+
+// noise = true: position the executor's stream for this chunk (sigma is the list's last entry, regression.cpp:503)
+void ArmNoise(cfb_model *model, bool noise, const std::vector<float> &p, idx_t rows) {
+  if (!noise) return;
+  Check(cfb_model_set_noise(model, std::fabs((double)p.back()), t_cache.noise_seed, t_cache.rows_done));
+  t_cache.rows_done += rows;
 }
 
 // The model sorts each column's keys ascending (the trainers emit them in lin_cat order, which is ascending
@@ -143,13 +166,14 @@ void linreg_impute(duckdb::DataChunk &args, duckdb::ExpressionState &, duckdb::V
   if (rows == 0) return;
   if (args.ColumnCount() < 3) throw InvalidInputException("linreg_predict(params, noise, normalize, columns...)");
   const std::vector<float> p = Params(args.data[0], rows);
-  if (Flag(args.data[1], rows)) throw InvalidInputException("linreg_predict: noise = true is not supported by the B200 build (see DESIGN.md)");
+  const bool noise = Flag(args.data[1], rows);
   const bool normalize = Flag(args.data[2], rows);
   Columns cols;
   Classify(args, 3, cols);
   const size_t n = cols.num.size(), m = cols.cat.size();
-  const int tag = (int)(0 | (normalize ? 2 : 0) | (n << 8) | (m << 16));
+  const int tag = (int)(0 | (normalize ? 2 : 0) | (noise ? 4 : 0) | (n << 8) | (m << 16));
   if (cfb_model *hit = Cached(p, tag)) {
+    ArmNoise(hit, noise, p, rows);
     Check(cfb_predict_host(hit, cols.num.data(), cols.num_sel.data(), cols.cat.data(), cols.cat_sel.data(), rows,
                            CFB_PREDICT_SCORE, FlatVector::GetData<float>(result)));
     return;
@@ -188,8 +212,164 @@ void linreg_impute(duckdb::DataChunk &args, duckdb::ExpressionState &, duckdb::V
   }
   M.bias.push_back(bias);
   SortColumns(M);
-  Check(cfb_predict_host(Upload(M, p, tag), cols.num.data(), cols.num_sel.data(), cols.cat.data(), cols.cat_sel.data(), rows,
-                         CFB_PREDICT_SCORE, FlatVector::GetData<float>(result)));
+  cfb_model *model = Upload(M, p, tag);
+  ArmNoise(model, noise, p, rows);
+  Check(cfb_predict_host(model, cols.num.data(), cols.num_sel.data(), cols.cat.data(), cols.cat_sel.data(), rows, CFB_PREDICT_SCORE,
+                         FlatVector::GetData<float>(result)));
+}
+
+namespace {
+// The head shared by the nb / qda parameter lists (naive_bayes.cpp:186-210, qda.cpp:367-390):
+// [K | S | idx_0..idx_{S-1} | unique keys], S = m + 1 index entries when there are categorical columns.
+struct ClassHead {
+  size_t K = 0, S = 0, total = 0, next = 2;
+  std::vector<int64_t> offs;
+  std::vector<int32_t> keys;
+};
+ClassHead ParseHead(const std::vector<float> &p, size_t m, const char *what) {
+  using namespace duckdb;
+  ClassHead h;
+  if (p.size() < 2) throw InvalidInputException(std::string(what) + ": parameter list too short");
+  h.K = (size_t)p[0];
+  h.S = (size_t)p[1];
+  if (h.K < 1) throw InvalidInputException(std::string(what) + ": no classes in the parameter list");
+  if ((h.S == 0) != (m == 0) || (h.S && h.S != m + 1))
+    throw InvalidInputException(std::string(what) + ": the parameter list was trained on a different number of categorical columns");
+  h.offs.push_back(0);
+  if (h.S) {
+    if (p.size() < 2 + h.S) throw InvalidInputException(std::string(what) + ": parameter list too short");
+    for (size_t i = 0; i < h.S; i++) {
+      const int64_t v = (int64_t)p[2 + i];
+      if (i == 0 ? v != 0 : v < h.offs.back()) throw InvalidInputException(std::string(what) + ": malformed categorical index");
+      if (i) h.offs.push_back(v);
+    }
+    h.total = (size_t)h.offs.back();
+    if (p.size() < 2 + h.S + h.total) throw InvalidInputException(std::string(what) + ": parameter list too short");
+    for (size_t t = 0; t < h.total; t++) h.keys.push_back((int32_t)(int64_t)p[2 + h.S + t]);
+    h.next = 2 + h.S + h.total;
+  }
+  return h;
+}
+// ascending keys per column (the device's dense key maps want them sorted); perm[t] = position in the list's order
+std::vector<size_t> SortKeys(ClassHead &h, size_t m) {
+  std::vector<size_t> perm(h.total);
+  for (size_t i = 0; i < h.total; i++) perm[i] = i;
+  for (size_t c = 0; c < m; c++)
+    std::sort(perm.begin() + h.offs[c], perm.begin() + h.offs[c + 1], [&](size_t x, size_t y) { return h.keys[x] < h.keys[y]; });
+  std::vector<int32_t> k2(h.total);
+  for (size_t i = 0; i < h.total; i++) k2[i] = h.keys[perm[i]];
+  h.keys.swap(k2);
+  return perm;
+}
+}  // namespace
+
+// naive_bayes.cpp:153-263.  params = [K | S | idx | keys | labels[K] | priors[K] | per class: (mean, variance) per numeric
+//                                     column, then one probability per (column, key)]; the result is the class LABEL (:252)
+void nb_impute(duckdb::DataChunk &args, duckdb::ExpressionState &, duckdb::Vector &result) {
+  using namespace duckdb;
+  const idx_t rows = args.size();
+  if (rows == 0) return;
+  if (args.ColumnCount() < 2) throw InvalidInputException("nb_predict(params, normalize, columns...)");
+  const std::vector<float> p = Params(args.data[0], rows);
+  Columns cols;
+  Classify(args, 2, cols);
+  const size_t n = cols.num.size(), m = cols.cat.size();
+  const int tag = (int)(8 | (n << 8) | (m << 16));
+  cfb_model *model = Cached(p, tag);
+  if (!model) {
+    ClassHead h = ParseHead(p, m, "nb_predict");
+    const size_t K = h.K, total = h.total, per_class = 2 * n + total, at = h.next + 2 * K;
+    if (p.size() < at + K * per_class) throw InvalidInputException("nb_predict: parameter list too short for these columns");
+    const std::vector<size_t> perm = SortKeys(h, m);
+    std::vector<int32_t> labels(K);
+    std::vector<double> prior(K), mean(K * n), var(K * n), prob(K * total);
+    for (size_t k = 0; k < K; k++) {
+      labels[k] = (int32_t)p[h.next + k];
+      prior[k] = p[h.next + K + k];
+      for (size_t j = 0; j < n; j++) {
+        mean[k * n + j] = p[at + k * per_class + 2 * j];
+        var[k * n + j] = p[at + k * per_class + 2 * j + 1];
+      }
+      for (size_t t = 0; t < total; t++) prob[k * total + t] = p[at + k * per_class + 2 * n + perm[t]];
+    }
+    cfb_nb_model M{};
+    M.n_num = (int)n;
+    M.n_cat = (int)m;
+    M.n_classes = (int)K;
+    M.labels = labels.data();
+    M.prior = prior.data();
+    M.mean = mean.data();
+    M.var = var.data();
+    M.cat_offsets = h.offs.data();
+    M.cat_keys = h.keys.data();
+    M.cat_prob = prob.data();
+    cfb_model_destroy(t_cache.model);
+    t_cache.model = nullptr;
+    Check(cfb_model_create_nb(Device(), &M, &t_cache.model));
+    t_cache.params = p;
+    t_cache.tag = tag;
+    model = t_cache.model;
+  }
+  Check(cfb_predict_host(model, cols.num.data(), cols.num_sel.data(), cols.cat.data(), cols.cat_sel.data(), rows, CFB_PREDICT_LABEL,
+                         FlatVector::GetData<int32_t>(result)));
+}
+
+// qda.cpp:338-498.  params = [K | S | idx | keys | labels[K] | per class: Q[p x p] column-major, l[p], intercept |
+//                             (means[p] when normalize)], p = n + number of keys; the result is the class LABEL (:480)
+void qda_impute(duckdb::DataChunk &args, duckdb::ExpressionState &, duckdb::Vector &result) {
+  using namespace duckdb;
+  const idx_t rows = args.size();
+  if (rows == 0) return;
+  if (args.ColumnCount() < 2) throw InvalidInputException("qda_predict(params, normalize, columns...)");
+  const std::vector<float> p = Params(args.data[0], rows);
+  const bool normalize = Flag(args.data[1], rows);
+  Columns cols;
+  Classify(args, 2, cols);
+  const size_t n = cols.num.size(), m = cols.cat.size();
+  const int tag = (int)(16 | (normalize ? 2 : 0) | (n << 8) | (m << 16));
+  cfb_model *model = Cached(p, tag);
+  if (!model) {
+    ClassHead h = ParseHead(p, m, "qda_predict");
+    const size_t K = h.K, total = h.total, P = n + total, per_class = P * P + P + 1, at = h.next + K;
+    if (P == 0 || p.size() < at + K * per_class + (normalize ? P : 0)) throw InvalidInputException("qda_predict: parameter list too short for these columns");
+    const std::vector<size_t> perm = SortKeys(h, m);
+    // feature f -> its position in the list's order (numeric columns stay, keys follow the sort)
+    std::vector<size_t> src(P);
+    for (size_t i = 0; i < n; i++) src[i] = i;
+    for (size_t t = 0; t < total; t++) src[n + t] = n + perm[t];
+    std::vector<int32_t> labels(K);
+    std::vector<double> quad(K * P * P), lin(K * P), icpt(K), center(P);
+    for (size_t k = 0; k < K; k++) {
+      labels[k] = (int32_t)p[h.next + k];
+      const size_t base = at + k * per_class;
+      for (size_t j = 0; j < P; j++) {
+        for (size_t i = 0; i < P; i++) quad[k * P * P + i + j * P] = p[base + src[i] + src[j] * P];
+        lin[k * P + j] = p[base + P * P + src[j]];
+      }
+      icpt[k] = p[base + P * P + P];
+    }
+    if (normalize)
+      for (size_t j = 0; j < P; j++) center[j] = p[at + K * per_class + src[j]];
+    cfb_qda_model M{};
+    M.n_num = (int)n;
+    M.n_cat = (int)m;
+    M.n_classes = (int)K;
+    M.labels = labels.data();
+    M.quad = quad.data();
+    M.lin = lin.data();
+    M.intercept = icpt.data();
+    M.center = normalize ? center.data() : nullptr;
+    M.cat_offsets = h.offs.data();
+    M.cat_keys = h.keys.data();
+    cfb_model_destroy(t_cache.model);
+    t_cache.model = nullptr;
+    Check(cfb_model_create_qda(Device(), &M, &t_cache.model));
+    t_cache.params = p;
+    t_cache.tag = tag;
+    model = t_cache.model;
+  }
+  Check(cfb_predict_host(model, cols.num.data(), cols.num_sel.data(), cols.cat.data(), cols.cat_sel.data(), rows, CFB_PREDICT_LABEL,
+                         FlatVector::GetData<int32_t>(result)));
 }
 
 // lda.cpp:421-590.  params = [K | S | idx_0..idx_{S-1} | unique keys | target labels[K] | coefficients[K][n + total] |
@@ -265,6 +445,18 @@ duckdb::unique_ptr<duckdb::FunctionData> linreg_impute_bind(duckdb::ClientContex
 duckdb::unique_ptr<duckdb::FunctionData> LDA_impute_bind(duckdb::ClientContext &, duckdb::ScalarFunction &function,
                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &) {
   function.return_type = duckdb::LogicalType::INTEGER;  // lda.cpp:593-601
+  function.varargs = duckdb::LogicalType::ANY;
+  return duckdb::make_uniq<duckdb::VariableReturnBindData>(function.return_type);
+}
+duckdb::unique_ptr<duckdb::FunctionData> nb_impute_bind(duckdb::ClientContext &, duckdb::ScalarFunction &function,
+                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &) {
+  function.return_type = duckdb::LogicalType::INTEGER;  // naive_bayes.cpp:265-275
+  function.varargs = duckdb::LogicalType::ANY;
+  return duckdb::make_uniq<duckdb::VariableReturnBindData>(function.return_type);
+}
+duckdb::unique_ptr<duckdb::FunctionData> qda_impute_bind(duckdb::ClientContext &, duckdb::ScalarFunction &function,
+                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &) {
+  function.return_type = duckdb::LogicalType::INTEGER;  // qda.cpp:500-509
   function.varargs = duckdb::LogicalType::ANY;
   return duckdb::make_uniq<duckdb::VariableReturnBindData>(function.return_type);
 }

@@ -66,6 +66,16 @@ void Load(duckdb::DatabaseInstance &instance) {
   lda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
   ExtensionUtil::RegisterFunction(instance, lda_predict);
 
+  // qda_predict / nb_predict (ext.cpp:234-249)
+  ScalarFunction qda_predict("qda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::qda_impute, ML::qda_impute_bind, nullptr);
+  qda_predict.varargs = LogicalType::ANY;
+  qda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, qda_predict);
+  ScalarFunction nb_predict("nb_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::nb_impute, ML::nb_impute_bind, nullptr);
+  nb_predict.varargs = LogicalType::ANY;
+  nb_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, nb_predict);
+
   constexpr int kMaxCols = 20;
   for (int i = 0; i <= kMaxCols; i++)
     for (int j = 0; j <= kMaxCols; j++) {

@@ -113,12 +113,19 @@ void WriteResults(const std::vector<cfb_result> &res, duckdb::Vector &result, bo
 
 }  // namespace Triple
 
-// linreg_predict / lda_predict: the write-back step of MICE (ML/regression.h, ML/lda.h)
+// linreg_predict / lda_predict / nb_predict / qda_predict: the write-back step of MICE (ML/regression.h, ML/lda.h, ...)
 namespace ML {
 void linreg_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
 duckdb::unique_ptr<duckdb::FunctionData> linreg_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
                                                             duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 void LDA_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
 duckdb::unique_ptr<duckdb::FunctionData> LDA_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                         duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+// nb_predict / qda_predict (ML/naive_bayes.h, ML/qda.h)
+void nb_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> nb_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+void qda_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> qda_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 }  // namespace ML

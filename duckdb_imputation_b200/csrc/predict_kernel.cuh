@@ -33,7 +33,34 @@ struct PredictArgs {
   const double *d_model;    // [kb] bias | [n][kb] w_num | [total][kb] w_cat  (padding: weight 0, bias -inf)
   const int *d_map;         // [map_total] position within w_cat rows, or -1
   void *out;
+  // stochastic regression (linreg_predict with noise = true, regression.cpp:495-505): score += sigma * N(0, 1), the
+  // normal drawn by a counter-based generator from (seed, first_row + row) -- reproducible whatever the chunking
+  double noise_sigma;
+  unsigned long long noise_seed, noise_first;
 };
+
+// Philox-4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): a pure function of (key, counter).
+__device__ __forceinline__ uint4 philox4x32(unsigned long long key, unsigned long long counter) {
+  unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+  uint4 c = make_uint4((unsigned)counter, (unsigned)(counter >> 32), 0x9E3779B9u, 0xBB67AE85u);
+#pragma unroll
+  for (int round = 0; round < 10; round++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+// One standard normal per (seed, row): Box-Muller on two 53-bit / 32-bit uniforms, the same transform the reference
+// applies to libc random() (regression.cpp:496-503).
+__device__ __forceinline__ double predict_normal(unsigned long long seed, unsigned long long row) {
+  const uint4 r = philox4x32(seed, row);
+  const double u1 = ((double)(((unsigned long long)r.x << 21) ^ (r.y >> 11)) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+  const double u2 = (double)r.z * (1.0 / 4294967296.0);                                                          // [0, 1)
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
 
 __host__ __device__ inline size_t predict_smem_bytes(int n, int kb, int total, int map_total) {
   return (size_t)kb * (1 + n + total) * 8 + (size_t)map_total * 4;
@@ -87,6 +114,13 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
       if (p2 >= 0) acc2 += w_cat[p2];
       if (p3 >= 0) acc3 += w_cat[p3];
     }
+    if (a.noise_sigma != 0.0) {
+      const unsigned long long r0 = a.noise_first + 4 * q;
+      acc0 += a.noise_sigma * predict_normal(a.noise_seed, r0);
+      acc1 += a.noise_sigma * predict_normal(a.noise_seed, r0 + 1);
+      acc2 += a.noise_sigma * predict_normal(a.noise_seed, r0 + 2);
+      acc3 += a.noise_sigma * predict_normal(a.noise_seed, r0 + 3);
+    }
     if (!a.cols.group) {
       reinterpret_cast<float4 *>(out)[q] = make_float4((float)acc0, (float)acc1, (float)acc2, (float)acc3);
     } else {
@@ -107,6 +141,7 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
       const int pos = d < (unsigned)a.map_len[c] ? map[a.map_off[c] + d] : -1;
       if (pos >= 0) acc += w_cat[pos];
     }
+    if (a.noise_sigma != 0.0) acc += a.noise_sigma * predict_normal(a.noise_seed, a.noise_first + r);
     out[r] = (float)acc;
   }
 }
@@ -162,6 +197,112 @@ __global__ void __launch_bounds__(kPredictThreads) predict_multi_kernel(const __
       }
     if (a.mode == 0) static_cast<float *>(a.out)[r] = (float)acc[0];
     else static_cast<int *>(a.out)[r] = best_k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nb_predict (ML::nb_impute, ML/naive_bayes.cpp:153-263): per row and class the product of the prior, one Gaussian
+// density per numeric column and one probability per categorical column; the LABEL of the first class whose product
+// is the largest (class 0 when every product is 0).  fp64 and the reference's own expression, so that the products
+// agree with it to rounding.  Model in global memory (read through L1): [K] labels live in `labels`.
+struct NbArgs {
+  ScanCols cols;  // group = row mask (nullable)
+  unsigned long long n_rows;
+  int n, m, n_classes, total;
+  int map_lo[kMaxCat], map_off[kMaxCat], map_len[kMaxCat];
+  const int *d_map;        // dense key -> position in [0, total), or -1
+  const int *labels;       // [K]
+  const double *prior;     // [K]
+  const double *norm;      // [K][n]  1 / sqrt(2 pi (var + 1e-9))
+  const double *mean;      // [K][n]
+  const double *two_var;   // [K][n]  2 (var + 1e-9)
+  const double *cat_prob;  // [K][total]
+  int *out;
+};
+
+__global__ void __launch_bounds__(kPredictThreads) predict_nb_kernel(const __grid_constant__ NbArgs a) {
+  for (unsigned long long r = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
+       r += (unsigned long long)gridDim.x * kPredictThreads) {
+    if (a.cols.group && a.cols.group[r] == 0) continue;
+    int pos[kMaxCat];
+    for (int c = 0; c < a.m; c++) {
+      const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
+      pos[c] = d < (unsigned)a.map_len[c] ? a.d_map[a.map_off[c] + d] : -1;
+    }
+    int best = 0;
+    double max_prob = 0.0;
+    for (int k = 0; k < a.n_classes; k++) {
+      double prob = a.prior[k];
+      for (int j = 0; j < a.n; j++) {
+        const double d = (double)a.cols.num[j][r] - a.mean[k * a.n + j];
+        prob *= a.norm[k * a.n + j] * exp(-(d * d) / a.two_var[k * a.n + j]);
+      }
+      for (int c = 0; c < a.m; c++) prob *= pos[c] >= 0 ? a.cat_prob[(size_t)k * a.total + pos[c]] : 0.0;
+      if (prob > max_prob) {
+        max_prob = prob;
+        best = k;
+      }
+    }
+    a.out[r] = a.labels[best];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// qda_predict (ML::qda_impute, ML/qda.cpp:338-498): score_k = intercept_k + f^T Q_k f + l_k . f over
+// f = [numeric | one-hot] - centre.  The reference multiplies the dense p x p matrix per row and class
+// (p = n + number of keys).  Here f = z - c with z sparse (n numeric values and m ones), and the host folds the
+// centre into the model: score_k = z^T Q_k z + g_k . z + b_k with g_k = l_k - (Q_k + Q_k^T) c, b_k = intercept_k +
+// c^T Q_k c - l_k . c -- (n + m)^2 terms per row and class whatever the number of keys.
+struct QdaArgs {
+  ScanCols cols;  // group = row mask (nullable)
+  unsigned long long n_rows;
+  int n, m, n_classes, total, p;  // p = n + total
+  int map_lo[kMaxCat], map_off[kMaxCat], map_len[kMaxCat];
+  const int *d_map;
+  const int *labels;  // [K]
+  const double *Q;    // [K][p][p], Q[k][i + j * p] (column-major like the reference's dgemv operand)
+  const double *g;    // [K][p]
+  const double *b;    // [K]
+  int *out;
+};
+
+__global__ void __launch_bounds__(kPredictThreads) predict_qda_kernel(const __grid_constant__ QdaArgs a) {
+  const int n = a.n, m = a.m, p = a.p;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
+       r += (unsigned long long)gridDim.x * kPredictThreads) {
+    if (a.cols.group && a.cols.group[r] == 0) continue;
+    double x[32];
+    int at[kMaxCat];  // index of the row's one-hot entry of column c in f, or -1
+    for (int i = 0; i < n; i++) x[i] = (double)a.cols.num[i][r];
+    for (int c = 0; c < m; c++) {
+      const unsigned d = (unsigned)(a.cols.cat[c][r] - a.map_lo[c]);
+      const int pos = d < (unsigned)a.map_len[c] ? a.d_map[a.map_off[c] + d] : -1;
+      at[c] = pos >= 0 ? n + pos : -1;
+    }
+    int best = 0;
+    double max_score = -1.7976931348623157e308;
+    for (int k = 0; k < a.n_classes; k++) {
+      const double *Q = a.Q + (size_t)k * p * p, *g = a.g + (size_t)k * p;
+      double s = a.b[k];
+      for (int j = 0; j < n; j++) {  // numeric x numeric, numeric x one-hot, linear
+        double col = g[j];
+        for (int i = 0; i < n; i++) col += x[i] * Q[i + (size_t)j * p];
+        for (int c = 0; c < m; c++)
+          if (at[c] >= 0) col += Q[at[c] + (size_t)j * p] + Q[j + (size_t)at[c] * p];
+        s += col * x[j];
+      }
+      for (int c = 0; c < m; c++) {  // one-hot x one-hot, linear
+        if (at[c] < 0) continue;
+        s += g[at[c]];
+        for (int e = 0; e < m; e++)
+          if (at[e] >= 0) s += Q[at[c] + (size_t)at[e] * p];
+      }
+      if (s > max_score) {
+        max_score = s;
+        best = k;
+      }
+    }
+    a.out[r] = a.labels[best];
   }
 }
 

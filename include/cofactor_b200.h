@@ -280,8 +280,48 @@ typedef struct cfb_model cfb_model;
 int cfb_model_create(int device, const cfb_linear_model *model, cfb_model **out);
 void cfb_model_destroy(cfb_model *model);
 
+/* Stochastic regression: linreg_predict(params, noise = true, ...) adds sigma * N(0, 1) to every prediction
+ * (ML/regression.cpp:495-505; the MICE driver always asks for it, imputation_base.cpp:133).  The reference draws from
+ * libc random() seeded from /dev/urandom; here the normal of row r is a pure function of (seed, first_row + r) --
+ * Philox-4x32-10 + Box-Muller on the device -- so a query is reproducible whatever its chunking.  sigma = 0 switches
+ * the noise off.  Applies to CFB_PREDICT_SCORE of a single-output linear model; first_row is where the next
+ * cfb_predict_* call's rows start in the stream.                                                              */
+int cfb_model_set_noise(cfb_model *model, double sigma, uint64_t seed, uint64_t first_row);
+
+/* Gaussian naive Bayes (ML::nb_impute, ML/naive_bayes.cpp:153-263): per class k
+ *     p_k(row) = prior[k] * PROD_j N(x_j; mean[k][j], var[k][j] + 1e-9) * PROD_c prob[k][position of key_c]
+ * (0 for a key the model does not hold); the result is labels[first k with the largest p_k] (labels[0] when every
+ * p_k is 0), computed in fp64 with the reference's expression.                                                  */
+typedef struct cfb_nb_model {
+  int32_t n_num, n_cat, n_classes;
+  const int32_t *labels;      /* [n_classes]                                          */
+  const double *prior;        /* [n_classes]                                          */
+  const double *mean, *var;   /* [n_classes][n_num]                                   */
+  const int64_t *cat_offsets; /* [n_cat + 1]                                          */
+  const int32_t *cat_keys;    /* [cat_offsets[n_cat]], ascending within a column      */
+  const double *cat_prob;     /* [n_classes][cat_offsets[n_cat]]                      */
+} cfb_nb_model;
+int cfb_model_create_nb(int device, const cfb_nb_model *model, cfb_model **out);
+
+/* Quadratic discriminant analysis (ML::qda_impute, ML/qda.cpp:338-498): over the features f = [numeric | one-hot]
+ * minus `center` (NULL = not normalized),  score_k = intercept[k] + f^T Q_k f + lin[k] . f ;  the result is
+ * labels[first k with the largest score].  quad is [n_classes][p][p] with p = n_num + number of keys, each Q_k
+ * column-major as the reference hands it to dgemv.                                                             */
+typedef struct cfb_qda_model {
+  int32_t n_num, n_cat, n_classes;
+  const int32_t *labels;      /* [n_classes]                                          */
+  const double *quad;         /* [n_classes][p][p]                                    */
+  const double *lin;          /* [n_classes][p]                                       */
+  const double *intercept;    /* [n_classes]                                          */
+  const double *center;       /* [p] or NULL                                          */
+  const int64_t *cat_offsets; /* [n_cat + 1]                                          */
+  const int32_t *cat_keys;    /* [cat_offsets[n_cat]], ascending within a column      */
+} cfb_qda_model;
+int cfb_model_create_qda(int device, const cfb_qda_model *model, cfb_model **out);
+
 #define CFB_PREDICT_SCORE 0  /* out: float  [rows], score_0                              */
 #define CFB_PREDICT_ARGMAX 1 /* out: int32  [rows], first index of the largest score     */
+#define CFB_PREDICT_LABEL 2  /* out: int32  [rows], the class label (naive Bayes / QDA models) */
 
 /* Device-resident columns -> d_out (device).  d_row_mask (nullable, int32 per row): only rows with a
  * non-zero mask are written, the others keep their value -- with d_out aliasing the imputed column
