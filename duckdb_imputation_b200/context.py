@@ -111,6 +111,12 @@ class CofactorContext:
         finally:
             nat.lib().cfb_result_free(C.byref(res))
 
+    def finalize_result(self, group: int = 0) -> "ResultHandle":
+        """The canonical result as an owned cfb_result (for cfb_result_combine / cfb_result_multiply)."""
+        h = ResultHandle()
+        nat.check(nat.lib().cfb_ctx_finalize(self._h, group, C.byref(h.res)))
+        return h
+
     def finalize(self, group: int = 0, narrow: bool = True) -> dict:
         return arrays_to_struct(self.finalize_arrays(group), narrow)
 
@@ -133,6 +139,31 @@ class CofactorContext:
 
     def import_partial(self, d_f64, d_u64, stream: int = 0):
         nat.check(nat.lib().cfb_ctx_import_partial(self._h, _addr(d_f64), _addr(d_u64), stream or None))
+
+
+class ResultHandle:
+    """An owned cfb_result: ring sum / difference of results through the C ABI (cfb_result_combine) -- the delta
+    cofactors of a MICE loop (imputation/triple/sub.cpp:71-219): observed = total - nulls."""
+
+    def __init__(self):
+        self.res = nat.Result()
+
+    def combine(self, other: "ResultHandle", sign: int) -> "ResultHandle":
+        out = ResultHandle()
+        nat.check(nat.lib().cfb_result_combine(C.byref(self.res), C.byref(other.res), sign, C.byref(out.res)))
+        return out
+
+    def arrays(self) -> dict:
+        return result_arrays(self.res)
+
+    def close(self):
+        nat.lib().cfb_result_free(C.byref(self.res))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _keep_sel(sels, keep):

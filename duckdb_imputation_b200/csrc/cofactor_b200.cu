@@ -186,6 +186,9 @@ struct cfb_ctx {
   int slab_grid = 0;
   // chain_sum_kernel: per-CTA count slabs (all zero between launches) and the packed one-byte slots it hands to
   // pair_packed_kernel
+  float *d_chain_slab = nullptr;  // its own fp32 slab: sharing d_slab with the slab / role kernels re-allocated it (with a
+  long long chain_slab_floats = 0;  // stream sync) every time a context alternated between large and small scans
+  int chain_slab_grid = 0;
   unsigned *d_cnt_slab = nullptr;
   long long cnt_slab_words = 0;  // per CTA
   int cnt_slab_grid = 0;
@@ -829,8 +832,20 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   if (tile < 512) return 1;
   const unsigned long long n_tiles = (rows + tile - 1) / tile;
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * cfb::kChainCtasPerSm, n_tiles);
-  int rc = ensure_slab(c, D * 4 * cfb::chain_quads(c->n), grid, s);
-  if (rc) return rc;
+  const long long slab_floats = std::max<long long>(4, D * 4 * cfb::chain_quads(c->n));
+  if (slab_floats != c->chain_slab_floats || grid > c->chain_slab_grid) {
+    if (c->d_chain_slab) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
+      cudaFree(c->d_chain_slab);
+      c->d_chain_slab = nullptr;
+    }
+    const int alloc_grid = std::max(grid, c->chain_slab_grid);
+    CU(cudaMalloc(&c->d_chain_slab, (size_t)slab_floats * alloc_grid * sizeof(float)));
+    CU(cudaMemsetAsync(c->d_chain_slab, 0, (size_t)slab_floats * alloc_grid * sizeof(float), s));
+    c->chain_slab_floats = slab_floats;
+    c->chain_slab_grid = alloc_grid;
+  }
   if (D != c->cnt_slab_words || grid > c->cnt_slab_grid) {
     if (c->d_cnt_slab) {
       CU(cudaStreamSynchronize(c->stream));
@@ -854,7 +869,7 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   p.grid = grid;
   p.smem_max = dev_info(c->device).smem_optin - 1024;
   p.smem_bytes = cfb::chain_smem_bytes(c->n, c->m, heads, (int)c->lay.total_dom, tile);
-  p.slab = c->d_slab;
+  p.slab = c->d_chain_slab;
   p.cnt_slab = c->d_cnt_slab;
   p.f64 = c->d_f64;
   p.u64 = c->d_u64;
@@ -1968,7 +1983,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   c->cur = 0;
   c->uses_group = false;
   c->user_stream = nullptr;
-  if (c->packed_cap > (64u << 20)) {  // a parked context keeps small scratch only
+  if (c->packed_cap > (160u << 20)) {  // a parked context keeps moderate scratch only (<= 13 M rows x 12 columns)
     cudaFree(c->d_packed);
     c->d_packed = nullptr;
     c->packed_cap = 0;
@@ -1995,6 +2010,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_partials);
   cudaFree(c->d_ticket);
   cudaFree(c->d_slab);
+  cudaFree(c->d_chain_slab);
   cudaFree(c->d_cnt_slab);
   cudaFree(c->d_packed);
   delete c->role_plan;

@@ -33,3 +33,29 @@ def test_device_loop_matches_host_loop():
         assert (got[msk] == h_cat[c][msk]).mean() > 0.995  # near-ties between two classes may fall either way
     # and the imputations are informative
     assert np.abs(d_num[0].cpu().numpy()[mn[0]] - truth[("n", 0)][mn[0]]).mean() < 0.6 * np.abs(num[0][mn[0]] - truth[("n", 0)][mn[0]]).mean()
+
+
+def test_delta_cofactor_loop_matches_the_filtered_scan_loop():
+    """with the table partitioned by NULL pattern, the cofactor over the rows where a column is
+    observed is total - nulls (cfb_result_combine, the arithmetic of subtract_triple, imputation/triple/sub.cpp:71-219)
+    and only the NULL rows (20 %) are scanned per step.  Same models, same imputations as the loop that rescans the
+    whole table behind a row filter."""
+    rows = 60_001
+    num, cat, mn, mc, _ = mice_loop.synthetic_table(rows, n=5, m=3, dom=5, null_num=(0, 3), null_cat=(2,), seed=21)
+
+    def dev():
+        return ([torch.from_numpy(c.copy()).cuda() for c in num], [torch.from_numpy(c.copy()).cuda() for c in cat],
+                {c: torch.from_numpy(m.astype(np.int32)).cuda() for c, m in mn.items()},
+                {c: torch.from_numpy(m.astype(np.int32)).cuda() for c, m in mc.items()})
+
+    a_num, a_cat, a_nn, a_nc = dev()
+    mice_loop.mice_gpu(a_num, a_cat, a_nn, a_nc, 2, rows)
+    b_num, b_cat, b_nn, b_nc = dev()
+    _, order, _ = mice_loop.mice_gpu_delta(b_num, b_cat, b_nn, b_nc, 2, rows)
+    order = order.cpu().numpy()
+    for c in mn:
+        want, got = a_num[c].cpu().numpy()[order], b_num[c].cpu().numpy()
+        assert np.abs(got - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    for c in mc:
+        want, got = a_cat[c].cpu().numpy()[order], b_cat[c].cpu().numpy()
+        assert (got == want).mean() > 0.999

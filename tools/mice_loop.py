@@ -146,6 +146,123 @@ def mice_gpu(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, lo
     return out
 
 
+# ------------------------------------------------------------------ the device loop with delta cofactors
+def partition_by_null_pattern(d_num, d_cat, d_null_num, d_null_cat):
+    """Reorder the table (in place, once) so that the rows with the same NULL pattern over the imputed columns are
+    contiguous -- what the reference's partition step does to the base table (imputation/partition.cpp).  Returns
+    {(kind, column): [(lo, hi), ...]}: the row ranges where that column is NULL (each range 4-row aligned start is NOT
+    guaranteed: ranges are cut to multiples of 4 rows, the few boundary rows are returned as `ragged` ranges too)."""
+    import torch
+    cols = [("n", c) for c in d_null_num] + [("c", c) for c in d_null_cat]
+    masks = [d_null_num[c] if k == "n" else d_null_cat[c] for k, c in cols]
+    code = torch.zeros_like(masks[0], dtype=torch.int64)
+    for b, msk in enumerate(masks):
+        code += (msk != 0).to(torch.int64) << b
+    # every pattern's block is padded in the ORDER only: rows keep their identity, blocks start where the previous ends
+    order = torch.argsort(code, stable=True)
+    for t in list(d_num) + list(d_cat) + masks:
+        t.copy_(t[order])
+    counts = torch.bincount(code, minlength=1 << len(cols)).cpu().tolist()
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    ranges = {}
+    for b, key in enumerate(cols):
+        rs = []
+        for pat in range(1 << len(cols)):
+            if (pat >> b) & 1 and counts[pat]:
+                lo, hi = int(starts[pat]), int(starts[pat + 1])
+                if rs and rs[-1][1] == lo:
+                    rs[-1] = (rs[-1][0], hi)
+                else:
+                    rs.append((lo, hi))
+        ranges[key] = rs
+    return ranges, order
+
+
+def _scan_ranges(ctx, d_num, d_cat, ranges):
+    """Cofactor of the rows in `ranges`: device pointers must be 16-byte aligned, so a range [lo, hi) is scanned as the
+    aligned middle plus (at most 3 + 3) boundary rows through a slot filter over the enclosing aligned window."""
+    import torch
+    for lo, hi in ranges:
+        a_lo, a_hi = (lo + 3) // 4 * 4, hi
+        if a_lo >= a_hi:
+            a_lo = a_hi = lo
+        if a_hi > a_lo:
+            ctx.scan_device([t[a_lo:a_hi] for t in d_num], [t[a_lo:a_hi] for t in d_cat], a_hi - a_lo)
+        if lo < a_lo:  # the ragged head: rows [lo, a_lo) inside the aligned window [a_lo - 4, a_lo)
+            w = a_lo - 4
+            slot = torch.full((4,), -1, dtype=torch.int32, device=d_num[0].device if d_num else d_cat[0].device)
+            slot[lo - w:] = 0
+            ctx.scan_device([t[w:a_lo] for t in d_num], [t[w:a_lo] for t in d_cat], 4, d_group=slot)
+
+
+def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None):
+    """The loop with DELTA COFACTORS (the idea of imputation_low.cpp:85-110 and the Value-level subtract_triple /
+    sum_triple helpers, imputation/triple/sub.cpp:71-219): the table is partitioned by NULL pattern once; the cofactor
+    of the whole table is computed once and then maintained; per imputed column only its NULL rows (20 %) are scanned:
+
+        nulls    = cofactor(rows where c is NULL)                      one scan of the NULL ranges
+        observed = total - nulls                                       cfb_result_combine(total, nulls, -1)
+        model    = train(observed);  c[NULL rows] = predict(model)     contiguous ranges, no mask
+        total    = total - nulls + cofactor(rows where c is NULL)      second scan of the NULL ranges, two combines
+
+    Returns (per-iteration timings, the permutation applied to the rows)."""
+    import torch
+    from duckdb_imputation_b200 import CFB_TRIPLE, CofactorContext, predict
+    n, m = len(d_num), len(d_cat)
+    ranges, order = partition_by_null_pattern(d_num, d_cat, d_null_num, d_null_cat)
+
+    def cofactor(rs):
+        with CofactorContext(CFB_TRIPLE, n, m) as ctx:
+            if domains is not None:
+                ctx.set_cat_domain([d[0] for d in domains], [d[1] for d in domains])
+            _scan_ranges(ctx, d_num, d_cat, rs)
+            return ctx.finalize_result()
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    total = cofactor([(0, rows)])
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    out = []
+    for it in range(iters):
+        t = {"scan": 0.0, "train": 0.0, "predict": 0.0}
+        for kind, cols in (("c", d_null_cat), ("n", d_null_num)):
+            for c in cols:
+                rs = ranges[(kind, c)]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nulls = cofactor(rs)
+                observed = total.combine(nulls, -1)
+                res = observed.arrays()
+                t1 = time.perf_counter()
+                mdl = train_lda(res, c) if kind == "c" else train_linreg(res, c)
+                lm = predict.LinearModel(mdl["bias"], mdl["w_num"], mdl["keys"], mdl["w_cat"])
+                t2 = time.perf_counter()
+                for lo, hi in rs:
+                    if kind == "c":
+                        predict.predict_device(lm, [x[lo:hi] for x in d_num], [x[lo:hi] for k, x in enumerate(d_cat) if k != c], hi - lo,
+                                               predict.ARGMAX, d_cat[c][lo:hi])
+                    else:
+                        predict.predict_device(lm, [x[lo:hi] for k, x in enumerate(d_num) if k != c], [x[lo:hi] for x in d_cat], hi - lo,
+                                               predict.SCORE, d_num[c][lo:hi])
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+                new_nulls = cofactor(rs)
+                total2 = observed.combine(new_nulls, +1)
+                for h in (total, nulls, observed, new_nulls):
+                    h.close()
+                total = total2
+                t4 = time.perf_counter()
+                lm.close()
+                t["scan"] += (t1 - t0 + t4 - t3) * 1e3
+                t["train"] += (t2 - t1) * 1e3
+                t["predict"] += (t3 - t2) * 1e3
+        out.append(t)
+        if log:
+            log(it, t)
+    total.close()
+    return out, order, setup_ms
+
+
 def synthetic_table(rows, n=20, m=10, dom=10, null_num=(0, 1), null_cat=(0,), null_frac=0.2, seed=5):
     """Correlated columns (so that there is something to impute), NULL cells pre-filled with the column mean / mode
     as init_baseline does (partition.cpp:700-712)."""
@@ -203,6 +320,14 @@ def main():
     ts = mice_gpu(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m, log=log)
     tot = sum(sum(t.values()) for t in ts)
     scans = iters * (len(null_num) + len(null_cat))
+    # the same loop with delta cofactors: one partition + one full scan up front, then only the NULL rows per step
+    td, _, setup_ms = mice_gpu_delta(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m)
+    totd = sum(sum(t.values()) for t in td)
+    print(json.dumps({"summary": "MICE loop with delta cofactors (total - nulls; only the NULL rows are scanned)", "rows": rows,
+                      "iterations": iters, "ms_per_iteration": round(totd / iters, 2), "setup_full_scan_ms": round(setup_ms, 2),
+                      "ms_per_column_scans": round(sum(t["scan"] for t in td) / scans, 2),
+                      "ms_per_predict": round(sum(t["predict"] for t in td) / scans, 2),
+                      "ms_per_train_host": round(sum(t["train"] for t in td) / scans, 2)}), flush=True)
     print(json.dumps({"summary": "MICE loop on one B200, table resident in HBM", "rows": rows, "iterations": iters,
                       "ms_per_iteration": round(tot / iters, 2), "cofactor_scans": scans,
                       "ms_per_scan": round(sum(t["scan"] for t in ts) / scans, 2),
