@@ -630,6 +630,10 @@ def main():
                "rows_per_step": er, "steps": esteps, "host_threads": threads,
                "gb_per_s": world * er * esteps * BYTES_PER_ROW / dt / 1e9,
                "host_copy_ceiling_gb_per_s": ceil_nt, "stage_isa": lib.cfb_stage_isa().decode(),
+               # bytes the host memory system moves: the feed reads the source, writes the staging tile and the DMA engine
+               # reads it again (3 per payload byte); the copy-only ceiling moves 2 per payload byte
+               "host_dram_traffic_gb_per_s": 3 * world * er * esteps * BYTES_PER_ROW / dt / 1e9,
+               "host_copy_ceiling_traffic_gb_per_s": 2 * ceil_nt,
                "host_copy_ceiling_note": "aggregate GB/s of the staging copy alone (non-temporal stores, 8 KB pieces, private "
                                          "buffers, %d threads x %d ranks at the same time): the host-memory bound of the feed" % (threads, world),
                "path": "pageable host columns -> DuckDB aggregate callbacks (replay host: %d threads, 2048-row chunks, "
