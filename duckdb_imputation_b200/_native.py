@@ -58,7 +58,7 @@ SIGNATURES = {
     "cfb_ctx_combine_slots": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cfb_ctx_finalize": (C.c_int, [_P, C.c_int, C.POINTER(Result)]),
     "cfb_result_free": (None, [C.POINTER(Result)]),
-    "cfb_result_combine": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.c_int, C.POINTER(Result)]),
+    "cfb_result_combine": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.c_int, C.c_int, C.POINTER(Result)]),
     "cfb_result_multiply": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.POINTER(Result)]),
     "cfb_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "cfb_model_destroy": (None, [_P]),

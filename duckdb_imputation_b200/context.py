@@ -148,9 +148,9 @@ class ResultHandle:
     def __init__(self):
         self.res = nat.Result()
 
-    def combine(self, other: "ResultHandle", sign: int) -> "ResultHandle":
+    def combine(self, other: "ResultHandle", sign: int, keep_zero_keys: bool = False) -> "ResultHandle":
         out = ResultHandle()
-        nat.check(nat.lib().cfb_result_combine(C.byref(self.res), C.byref(other.res), sign, C.byref(out.res)))
+        nat.check(nat.lib().cfb_result_combine(C.byref(self.res), C.byref(other.res), sign, 1 if keep_zero_keys else 0, C.byref(out.res)))
         return out
 
     def arrays(self) -> dict:

@@ -2752,9 +2752,11 @@ int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *ou
   return CFB_OK;
 }
 
-int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_result *out) {
+int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int flags, cfb_result *out) {
   if (!a || !b || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (sign != 1 && sign != -1) return fail(CFB_ERR_INVALID, "sign must be +1 or -1");
+  if (flags & ~CFB_COMBINE_KEEP_ZERO_KEYS) return fail(CFB_ERR_INVALID, "combine: unknown flag");
+  const bool keep_zero = (flags & CFB_COMBINE_KEEP_ZERO_KEYS) != 0;
   if (a->kind != b->kind || a->n_num != b->n_num || a->n_cat != b->n_cat || a->n_quad != b->n_quad)
     return fail(CFB_ERR_INVALID, "combine: the two results have different shapes");
   const bool nb = a->kind == CFB_NB;
@@ -2794,7 +2796,7 @@ int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_r
         py = y++;
       }
       const int64_t cnt = (px >= 0 ? a->cat_counts[px] : 0) + sign * (py >= 0 ? b->cat_counts[py] : 0);
-      if (cnt == 0) continue;
+      if (cnt == 0 && !keep_zero) continue;
       keys.push_back(key);
       counts.push_back(cnt);
       src.emplace_back(px, py);
@@ -2833,7 +2835,7 @@ int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_r
       } else {
         u = a->pair_key1[x], v = a->pair_key2[x], cnt = a->pair_counts[x++] + sign * b->pair_counts[y++];
       }
-      if (cnt == 0) continue;
+      if (cnt == 0 && !keep_zero) continue;
       k1.push_back(u);
       k2.push_back(v);
       pc.push_back(cnt);

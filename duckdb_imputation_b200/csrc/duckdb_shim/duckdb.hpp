@@ -180,7 +180,9 @@ struct UnifiedVectorFormat {
   }
 };
 
-// A scalar of one of the fixed-width types (what Vector::GetValue / SetValue exchange on this path).
+// A scalar of one of the fixed-width types (what Vector::GetValue / SetValue exchange on this path), or a nested
+// LIST / STRUCT value (what the MICE drivers' Value-level ring helpers take and return: duckdb::Value::LIST /
+// ::STRUCT, ListValue::GetChildren, StructValue::GetChildren).
 class Value {
  public:
   Value() : v_(0.0) {}
@@ -191,11 +193,52 @@ class Value {
   Value(double d) : v_(d) {}                // NOLINT
   template <class T>
   T GetValue() const {
+    if (nested_ != 0) throw Exception("Conversion Error: Unimplemented type for cast (nested value -> scalar)");
     return static_cast<T>(v_);
   }
+  static Value LIST(const LogicalType &, vector<Value> values) {
+    Value v;
+    v.nested_ = 1;
+    v.children_ = std::move(values);
+    return v;
+  }
+  // DuckDB 0.9.2: the child type is taken from the first element, so an empty list is refused
+  static Value LIST(vector<Value> values) {
+    if (values.empty())
+      throw InternalException("Value::LIST without providing a child-type requires a non-empty list of values. Use Value::LIST(child_type, list) instead.");
+    return LIST(LogicalType(), std::move(values));
+  }
+  static Value STRUCT(child_list_t<Value> values) {
+    Value v;
+    v.nested_ = 2;
+    for (auto &kv : values) {
+      v.names_.push_back(kv.first);
+      v.children_.push_back(std::move(kv.second));
+    }
+    return v;
+  }
+  bool IsList() const { return nested_ == 1; }
+  bool IsStruct() const { return nested_ == 2; }
+  const vector<Value> &NestedChildren() const { return children_; }
+  const vector<string> &ChildNames() const { return names_; }
 
  private:
   double v_;
+  int nested_ = 0;  // 0 scalar, 1 LIST, 2 STRUCT
+  vector<Value> children_;
+  vector<string> names_;
+};
+struct ListValue {
+  static const vector<Value> &GetChildren(const Value &v) {
+    if (!v.IsList()) throw InternalException("ListValue::GetChildren on a value that is not a LIST");
+    return v.NestedChildren();
+  }
+};
+struct StructValue {
+  static const vector<Value> &GetChildren(const Value &v) {
+    if (!v.IsStruct()) throw InternalException("StructValue::GetChildren on a value that is not a STRUCT");
+    return v.NestedChildren();
+  }
 };
 
 class Vector;

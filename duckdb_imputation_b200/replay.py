@@ -48,6 +48,9 @@ class Replay:
         l.replay_set_option.argtypes = [C.c_char_p, C.c_int]
         l.replay_load_via_entry_points.restype = C.c_int
         l.replay_load_via_entry_points.argtypes = [C.POINTER(C.c_char_p)]
+        l.replay_value_ring.restype = C.c_int
+        l.replay_value_ring.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.POINTER(P)]
+        l.replay_value_error.restype = C.c_char_p
         l.replay_free.argtypes = [P]
         l.replay_last_error.restype = C.c_char_p
         l.replay_list_functions.restype = P
@@ -158,6 +161,20 @@ class Replay:
         rc = self.lib.replay_scalar_structs(function.encode(), nb, len(columns), texts, rows, C.byref(out))
         if rc:
             raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            return json.loads(C.string_at(out).decode())
+        finally:
+            self.lib.replay_free(out)
+
+    VALUE_OPS = {"sum_triple": 0, "subtract_triple": 1, "sum_nb_triple": 2}
+
+    def value_ring(self, op: str, a: dict, b: dict) -> dict:
+        """Triple::sum_triple / subtract_triple / sum_nb_triple(a, b) on two ring STRUCT values (dicts; fields are
+        read by position) -- the Value-level helpers of the MICE drivers (imputation/include/sum_sub.h:10-14)."""
+        out = C.c_void_p()
+        rc = self.lib.replay_value_ring(self.VALUE_OPS[op], json.dumps(a).encode(), json.dumps(b).encode(), C.byref(out))
+        if rc:
+            raise ReplayError(self.lib.replay_value_error().decode("utf-8", "replace"))
         try:
             return json.loads(C.string_at(out).decode())
         finally:

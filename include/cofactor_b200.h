@@ -209,13 +209,15 @@ void cfb_result_free(cfb_result *res);
 int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *out);
 
 /* Ring sum / difference of two results: out = a + sign * b, sign = +1 or -1 -- the arithmetic of the Value-level
- * helpers sum_triple / subtract_triple of the MICE drivers (imputation/triple/sum.cpp, sub.cpp:71-219), used to
- * maintain delta cofactors (all rows minus the rows where a column is NULL).  Shapes must match (kind, n_num,
- * n_cat).  Categorical parts are merged by key (a missing key counts 0); keys whose count becomes 0 are dropped,
- * as a finalize of the corresponding state would.  A host-side function on two small results; `out` is owned by
- * the caller afterwards (cfb_result_free).  (The reference returns the non-empty operand unchanged when the
- * other one has empty lists, even for `empty - b`; here the difference is the difference.)                  */
-int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, cfb_result *out);
+ * helpers Triple::sum_triple / subtract_triple / sum_nb_triple of the MICE drivers (imputation/triple/sum.cpp:69-209,
+ * sub.cpp:71-216, sum_nb.cpp:38-82), used to maintain delta cofactors (all rows minus the rows where a column is
+ * NULL).  Shapes must match (kind, n_num, n_cat).  Categorical parts are merged by key (a missing key counts 0).
+ * flags = 0: keys (and key pairs) whose count becomes 0 are dropped, as a finalize of the corresponding state would;
+ * flags = CFB_COMBINE_KEEP_ZERO_KEYS: they stay with count 0, as the reference's std::map merge leaves them
+ * (sub.cpp:14-38) -- host/value_glue.cpp, the Value-level mirror, uses this.  A host-side function on two small
+ * results; `out` is owned by the caller afterwards (cfb_result_free).                                          */
+#define CFB_COMBINE_KEEP_ZERO_KEYS 1
+int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int flags, cfb_result *out);
 
 /* ------------------------------------------------- multi-GPU partial exchange */
 

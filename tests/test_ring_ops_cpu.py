@@ -12,11 +12,11 @@ from oracle import oracle
 from tests.parity import assert_parity, to_result
 
 
-def _combine(a, b, sign):
+def _combine(a, b, sign, flags=0):
     ra, ka = to_result(a)
     rb, kb = to_result(b)
     out = nat.Result()
-    nat.check(nat.lib().cfb_result_combine(C.byref(ra), C.byref(rb), sign, C.byref(out)))
+    nat.check(nat.lib().cfb_result_combine(C.byref(ra), C.byref(rb), sign, flags, C.byref(out)))
     try:
         return result_arrays(out)
     finally:
@@ -46,3 +46,21 @@ def test_combine_rejects_mismatched_shapes_and_signs():
         _combine(A, B, 1)
     with pytest.raises(nat.CofactorError, match="sign"):
         _combine(A, A, 2)
+    with pytest.raises(nat.CofactorError, match="flag"):
+        _combine(A, A, 1, flags=6)
+
+
+def test_keep_zero_keys_leaves_the_emptied_keys_in_place():
+    """CFB_COMBINE_KEEP_ZERO_KEYS: what the reference's std::map merge does (sub.cpp:14-38): (A u B) - B still lists
+    the keys only B had, with count 0."""
+    rng = np.random.default_rng(3)
+    cat = [np.concatenate([rng.integers(0, 4, 50), rng.integers(4, 8, 30)]).astype(np.int32)]
+    num = [rng.random(80).astype(np.float32)]
+    B = oracle.aggregate_arrays(oracle.TRIPLE, [num[0][50:]], [cat[0][50:]])[0]
+    W = oracle.aggregate_arrays(oracle.TRIPLE, num, cat)[0]
+    kept = _combine(W, B, -1, flags=1)
+    dropped = _combine(W, B, -1)
+    assert list(kept["cat_keys"]) == list(W["cat_keys"]) and len(dropped["cat_keys"]) < len(kept["cat_keys"])
+    zero = [i for i, k in enumerate(kept["cat_keys"]) if k >= 4]
+    assert zero and all(kept["cat_counts"][i] == 0 for i in zero)
+    assert len(kept["pair_counts"]) == len(W["pair_counts"])

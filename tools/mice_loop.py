@@ -175,6 +175,8 @@ def partition_by_null_pattern(d_num, d_cat, d_null_num, d_null_cat):
                 else:
                     rs.append((lo, hi))
         ranges[key] = rs
+    ranges["patterns"] = {pat: (int(starts[pat]), int(starts[pat + 1])) for pat in range(1 << len(cols)) if counts[pat]}
+    ranges["bit"] = {key: b for b, key in enumerate(cols)}
     return ranges, order
 
 
@@ -195,17 +197,23 @@ def _scan_ranges(ctx, d_num, d_cat, ranges):
             ctx.scan_device([t[w:a_lo] for t in d_num], [t[w:a_lo] for t in d_cat], 4, d_group=slot)
 
 
-def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None):
+def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None, per_pattern=True):
     """The loop with DELTA COFACTORS (the idea of imputation_low.cpp:85-110 and the Value-level subtract_triple /
     sum_triple helpers, imputation/triple/sub.cpp:71-219): the table is partitioned by NULL pattern once; the cofactor
-    of the whole table is computed once and then maintained; per imputed column only its NULL rows (20 %) are scanned:
+    of the whole table is computed once and then maintained; per imputed column only its NULL rows (20 %) are scanned.
 
+    per_pattern=False, the reference's scheme (two scans of the NULL rows per column):
         nulls    = cofactor(rows where c is NULL)                      one scan of the NULL ranges
         observed = total - nulls                                       cfb_result_combine(total, nulls, -1)
         model    = train(observed);  c[NULL rows] = predict(model)     contiguous ranges, no mask
-        total    = total - nulls + cofactor(rows where c is NULL)      second scan of the NULL ranges, two combines
+        total    = observed + cofactor(rows where c is NULL)           second scan of the NULL ranges
 
-    Returns (per-iteration timings, the permutation applied to the rows)."""
+    per_pattern=True (default) keeps one cofactor PER NULL PATTERN P (the partitions), total = sum over P: the first of
+    the two scans disappears because nulls = sum of the kept cofactors of the patterns that contain c; after the
+    write-back each of those partitions is rescanned once and its cofactor replaced (ONE scan of the NULL rows per
+    column, the rest is ring arithmetic on small results).
+
+    Returns (per-iteration timings, the permutation applied to the rows, setup ms)."""
     import torch
     from duckdb_imputation_b200 import CFB_TRIPLE, CofactorContext, predict
     n, m = len(d_num), len(d_cat)
@@ -218,9 +226,27 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
             _scan_ranges(ctx, d_num, d_cat, rs)
             return ctx.finalize_result()
 
+    def ring_sum(handles):
+        """(sum of the results, whether the caller owns it): one handle is returned as it is."""
+        acc, owned = handles[0], False
+        for h in handles[1:]:
+            nxt = acc.combine(h, +1)
+            if owned:
+                acc.close()
+            acc, owned = nxt, True
+        return acc, owned
+
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    total = cofactor([(0, rows)])
+    by_pattern = {}
+    if per_pattern:
+        by_pattern = {pat: cofactor([r]) for pat, r in ranges["patterns"].items()}
+        total, owned = ring_sum(list(by_pattern.values()))
+        if not owned:  # a single pattern: keep `total` a handle of its own
+            only = total
+            total = only.combine(only, +1).combine(only, -1)
+    else:
+        total = cofactor([(0, rows)])
     setup_ms = (time.perf_counter() - t0) * 1e3
     out = []
     for it in range(iters):
@@ -228,9 +254,13 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
         for kind, cols in (("c", d_null_cat), ("n", d_null_num)):
             for c in cols:
                 rs = ranges[(kind, c)]
+                pats = [p for p in by_pattern if (p >> ranges["bit"][(kind, c)]) & 1]
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                nulls = cofactor(rs)
+                if per_pattern:
+                    nulls, nulls_owned = ring_sum([by_pattern[p] for p in pats])
+                else:
+                    nulls, nulls_owned = cofactor(rs), True
                 observed = total.combine(nulls, -1)
                 res = observed.arrays()
                 t1 = time.perf_counter()
@@ -246,10 +276,17 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
                                                predict.SCORE, d_num[c][lo:hi])
                 torch.cuda.synchronize()
                 t3 = time.perf_counter()
-                new_nulls = cofactor(rs)
+                if per_pattern:
+                    for p in pats:
+                        by_pattern[p].close()
+                        by_pattern[p] = cofactor([ranges["patterns"][p]])
+                    new_nulls, new_owned = ring_sum([by_pattern[p] for p in pats])
+                else:
+                    new_nulls, new_owned = cofactor(rs), True
                 total2 = observed.combine(new_nulls, +1)
-                for h in (total, nulls, observed, new_nulls):
-                    h.close()
+                for h, own in ((total, True), (nulls, nulls_owned), (observed, True), (new_nulls, new_owned)):
+                    if own:
+                        h.close()
                 total = total2
                 t4 = time.perf_counter()
                 lm.close()
@@ -260,6 +297,8 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
         if log:
             log(it, t)
     total.close()
+    for h in by_pattern.values():
+        h.close()
     return out, order, setup_ms
 
 
@@ -321,13 +360,16 @@ def main():
     tot = sum(sum(t.values()) for t in ts)
     scans = iters * (len(null_num) + len(null_cat))
     # the same loop with delta cofactors: one partition + one full scan up front, then only the NULL rows per step
-    td, _, setup_ms = mice_gpu_delta(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m)
-    totd = sum(sum(t.values()) for t in td)
-    print(json.dumps({"summary": "MICE loop with delta cofactors (total - nulls; only the NULL rows are scanned)", "rows": rows,
-                      "iterations": iters, "ms_per_iteration": round(totd / iters, 2), "setup_full_scan_ms": round(setup_ms, 2),
-                      "ms_per_column_scans": round(sum(t["scan"] for t in td) / scans, 2),
-                      "ms_per_predict": round(sum(t["predict"] for t in td) / scans, 2),
-                      "ms_per_train_host": round(sum(t["train"] for t in td) / scans, 2)}), flush=True)
+    for per_pattern in (False, True):
+        td, _, setup_ms = mice_gpu_delta(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m, per_pattern=per_pattern)
+        totd = sum(sum(t.values()) for t in td)
+        what = ("one kept cofactor per NULL pattern, ONE scan of the NULL rows per column" if per_pattern
+                else "total - nulls, two scans of the NULL rows per column")
+        print(json.dumps({"summary": f"MICE loop with delta cofactors ({what})", "rows": rows,
+                          "iterations": iters, "ms_per_iteration": round(totd / iters, 2), "setup_full_scan_ms": round(setup_ms, 2),
+                          "ms_per_column_scans": round(sum(t["scan"] for t in td) / scans, 2),
+                          "ms_per_predict": round(sum(t["predict"] for t in td) / scans, 2),
+                          "ms_per_train_host": round(sum(t["train"] for t in td) / scans, 2)}), flush=True)
     print(json.dumps({"summary": "MICE loop on one B200, table resident in HBM", "rows": rows, "iterations": iters,
                       "ms_per_iteration": round(tot / iters, 2), "cofactor_scans": scans,
                       "ms_per_scan": round(sum(t["scan"] for t in ts) / scans, 2),
