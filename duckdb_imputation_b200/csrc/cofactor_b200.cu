@@ -3128,3 +3128,6 @@ int cfb_ctx_allreduce(cfb_ctx *c, void *comm, void *stream) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------- sigma matrix + trainers
+#include "sigma_train.cuh"

@@ -346,6 +346,68 @@ int replay_predict(const char *scalar, const float *params, size_t n_params, con
   }
 }
 
+int replay_train(const char *scalar, const char *json_triple, int n_consts, const double *consts, const char *const_types,
+                 float **params_out, size_t *n_params_out) {
+  using namespace duckdb;
+  try {
+    if (!scalar || !json_triple || !params_out || !n_params_out || (n_consts && (!consts || !const_types)))
+      throw InvalidInputException("bad arguments");
+    *params_out = nullptr;
+    *n_params_out = 0;
+    auto it = Catalog().scalars.find(scalar);
+    if (it == Catalog().scalars.end())
+      throw InvalidInputException(std::string("Catalog Error: scalar function ") + scalar + " does not exist");
+    ScalarFunction fun = it->second;
+    const LogicalType arg_type = RingType(false);
+    ClientContext context;
+    vector<unique_ptr<Expression>> args;
+    args.push_back(make_uniq<Expression>());
+    args.back()->return_type = arg_type;
+    unique_ptr<FunctionData> bind_data;
+    if (fun.bind) bind_data = fun.bind(context, fun, args);
+    // SELECT <scalar>(<STRUCT literal>, <constants>): one row, every argument a CONSTANT vector but the STRUCT
+    DataChunk chunk;
+    chunk.data.emplace_back(arg_type, 1);
+    const char *p = json_triple;
+    ParseValue(p, chunk.data[0], 0);
+    for (int i = 0; i < n_consts; i++) {
+      switch (const_types[i]) {
+        case 'i':
+          chunk.data.emplace_back(LogicalType::INTEGER, 1);
+          FlatVector::GetData<int32_t>(chunk.data.back())[0] = (int32_t)consts[i];
+          break;
+        case 'f':
+          chunk.data.emplace_back(LogicalType::FLOAT, 1);
+          FlatVector::GetData<float>(chunk.data.back())[0] = (float)consts[i];
+          break;
+        case 'b':
+          chunk.data.emplace_back(LogicalType::BOOLEAN, 1);
+          FlatVector::GetData<uint8_t>(chunk.data.back())[0] = consts[i] != 0.0;
+          break;
+        default:
+          throw InvalidInputException("replay_train: constant types are 'i', 'f' or 'b'");
+      }
+      chunk.data.back().SetVectorType(VectorType::CONSTANT_VECTOR);
+    }
+    chunk.SetCardinality(1);
+    ExpressionState state;
+    Vector result(fun.return_type.id() == LogicalTypeId::LIST && !fun.return_type.children().empty()
+                      ? fun.return_type
+                      : LogicalType::LIST(LogicalType::FLOAT),
+                  1);
+    fun.function(chunk, state, result);
+    const list_entry_t e = ListVector::GetData(result)[0];
+    float *out = (float *)malloc(std::max<size_t>(1, e.length) * sizeof(float));
+    memcpy(out, FlatVector::GetData<float>(ListVector::GetEntry(result)) + e.offset, e.length * sizeof(float));
+    *params_out = out;
+    *n_params_out = e.length;
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out) {
   using namespace duckdb;
   try {

@@ -48,6 +48,12 @@ int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *co
 int replay_predict(const char *scalar, const float *params, size_t n_params, const int *flags, int n_flags, int n_num,
                    int n_cat, const float *const *num, const int32_t *const *cat, const uint32_t *sel, size_t n_sel,
                    size_t rows, void *out);
+/* Run  SELECT <scalar>(<ring STRUCT>, c1, c2, ...)  -- the trainers (linreg_train: label INTEGER, step FLOAT, lambda
+ * FLOAT, max_iterations INTEGER, variance BOOLEAN, normalize BOOLEAN; lda_train: label INTEGER, shrinkage FLOAT,
+ * normalize BOOLEAN).  const_types[i] in "ifb" says how consts[i] is handed over.  *params_out: the FLOAT[] the
+ * function returns (malloc'd, free with replay_free).                                                       */
+int replay_train(const char *scalar, const char *json_triple, int n_consts, const double *consts, const char *const_types,
+                 float **params_out, size_t *n_params_out);
 /* Shapes of DuckDB's protocol that a plain table scan does not produce (process-wide; "reset" restores all):
  *   no_simple = 1          never plan an ungrouped aggregate: use update() with per-row state pointers
  *   lift_shape = 1|2|3     the lifted STRUCT reaches the aggregate as a DICTIONARY vector (1), as a flat vector with

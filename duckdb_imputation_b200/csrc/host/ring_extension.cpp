@@ -66,6 +66,16 @@ void Load(duckdb::DatabaseInstance &instance) {
   lda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
   ExtensionUtil::RegisterFunction(instance, lda_predict);
 
+  // lda_train / linreg_train (ext.cpp:184-189, :202-207): sigma assembly and solves on the device
+  ScalarFunction lda_train_func("lda_train", {LogicalType::ANY}, LogicalTypeId::LIST, lda_train, lda_train_bind, nullptr);
+  lda_train_func.varargs = LogicalType::ANY;
+  lda_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, lda_train_func);
+  ScalarFunction linreg_train_func("linreg_train", {LogicalType::ANY}, LogicalTypeId::LIST, ML::ridge_linear_regression,
+                                   ML::ridge_linear_regression_bind, nullptr);
+  linreg_train_func.varargs = LogicalType::ANY;
+  linreg_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+  ExtensionUtil::RegisterFunction(instance, linreg_train_func);
   // qda_predict / nb_predict (ext.cpp:234-249)
   ScalarFunction qda_predict("qda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::qda_impute, ML::qda_impute_bind, nullptr);
   qda_predict.varargs = LogicalType::ANY;

@@ -128,4 +128,12 @@ duckdb::unique_ptr<duckdb::FunctionData> nb_impute_bind(duckdb::ClientContext &c
 void qda_impute(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
 duckdb::unique_ptr<duckdb::FunctionData> qda_impute_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
                                                          duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
+// linreg_train (ML/regression.h): sigma assembly + gradient descent on the device (train_glue.cpp)
+void ridge_linear_regression(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> ridge_linear_regression_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                                      duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);
 }  // namespace ML
+// lda_train (ML/lda.h:8, a global function in the reference too)
+void lda_train(duckdb::DataChunk &args, duckdb::ExpressionState &state, duckdb::Vector &result);
+duckdb::unique_ptr<duckdb::FunctionData> lda_train_bind(duckdb::ClientContext &context, duckdb::ScalarFunction &function,
+                                                        duckdb::vector<duckdb::unique_ptr<duckdb::Expression>> &arguments);

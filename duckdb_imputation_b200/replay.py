@@ -48,6 +48,9 @@ class Replay:
         l.replay_set_option.argtypes = [C.c_char_p, C.c_int]
         l.replay_load_via_entry_points.restype = C.c_int
         l.replay_load_via_entry_points.argtypes = [C.POINTER(C.c_char_p)]
+        l.replay_train.restype = C.c_int
+        l.replay_train.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_char_p, C.POINTER(P),
+                                   C.POINTER(C.c_size_t)]
         l.replay_value_ring.restype = C.c_int
         l.replay_value_ring.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.POINTER(P)]
         l.replay_value_error.restype = C.c_char_p
@@ -163,6 +166,22 @@ class Replay:
             raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
         try:
             return json.loads(C.string_at(out).decode())
+        finally:
+            self.lib.replay_free(out)
+
+    def train(self, function: str, triple: dict, *consts):
+        """SELECT function(triple, consts...): linreg_train(triple, label, step, lambda, max_iterations, variance,
+        normalize) / lda_train(triple, label, shrinkage, normalize) -> the FLOAT[] parameter list (numpy float32).
+        Python ints are handed over as INTEGER, floats as FLOAT, bools as BOOLEAN."""
+        types = "".join("b" if isinstance(c, bool) else "i" if isinstance(c, (int, np.integer)) else "f" for c in consts)
+        vals = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
+        out, n = C.c_void_p(), C.c_size_t()
+        rc = self.lib.replay_train(function.encode(), json.dumps(triple).encode(), len(consts), vals, types.encode(),
+                                   C.byref(out), C.byref(n))
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_float)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
         finally:
             self.lib.replay_free(out)
 

@@ -336,6 +336,41 @@ int cfb_predict_device(cfb_model *model, const float *const *d_num_cols, const i
 int cfb_predict_host(cfb_model *model, const float *const *num_cols, const uint32_t *const *num_sel,
                      const int32_t *const *cat_cols, const uint32_t *const *cat_sel, size_t count, int mode, void *out);
 
+/* --------------------------------------------- the trainers' moment matrix and solves */
+
+/* The p x p "sigma" matrix of the one-hot expanded design [1 | numeric columns | one column per (categorical column,
+ * key)] -- what build_sigma_matrix assembles on the host for every trainer (ML/utils.cpp:176-310) -- assembled on the
+ * device in fp64, with the reference's one-hot layout (n_cols_1hot_expansion, ML/utils.cpp:522-576: the keys that
+ * occur, per column, ascending as uint64; drop_first removes each column's first key).
+ *   label_cat >= 0   that categorical column is the class label of LDA: it is left out of the matrix, and the handle
+ *                    also holds the per-class sums (build_sum_vector, ML/lda.cpp:58-144); -1 keeps every column.
+ * cfb_sigma_from_ctx reads the dense device state of a context directly (no finalize; the only read-back is which
+ * keys occur); contexts with hashed pair counts or key dictionaries go through cfb_ctx_finalize internally.      */
+typedef struct cfb_sigma cfb_sigma;
+int cfb_sigma_from_result(int device, const cfb_result *res, int label_cat, int drop_first, cfb_sigma **out);
+int cfb_sigma_from_ctx(cfb_ctx *ctx, int group, int label_cat, int drop_first, cfb_sigma **out);
+void cfb_sigma_destroy(cfb_sigma *sigma);
+/* p; the number of classes (keys of label_cat; 0 without one); the length of cat_array (all columns' keys). */
+int cfb_sigma_shape(const cfb_sigma *sigma, int32_t *p, int32_t *n_classes, int64_t *n_cat_values);
+/* cat_array [n_cat_values] and cat_vars_idxs [n_cat + 1] as the trainers store them in their parameter lists. */
+int cfb_sigma_layout(const cfb_sigma *sigma, int64_t *cat_array, int32_t *cat_vars_idxs);
+/* The matrix (row-major, [p][p]) and the class sums ([n_classes][p]); either pointer may be NULL. */
+int cfb_sigma_download(const cfb_sigma *sigma, double *sigma_out, double *class_sums_out);
+
+/* ML::ridge_linear_regression (ML/regression.cpp:113-356) on the device: batch gradient descent with
+ * Barzilai-Borwein steps and backtracking line search on sigma, one persistent cooperative kernel (the matrix stays
+ * in L1 / L2; one grid barrier per matrix-vector product).  `label` is the numeric column to predict (0-based);
+ * step_size and lambda are FLOAT as in the reference.  coeff [p]: intercept, then one coefficient per matrix column
+ * (coeff[label + 1] = -1), already rescaled when normalize != 0; means [p] (normalize only); *variance =
+ * theta^T Sigma theta / N of the final parameters (the reference emits its square root).                          */
+int cfb_sigma_linreg_train(cfb_sigma *sigma, int label, float step_size, float lambda, int max_iterations, int normalize,
+                           double *coeff, double *means, double *variance, int32_t *iterations);
+/* lda_train (ML/lda.cpp:154-330) on the device: within-class covariance with shrinkage, divided by N, solved against
+ * the class means by a blocked Cholesky factorisation (the reference calls dgelsd; for the positive definite matrix
+ * shrinkage > 0 produces the two agree; a matrix that is not positive definite is CFB_ERR_STATE here).
+ * coef [n_classes][p - 1], intercept [n_classes], means [p] (normalize only).                                     */
+int cfb_sigma_lda_train(cfb_sigma *sigma, float shrinkage, int normalize, double *coef, double *intercept, double *means);
+
 /* ------------------------------------------------------ synthetic inputs (tests, bench) */
 
 /* Counter-based generators for device-resident synthetic columns: element i of the

@@ -391,3 +391,236 @@ def qda_predict(params, normalize, num_cols, cat_cols):
         l = p[base + P * P:base + P * P + P].astype(np.float64)
         scores[:, k] = np.float64(p[base + P * P + P]) + np.einsum("ri,ij,rj->r", feats, Q, feats) + feats @ l
     return p[label_off + np.argmax(scores, axis=1)].astype(np.int32), scores
+
+
+# ------------------------------------------------------------------ trainers (sigma matrix + solves)
+def _ref_key_order(keys):
+    """n_cols_1hot_expansion sorts a column's keys as uint64 (ML/utils.cpp:541-556): negative keys after the others."""
+    return sorted(keys, key=lambda k: int(k) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _emit_key(k):
+    """cat_array is uint64 (ML/utils.cpp:534): a negative key reaches the FLOAT[] as 2^64 + key."""
+    return float(int(k) & 0xFFFFFFFFFFFFFFFF)
+
+
+def one_hot_layout(s: dict, drop_first=False):
+    """cat_array, cat_vars_idxs of n_cols_1hot_expansion (ML/utils.cpp:522-576) for a ring STRUCT dict."""
+    cat_array, idxs = [], [0]
+    for col in s["lin_cat"]:
+        ks = _ref_key_order([e["key"] for e in col])
+        if drop_first:
+            ks = ks[1:]
+        cat_array += ks
+        idxs.append(len(cat_array))
+    return cat_array, idxs
+
+
+def build_sigma(s: dict, label_cat=-1, drop_first=False):
+    """Restatement of build_sigma_matrix (ML/utils.cpp:176-310) over a ring STRUCT dict (values as the STRUCT holds
+    them: FLOAT).  Returns (sigma [p, p] float64, cat_array, cat_vars_idxs).  With a categorical label the column is
+    left out and the later columns move up (`skipped_var_categories`)."""
+    n, m = len(s["lin_agg"]), len(s["lin_cat"])
+    cat_array, idxs = one_hot_layout(s, drop_first)
+    label_keys = idxs[label_cat + 1] - idxs[label_cat] if label_cat >= 0 else 0
+    p = 1 + n + idxs[m] - label_keys
+    sig = np.zeros((p, p))
+    sig[0, 0] = s["N"]
+    lin = np.asarray(s["lin_agg"], np.float64)
+    sig[0, 1:n + 1] = lin
+    sig[1:n + 1, 0] = lin
+    q = np.asarray(s["quad_agg"], np.float64)
+    for i in range(n):
+        for j in range(i, n):
+            sig[1 + i, 1 + j] = sig[1 + j, 1 + i] = q[i * n - i * (i + 1) // 2 + j]
+
+    def index(k, key):
+        if k == label_cat:
+            return -1
+        col = cat_array[idxs[k]:idxs[k + 1]]
+        if key not in col:
+            return -1                                            # dropped first key
+        return 1 + n + idxs[k] + col.index(key) - (label_keys if label_cat >= 0 and k > label_cat else 0)
+
+    for k in range(m):
+        for e in s["lin_cat"][k]:
+            i = index(k, e["key"])
+            if i >= 0:
+                sig[0, i] = sig[i, 0] = sig[i, i] = e["value"]
+    for num in range(n):
+        for k in range(m):
+            for e in s["quad_num_cat"][num * m + k]:
+                i = index(k, e["key"])
+                if i >= 0:
+                    sig[i, 1 + num] = sig[1 + num, i] = e["value"]
+    t = 0
+    for k in range(m):
+        for l in range(k, m):
+            for e in s["quad_cat"][t]:
+                a, b = index(k, e["key1"]), index(l, e["key2"])
+                if a >= 0 and b >= 0:
+                    sig[a, b] = sig[b, a] = e["value"]
+            t += 1
+    return sig, cat_array, idxs
+
+
+def standardize_sigma(sig):
+    """standardize_sigma (ML/utils.cpp:580-599); returns (sigma', means, stds)."""
+    N = sig[0, 0]
+    means = sig[0] / N
+    with np.errstate(invalid="ignore", divide="ignore"):
+        stds = np.sqrt(np.diag(sig) / N - (sig[0] / N) ** 2)
+        out = sig.copy()
+        out[1:, 1:] = (sig[1:, 1:] - np.outer(means[1:], sig[0, 1:]) - np.outer(sig[0, 1:], means[1:])
+                       + N * np.outer(means[1:], means[1:])) / np.outer(stds[1:], stds[1:])
+    out[0, 1:] = 0
+    out[1:, 0] = 0
+    return out, means, stds
+
+
+def linreg_train(s: dict, label, step_size, lam, max_iterations, compute_variance, normalize):
+    """Restatement of ML::ridge_linear_regression (ML/regression.cpp:113-356): batch gradient descent with
+    Barzilai-Borwein steps and backtracking line search on the sigma matrix; step_size and lambda are FLOATs.
+    Returns the FLOAT[] parameter list linreg_predict reads."""
+    f32 = np.float32
+    n, m = len(s["lin_agg"]), len(s["lin_cat"])
+    sig, cat_array, idxs = build_sigma(s)
+    p = sig.shape[0]
+    means = stds = None
+    if normalize:
+        sig, means, stds = standardize_sigma(sig)
+    step, lam = f32(step_size), f32(lam)
+    N = sig[0, 0]
+    theta = np.zeros(p)
+    lab = label + 1
+    theta[lab] = -1
+    prev_theta = theta.copy()
+
+    def gradient(th):
+        g = sig @ th / N if N != 0 else np.zeros(p)
+        g[lab] = 0
+        return g
+
+    def error(th):
+        if N == 0:
+            return 0.0
+        return (th @ (sig @ th) / N + float(lam) * (np.sum(th[1:] ** 2) - 1)) / 2
+
+    grad = gradient(theta)
+    upd = grad + float(lam) * theta
+    upd[0] = grad[0]
+    first_norm = np.sqrt(np.sum(upd ** 2) - float(lam) * float(lam))
+    prev_error = error(theta)
+    it = 1
+    while True:
+        update = grad + float(lam) * theta
+        update[0] = grad[0]
+        sq = np.sum(update ** 2)
+        prev_theta, prev_grad = theta.copy(), grad.copy()
+        theta = theta - float(step) * update
+        theta[lab] = -1
+        gnorm = sq - float(lam) * float(lam)
+        dparam = float(step) * np.sqrt(sq)
+        err = error(theta)
+        bt = 0
+        while err > prev_error - float(step / f32(2)) * gnorm and bt < 500:
+            step = step / f32(2)
+            newp = prev_theta - float(step) * update
+            dparam = np.sqrt(np.sum((theta - newp) ** 2))
+            theta = newp
+            theta[lab] = -1
+            err = error(theta)
+            bt += 1
+        if dparam < 1e-20 or np.sqrt(gnorm) / (first_norm + 0.001) < 1e-8:
+            break
+        grad = gradient(theta)
+        pd, gd = theta - prev_theta, grad - prev_grad
+        dss, gss, dgs = np.sum(pd * pd), np.sum(gd * gd), np.sum(pd * gd)
+        if dgs != 0 and gss != 0:
+            ts, tm = dss / dgs, dgs / gss
+            if not (tm < 0 or ts < 0):
+                step = f32(tm if tm / ts > 0.5 else ts - 0.5 * tm)
+        prev_error = err
+        it += 1
+        if not it < max_iterations:
+            break
+    variance = theta @ (sig @ theta) / N if compute_variance else None
+    if normalize:
+        theta[1:] = theta[1:] / stds[1:] * stds[lab]
+        theta[0] = theta[0] * stds[lab] + means[lab]
+    out = [float(m)]
+    if m > 0:
+        out += [float(i) for i in idxs] + [_emit_key(k) for k in cat_array]
+    out += [theta[i] for i in range(p) if i != lab]
+    if normalize:
+        out += [means[i] for i in range(1, p) if i != lab]
+    if compute_variance:
+        out.append(np.sqrt(variance))
+    return np.asarray(out, np.float32), it
+
+
+def lda_train(s: dict, label, shrinkage, normalize, unshifted_sums=False):
+    """Restatement of lda_train (ML/lda.cpp:154-410).  The class sums of the OTHER categorical columns are placed at
+    their sigma positions.  unshifted_sums=True reproduces the reference where it differs: build_sum_vector adds the
+    UN-shifted cat_array index (lda.cpp:131) although the sigma matrix moved the columns behind the label up by the
+    label's key count, so for those columns the sums land `label keys` slots too far right (into the next class's
+    row of the flat array; past its end for the last class -- dropped here).  dgelsd -> numpy lstsq."""
+    n, m = len(s["lin_agg"]), len(s["lin_cat"])
+    sig, cat_array, idxs = build_sigma(s, label_cat=label)
+    p = sig.shape[0]
+    classes = cat_array[idxs[label]:idxs[label + 1]]
+    C = len(classes)
+    label_keys = C
+    sums = np.zeros((C, p))
+    for e in s["lin_cat"][label]:
+        sums[classes.index(e["key"]), 0] = e["value"]
+    for num in range(n):
+        for e in s["quad_num_cat"][num * m + label]:
+            sums[classes.index(e["key"]), 1 + num] = e["value"]
+
+    def index(k, key):
+        col = cat_array[idxs[k]:idxs[k + 1]]
+        return 1 + n + idxs[k] + col.index(key) - (label_keys if k > label and not unshifted_sums else 0)
+
+    flat = sums.reshape(-1)
+    t = 0
+    for k in range(m):
+        for l in range(k, m):
+            if k != l and (k == label or l == label):
+                for e in s["quad_cat"][t]:
+                    at = (classes.index(e["key1"]) * p + index(l, e["key2"]) if k == label
+                          else classes.index(e["key2"]) * p + index(k, e["key1"]))
+                    if at < flat.size:
+                        flat[at] = e["value"]
+            t += 1
+    means = stds = None
+    if normalize:
+        sig, means, stds = standardize_sigma(sig)
+        sums[:, 1:] = (sums[:, 1:] - means[None, 1:] * sums[:, :1]) / stds[None, 1:]
+    S = sig[1:, 1:].copy()
+    q = p - 1
+    for c in range(C):
+        S -= np.outer(sums[c, 1:], sums[c, 1:]) / sums[c, 0]
+    mean_vec = sums[:, 1:] / sums[:, :1]                        # [C, q]
+    sh = np.float32(shrinkage)
+    mu = np.trace(S) / np.float32(q)
+    S = S * float(np.float32(1) - sh)
+    S[np.diag_indices(q)] += float(sh) * mu
+    S /= float(s["N"])
+    coef = np.linalg.lstsq(S, mean_vec.T, rcond=None)[0].T       # [C, q]
+    intercept = -0.5 * np.sum(mean_vec * coef, axis=1) + np.log(sums[:, 0] / float(s["N"]))
+    if normalize:
+        coef = coef / stds[None, 1:]
+    out = [float(C), float(0 if m == 1 else m)]
+    if q - n > 0:
+        remove = 0
+        for i in range(m + 1):
+            if i == label:
+                remove = label_keys
+                continue
+            out.append(float(idxs[i] - remove))
+        out += [_emit_key(k) for k in cat_array[:idxs[label]]] + [_emit_key(k) for k in cat_array[idxs[label + 1]:]]
+    out += [_emit_key(k) for k in classes] + [v for v in coef.reshape(-1)] + [v for v in intercept]
+    if normalize:
+        out += [means[i + 1] for i in range(q)]
+    return np.asarray(out, np.float32)

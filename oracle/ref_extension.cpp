@@ -30,7 +30,7 @@ const char *Implementation() { return "reference"; }
 void Load(duckdb::DatabaseInstance &db) {
   using namespace duckdb;
   // the predict side of the write-back step, as load_ml registers it (duckdb_imputation_extension.cpp:193-249); the
-  // trainers are not registered (no BLAS / LAPACK here), qda_predict neither (ML/qda.cpp does not compile with g++:
+  // QDA trainer is not registered, qda_predict neither (ML/qda.cpp does not compile with g++:
   // `new double[wkopt]` with a double, qda.cpp:209)
   {
     ScalarFunction lda_predict("lda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, LDA_impute, LDA_impute_bind, nullptr, LDA_impute_stats);
@@ -42,6 +42,16 @@ void Load(duckdb::DatabaseInstance &db) {
     linreg_predict.varargs = LogicalType::ANY;
     linreg_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
     ExtensionUtil::RegisterFunction(db, linreg_predict);
+    // the trainers of load_ml (duckdb_imputation_extension.cpp:184-189, :202-207): pins for SURVEY 8 f4
+    ScalarFunction lda_train_func("lda_train", {LogicalType::ANY}, LogicalTypeId::LIST, lda_train, lda_train_bind, nullptr);
+    lda_train_func.varargs = LogicalType::ANY;
+    lda_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, lda_train_func);
+    ScalarFunction linreg_train_func("linreg_train", {LogicalType::ANY}, LogicalTypeId::LIST, ML::ridge_linear_regression,
+                                     ML::ridge_linear_regression_bind, nullptr);
+    linreg_train_func.varargs = LogicalType::ANY;
+    linreg_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, linreg_train_func);
     ScalarFunction nb_predict("nb_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::nb_impute, ML::nb_impute_bind, nullptr);
     nb_predict.varargs = LogicalType::ANY;
     nb_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;

@@ -4,7 +4,8 @@
 // here and the trainers are out of scope:
 //   dgemv   is needed by LDA_impute itself (lda.cpp:561): the textbook column-major y = alpha * op(A) x + beta * y,
 //           written here (the reference links a system BLAS);
-//   dgemm, dgelsd   are only reached from the trainers: they abort loudly.
+//   dgemm, dgelsd   are only reached from lda_train: forwarded to scipy's bundled OpenBLAS when the test harness
+//           names it (below), else they abort loudly.
 #include <cstdio>
 #include <cstdlib>
 
@@ -20,10 +21,35 @@ extern "C" void dgemv(char *trans, int *m, int *n, double *alpha, double *a, int
   }
 }
 
-#define CFB_REF_STUB(name)                                                                           \
-  extern "C" void name(...) {                                                                        \
-    fprintf(stderr, "oracle/_ref: " #name " called -- the reference's trainers are not available\n"); \
-    abort();                                                                                         \
+// dgelsd / dgemm (lda_train, lda.cpp:294-316): forwarded to the LAPACK that ships inside scipy's wheel
+// (scipy.libs/libscipy_openblas*.so exports the Fortran symbols with a scipy_ prefix); oracle/ref_replay.py puts the
+// path into CFB_REF_LAPACK.  Without it the trainers abort loudly, as before.
+#include <dlfcn.h>
+
+namespace {
+void *lapack_symbol(const char *name) {
+  static void *handle = [] {
+    const char *path = getenv("CFB_REF_LAPACK");
+    return path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : nullptr;
+  }();
+  void *sym = handle ? dlsym(handle, name) : nullptr;
+  if (!sym) {
+    fprintf(stderr, "oracle/_ref: %s is not available (set CFB_REF_LAPACK to scipy's libscipy_openblas) -- the reference's LDA trainer cannot run\n", name);
+    abort();
   }
-CFB_REF_STUB(dgemm)
-CFB_REF_STUB(dgelsd)
+  return sym;
+}
+}  // namespace
+
+extern "C" void dgelsd(int *m, int *n, int *nrhs, double *a, int *lda, double *b, int *ldb, double *s, double *rcond, int *rank,
+                       double *work, int *lwork, int *iwork, int *info) {
+  using fn = void (*)(int *, int *, int *, double *, int *, double *, int *, double *, double *, int *, double *, int *, int *, int *);
+  static fn f = (fn)lapack_symbol("scipy_dgelsd_");
+  f(m, n, nrhs, a, lda, b, ldb, s, rcond, rank, work, lwork, iwork, info);
+}
+extern "C" void dgemm(char *ta, char *tb, int *m, int *n, int *k, double *alpha, double *a, int *lda, double *b, int *ldb,
+                      double *beta, double *c, int *ldc) {
+  using fn = void (*)(char *, char *, int *, int *, int *, double *, double *, int *, double *, int *, double *, double *, int *);
+  static fn f = (fn)lapack_symbol("scipy_dgemm_");
+  f(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}

@@ -37,22 +37,25 @@ def time_sum_to_triple(num_cols, cat_cols, threads: int) -> float:
 
 
 class _quiet_stdout:
-    """The reference's predict functions print per-row debug lines to std::cout (regression.cpp:440, :466, lda.cpp:525):
-    file descriptor 1 points at /dev/null while they run."""
+    """The reference's predict functions and trainers print debug lines to std::cout / std::cerr (regression.cpp:440,
+    :466, lda.cpp:157-330, ML/utils.cpp:7): file descriptors 1 and 2 point at /dev/null while they run."""
 
     def __enter__(self):
         import sys
         sys.stdout.flush()
-        self._saved = os.dup(1)
+        sys.stderr.flush()
+        self._saved = [os.dup(1), os.dup(2)]
         self._null = os.open(os.devnull, os.O_WRONLY)
         os.dup2(self._null, 1)
+        os.dup2(self._null, 2)
 
     def __exit__(self, *a):
         import ctypes
         ctypes.CDLL(None).fflush(None)
-        os.dup2(self._saved, 1)
-        os.close(self._saved)
-        os.close(self._null)
+        os.dup2(self._saved[0], 1)
+        os.dup2(self._saved[1], 2)
+        for fd in self._saved + [self._null]:
+            os.close(fd)
 
 
 def predict(function: str, params, flags, num_cols, cat_cols, where=None):
@@ -66,3 +69,28 @@ def seed_libc_random(seed: int):
     """linreg_predict(noise = true) draws from libc random() (regression.cpp:495-505)."""
     import ctypes
     ctypes.CDLL(None).srandom(ctypes.c_uint(seed))
+
+
+def lapack_available() -> bool:
+    """lda_train calls dgelsd / dgemm; oracle/ref_ml_stubs.cpp forwards them to the OpenBLAS inside scipy's wheel."""
+    return _lapack_path() is not None
+
+
+def _lapack_path():
+    import glob
+    try:
+        import scipy
+    except ImportError:
+        return None
+    libs = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+    return libs[0] if libs else None
+
+
+def train(function: str, triple: dict, *consts):
+    """The reference's own linreg_train / lda_train (ML::ridge_linear_regression, lda_train compiled from /root/reference
+    into oracle/_ref) on a ring STRUCT -> FLOAT[] parameter list."""
+    path = _lapack_path()
+    if path:
+        os.environ.setdefault("CFB_REF_LAPACK", path)
+    with _quiet_stdout():
+        return ref().train(function, triple, *consts)
