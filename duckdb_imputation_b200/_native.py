@@ -84,7 +84,7 @@ SIGNATURES = {
     "cfb_sigma_layout": (C.c_int, [_P, _P, _P]),
     "cfb_sigma_download": (C.c_int, [_P, _P, _P]),
     "cfb_sigma_linreg_train": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P,
-                                         C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cfb_sigma_lda_train": (C.c_int, [_P, C.c_float, C.c_int, _P, _P, _P]),
     "cfb_gen_uniform_f32": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64, _P]),
     "cfb_gen_int32": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint32, _P]),

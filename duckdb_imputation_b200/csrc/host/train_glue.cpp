@@ -77,7 +77,7 @@ void ridge_linear_regression(duckdb::DataChunk &args, duckdb::ExpressionState &,
   Check(cfb_sigma_layout(h.s, cat_array.data(), idxs.data()));
   std::vector<double> coeff((size_t)p), means((size_t)p);
   double variance = 0.0;
-  Check(cfb_sigma_linreg_train(h.s, label, step_size, lambda, max_iterations, normalize, coeff.data(), means.data(), &variance, nullptr));
+  Check(cfb_sigma_linreg_train(h.s, label, step_size, lambda, max_iterations, normalize, coeff.data(), means.data(), &variance, nullptr, nullptr));
   // the parameter list (regression.cpp:276-354)
   std::vector<float> d;
   d.push_back((float)m);

@@ -172,10 +172,11 @@ struct BgdArgs {
   int p, label;         // label: index of the label's coefficient (numeric column + 1)
   float step_size, lambda;
   int max_iterations;
+  int rows_per_cta, warps_per_row;  // the band of rows a CTA owns; warps (1, 2, .. 32) sharing one row
   double *v[2];         // two [p] buffers for Sigma * theta (alternating)
   unsigned *barrier;    // zeroed before the launch
   double *theta_out;    // [p]
-  double *scalars_out;  // [0] iterations  [1] last error  [2] theta^T Sigma theta / N of the final theta  [3] backtracking steps
+  double *scalars_out;  // [0] iterations  [1] last error  [2] theta^T Sigma theta / N of the final theta  [3] matrix-vector products
 };
 
 __device__ __forceinline__ double ld_cg_f64(const double *p) {
@@ -184,17 +185,31 @@ __device__ __forceinline__ double ld_cg_f64(const double *p) {
   return v;
 }
 
-// Every thread of every CTA returns the same bits: fixed strides, fixed tree.
-__device__ __forceinline__ double bgd_block_sum(double x, double *red) {
+// K sums at once; every thread of every CTA returns the same bits: fixed strides, fixed trees (shuffle tree inside a
+// warp, one shared-memory exchange, the same tree over the 32 warp results).  `red` holds K * 32 doubles.
+template <int K>
+__device__ __forceinline__ void bgd_block_sums(double (&x)[K], double *red) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  __syncthreads();  // `red` may still be read from the previous sum
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  for (int k = 0; k < K; k++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
+  __syncthreads();  // `red` may still be read from the previous sums
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < K; k++) red[k * 32 + (threadIdx.x >> 5)] = x[k];
   __syncthreads();
-  double s = 0.0;
-#pragma unroll 8
-  for (int w = 0; w < kBgdThreads / 32; w++) s += red[w];
-  return s;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double v = red[k * 32 + (threadIdx.x & 31)];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    x[k] = v;
+  }
+}
+__device__ __forceinline__ double bgd_block_sum(double x, double *red) {
+  double a[1] = {x};
+  bgd_block_sums<1>(a, red);
+  return a[0];
 }
 
 struct BgdGrid {
@@ -202,6 +217,7 @@ struct BgdGrid {
   unsigned target;
   __device__ void sync() {
     __syncthreads();
+    if (gridDim.x == 1) return;  // one CTA: the block barrier orders its global writes for its own threads
     if (threadIdx.x == 0) {
       target += gridDim.x;
       __threadfence();
@@ -210,38 +226,64 @@ struct BgdGrid {
       do {
         asm volatile("ld.global.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter));
       } while ((int)(seen - target) < 0);
+      __threadfence();
     }
     __syncthreads();
   }
 };
 
-// v = Sigma * theta (this CTA's rows), grid barrier, returns theta^T v (same bits everywhere); *v_now = the full v.
-__device__ double bgd_matvec(const BgdArgs &a, const double *theta, int &flip, BgdGrid &grid, double *red, const double **v_now) {
+// vs = Sigma * theta (in shared memory, the same bits in every CTA), returns theta^T vs.  A CTA owns rows_per_cta
+// consecutive rows -- the same ones every time, so a band that fits L1 is served from there after the first product
+// -- and puts warps_per_row warps on each (fixed split, fixed order of the partial sums: the result does not depend
+// on timing).  With more than one CTA the bands are exchanged through global memory and one grid barrier.
+__device__ double bgd_matvec(const BgdArgs &a, const double *theta, double *vs, int &flip, BgdGrid &grid, double *red) {
   double *v = a.v[flip];
   flip ^= 1;
-  const int p = a.p, lane = threadIdx.x & 31;
-  const int warps = kBgdThreads / 32;
-  for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < p; row += gridDim.x * warps) {
-    const double *s = a.sigma + (long long)row * p;
+  const bool alone = gridDim.x == 1;
+  const int p = a.p, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = a.warps_per_row, part = warp % W, rows_at_once = (kBgdThreads / 32) / W;
+  const int row0 = blockIdx.x * a.rows_per_cta;
+  for (int r = warp / W; r - warp / W < a.rows_per_cta; r += rows_at_once) {  // uniform trip count: barriers inside
+    const int row = row0 + r;
+    const bool live = r < a.rows_per_cta && row < p;
     double acc = 0.0;
-    for (int j = lane; j < p; j += 32) acc = fma(s[j], theta[j], acc);
+    if (live) {
+      const double *s = a.sigma + (long long)row * p;
+#pragma unroll 8
+      for (int j = part * 32 + lane; j < p; j += 32 * W) acc = fma(s[j], theta[j], acc);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) v[row] = acc;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (W > 1) {
+      __syncthreads();
+      if (lane == 0) red[warp] = acc;
+      __syncthreads();
+      if (live && part == 0 && lane == 0) {
+        acc = 0.0;
+        for (int w = 0; w < W; w++) acc += red[warp + w];
+      }
+    }
+    if (live && part == 0 && lane == 0) {
+      if (alone) vs[row] = acc;
+      else v[row] = acc;
+    }
   }
   grid.sync();
-  double part = 0.0;
-  for (int i = threadIdx.x; i < p; i += kBgdThreads) part = fma(theta[i], ld_cg_f64(v + i), part);
-  *v_now = v;
-  return bgd_block_sum(part, red);
+  if (!alone) {
+    for (int i = threadIdx.x; i < p; i += kBgdThreads) vs[i] = ld_cg_f64(v + i);
+    __syncthreads();
+  }
+  double part_sum = 0.0;
+  for (int i = threadIdx.x; i < p; i += kBgdThreads) part_sum = fma(theta[i], vs[i], part_sum);
+  return bgd_block_sum(part_sum, red);
 }
 
-// Dynamic shared memory: 5 * p doubles (theta, prev_theta, grad, prev_grad, update) + 32 doubles.
+// Dynamic shared memory: 6 * p doubles (theta, prev_theta, grad, prev_grad, update, Sigma * theta) + 96 doubles.
 __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
   extern __shared__ double bgd_smem[];
   const int p = a.p, label = a.label, tid = threadIdx.x;
   double *theta = bgd_smem, *prev_theta = theta + p, *grad = prev_theta + p, *prev_grad = grad + p, *update = prev_grad + p;
-  double *red = update + p;
+  double *vs = update + p, *red = vs + p;
   BgdGrid grid{a.barrier, 0u};
   int flip = 0;
   const double count = a.sigma[0];
@@ -253,77 +295,75 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
     grad[i] = prev_grad[i] = update[i] = 0.0;
   }
   __syncthreads();
-  const double *v;
-  double quad_form = bgd_matvec(a, theta, flip, grid, red, &v);
+  double quad_form = bgd_matvec(a, theta, vs, flip, grid, red);
   // compute_gradient (regression.cpp:30-46)
   if (count != 0.0)
-    for (int i = tid; i < p; i += kBgdThreads) grad[i] = i == label ? 0.0 : ld_cg_f64(v + i) / count;
+    for (int i = tid; i < p; i += kBgdThreads) grad[i] = i == label ? 0.0 : vs[i] / count;
   __syncthreads();
-  double part = 0.0;
+  // compute_error (:48-77) from theta^T Sigma theta and SUM_{i >= 1} theta_i^2
+  auto error_of = [&](double qf, double sq_norm) { return count == 0.0 ? 0.0 : (qf / count + lambda * (sq_norm - 1.0)) / 2; };
+  double two[2] = {0.0, 0.0};
   for (int i = tid; i < p; i += kBgdThreads) {
     const double upd = i == 0 ? grad[0] : grad[i] + lambda * theta[i];
-    part += upd * upd;
+    two[0] += upd * upd;
+    if (i >= 1) two[1] += theta[i] * theta[i];
   }
-  double gradient_norm = bgd_block_sum(part, red) - (double)lambda * lambda;  // label correction (:180)
+  bgd_block_sums<2>(two, red);
+  double gradient_norm = two[0] - (double)lambda * lambda;  // label correction (:180)
   const double first_gradient_norm = sqrt(gradient_norm);
-  // compute_error (:48-77)
-  auto error_of = [&](double qf) {
-    if (count == 0.0) return 0.0;
-    double pn = 0.0;
-    for (int i = 1 + tid; i < p; i += kBgdThreads) pn += theta[i] * theta[i];
-    const double param_norm = bgd_block_sum(pn, red) - 1.0;
-    return (qf / count + lambda * param_norm) / 2;
-  };
-  double prev_error = error_of(quad_form);
+  double prev_error = error_of(quad_form, two[1]);
   double error = prev_error;
   int iterations = 1, backtracks = 0;
   do {
-    part = 0.0;
+    two[0] = two[1] = 0.0;
     for (int i = tid; i < p; i += kBgdThreads) {
       const double upd = i == 0 ? grad[0] : grad[i] + lambda * theta[i];
       update[i] = upd;
-      part += upd * upd;
+      two[0] += upd * upd;
       prev_theta[i] = theta[i];
       prev_grad[i] = grad[i];
-      theta[i] = i == label ? -1.0 : theta[i] - step * upd;
+      const double t = i == label ? -1.0 : theta[i] - step * upd;
+      theta[i] = t;
+      if (i >= 1) two[1] += t * t;
     }
-    const double sq = bgd_block_sum(part, red);
-    gradient_norm = sq - (double)lambda * lambda;
-    double dparam_norm = step * sqrt(sq);
-    quad_form = bgd_matvec(a, theta, flip, grid, red, &v);
-    error = error_of(quad_form);
+    bgd_block_sums<2>(two, red);
+    gradient_norm = two[0] - (double)lambda * lambda;
+    double dparam_norm = step * sqrt(two[0]);
+    quad_form = bgd_matvec(a, theta, vs, flip, grid, red);
+    error = error_of(quad_form, two[1]);
     int bt = 0;
     while (error > prev_error - (step / 2) * gradient_norm && bt < 500) {
       step /= 2;
-      part = 0.0;
+      two[0] = two[1] = 0.0;
       for (int i = tid; i < p; i += kBgdThreads) {
         const double newp = prev_theta[i] - step * update[i];
         const double dp = theta[i] - newp;
-        part += dp * dp;
-        theta[i] = i == label ? -1.0 : newp;
+        two[0] += dp * dp;
+        const double t = i == label ? -1.0 : newp;
+        theta[i] = t;
+        if (i >= 1) two[1] += t * t;
       }
-      dparam_norm = sqrt(bgd_block_sum(part, red));
-      quad_form = bgd_matvec(a, theta, flip, grid, red, &v);
-      error = error_of(quad_form);
+      bgd_block_sums<2>(two, red);
+      dparam_norm = sqrt(two[0]);
+      quad_form = bgd_matvec(a, theta, vs, flip, grid, red);
+      error = error_of(quad_form, two[1]);
       bt++;
     }
     backtracks += bt;
     gradient_norm = sqrt(gradient_norm);
     if (dparam_norm < 1e-20 || gradient_norm / (first_gradient_norm + 0.001) < 1e-8) break;
-    if (count != 0.0)
-      for (int i = tid; i < p; i += kBgdThreads) grad[i] = i == label ? 0.0 : ld_cg_f64(v + i) / count;
-    __syncthreads();
-    // compute_step_size (:79-107)
-    double dss = 0.0, gss = 0.0, dgs = 0.0;
+    // compute_gradient of the accepted theta (its Sigma * theta is still in vs), compute_step_size (:79-107)
+    double three[3] = {0.0, 0.0, 0.0};
     for (int i = tid; i < p; i += kBgdThreads) {
-      const double pd = theta[i] - prev_theta[i], gd = grad[i] - prev_grad[i];
-      dss += pd * pd;
-      gss += gd * gd;
-      dgs += pd * gd;
+      const double g = count != 0.0 ? (i == label ? 0.0 : vs[i] / count) : grad[i];
+      grad[i] = g;
+      const double pd = theta[i] - prev_theta[i], gd = g - prev_grad[i];
+      three[0] += pd * pd;
+      three[1] += gd * gd;
+      three[2] += pd * gd;
     }
-    dss = bgd_block_sum(dss, red);
-    gss = bgd_block_sum(gss, red);
-    dgs = bgd_block_sum(dgs, red);
+    bgd_block_sums<3>(three, red);
+    const double dss = three[0], gss = three[1], dgs = three[2];
     if (dgs != 0.0 && gss != 0.0) {
       const double ts = dss / dgs, tm = dgs / gss;
       if (!(tm < 0.0 || ts < 0.0)) step = (float)((tm / ts > 0.5) ? tm : ts - 0.5 * tm);
@@ -337,7 +377,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
       a.scalars_out[0] = (double)iterations;
       a.scalars_out[1] = error;
       a.scalars_out[2] = count != 0.0 ? quad_form / count : 0.0;  // the variance of :245-256 (theta[label] = -1)
-      a.scalars_out[3] = (double)backtracks;
+      a.scalars_out[3] = (double)(1 + iterations + backtracks);
     }
   }
 }

@@ -78,7 +78,7 @@ int sigma_alloc(cfb_sigma *s) {
   const int label_keys = s->label_cat >= 0 ? s->cat_idxs[s->label_cat + 1] - s->cat_idxs[s->label_cat] : 0;
   s->p = 1 + s->n + s->cat_idxs[s->m] - label_keys;
   s->n_classes = label_keys;
-  if (s->p > 5000) return fail(CFB_ERR_DOMAIN, "one-hot expansion of %d columns: more than 5000", s->p);
+  if (s->p > 4600) return fail(CFB_ERR_DOMAIN, "one-hot expansion of %d columns: more than 4600", s->p);
   CU(cudaMalloc(&s->d_sigma, (size_t)s->p * s->p * sizeof(double)));
   CU(cudaMemsetAsync(s->d_sigma, 0, (size_t)s->p * s->p * sizeof(double), s->stream));
   if (s->n_classes) {
@@ -343,7 +343,7 @@ int sigma_standardized_copy(const cfb_sigma *s, SigmaScratch &tmp, double **work
 }  // namespace
 
 extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, float lambda, int max_iterations, int normalize,
-                                      double *coeff, double *means, double *variance, int32_t *iterations) {
+                                      double *coeff, double *means, double *variance, int32_t *iterations, int32_t *products) {
   if (!s || !coeff) return fail(CFB_ERR_INVALID, "NULL argument");
   if (s->label_cat >= 0) return fail(CFB_ERR_STATE, "this sigma matrix leaves a categorical label out (LDA): build one with label_cat = -1");
   if (label < 0 || label >= s->n) return fail(CFB_ERR_INVALID, "label %d is not a numeric column (0..%d)", label, s->n - 1);
@@ -374,12 +374,17 @@ extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, 
   a.barrier = d_barrier;
   a.theta_out = d_theta;
   a.scalars_out = d_scalars;
-  const size_t smem = ((size_t)5 * p + 32) * sizeof(double);
+  const size_t smem = ((size_t)6 * p + 96) * sizeof(double);
   CU(cudaFuncSetAttribute(cfb::ridge_bgd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, s->device));
-  // one warp per row and sweep: more CTAs than rows / 32 would only wait at the barrier
-  const int grid = std::max(1, std::min(prop.multiProcessorCount, (p + 31) / 32));
+  int sms = 1;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  // bands of >= 8 rows (a band that fits L1 stays there between products), several warps on a row when the band is
+  // shorter than the CTA's 32 warps; a matrix of a few hundred KB is cheaper on ONE CTA than a grid barrier per product
+  static const int single_cta_max_p = getenv("CFB_BGD_SINGLE_CTA_MAX_P") ? atoi(getenv("CFB_BGD_SINGLE_CTA_MAX_P")) : 160;
+  const int grid = p <= single_cta_max_p ? 1 : std::max(1, std::min(sms, (p + 7) / 8));
+  a.rows_per_cta = (p + grid - 1) / grid;
+  a.warps_per_row = 1;
+  while (a.warps_per_row < 32 && a.rows_per_cta * a.warps_per_row * 2 <= 32) a.warps_per_row *= 2;
   void *params[] = {&a};
   CU(cudaLaunchCooperativeKernel((const void *)cfb::ridge_bgd_kernel, dim3(grid), dim3(cfb::kBgdThreads), params, smem, s->stream));
   g_launches++;
@@ -403,6 +408,7 @@ extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, 
   std::copy(theta.begin(), theta.end(), coeff);
   if (variance) *variance = scalars[2];
   if (iterations) *iterations = (int32_t)scalars[0];
+  if (products) *products = (int32_t)scalars[3];
   return CFB_OK;
 }
 

@@ -49,11 +49,11 @@ class Sigma:
 
     def linreg_train(self, label: int, step_size: float, lam: float, max_iterations: int, normalize: bool = False) -> dict:
         coeff, means = np.zeros(self.p), np.zeros(self.p)
-        var, it = C.c_double(), C.c_int32()
+        var, it, prod = C.c_double(), C.c_int32(), C.c_int32()
         nat.check(nat.lib().cfb_sigma_linreg_train(self.h, label, step_size, lam, max_iterations, int(normalize),
-                                                   coeff.ctypes.data, means.ctypes.data, C.byref(var), C.byref(it)))
+                                                   coeff.ctypes.data, means.ctypes.data, C.byref(var), C.byref(it), C.byref(prod)))
         return {"label": label, "coeff": coeff, "means": means if normalize else None, "variance": var.value,
-                "iterations": it.value}
+                "iterations": it.value, "products": prod.value}
 
     def lda_train(self, shrinkage: float, normalize: bool = False) -> dict:
         q = self.p - 1

@@ -362,9 +362,10 @@ int cfb_sigma_download(const cfb_sigma *sigma, double *sigma_out, double *class_
  * in L1 / L2; one grid barrier per matrix-vector product).  `label` is the numeric column to predict (0-based);
  * step_size and lambda are FLOAT as in the reference.  coeff [p]: intercept, then one coefficient per matrix column
  * (coeff[label + 1] = -1), already rescaled when normalize != 0; means [p] (normalize only); *variance =
- * theta^T Sigma theta / N of the final parameters (the reference emits its square root).                          */
+ * theta^T Sigma theta / N of the final parameters (the reference emits its square root); *iterations = gradient steps
+ * taken, *products = matrix-vector products spent (steps + backtracking trials + 1).  The last four may be NULL.   */
 int cfb_sigma_linreg_train(cfb_sigma *sigma, int label, float step_size, float lambda, int max_iterations, int normalize,
-                           double *coeff, double *means, double *variance, int32_t *iterations);
+                           double *coeff, double *means, double *variance, int32_t *iterations, int32_t *products);
 /* lda_train (ML/lda.cpp:154-330) on the device: within-class covariance with shrinkage, divided by N, solved against
  * the class means by a blocked Cholesky factorisation (the reference calls dgelsd; for the positive definite matrix
  * shrinkage > 0 produces the two agree; a matrix that is not positive definite is CFB_ERR_STATE here).

@@ -506,6 +506,7 @@ def linreg_train(s: dict, label, step_size, lam, max_iterations, compute_varianc
             return 0.0
         return (th @ (sig @ th) / N + float(lam) * (np.sum(th[1:] ** 2) - 1)) / 2
 
+    products = 1                                                 # Sigma * theta products spent (bench bookkeeping)
     grad = gradient(theta)
     upd = grad + float(lam) * theta
     upd[0] = grad[0]
@@ -522,6 +523,7 @@ def linreg_train(s: dict, label, step_size, lam, max_iterations, compute_varianc
         gnorm = sq - float(lam) * float(lam)
         dparam = float(step) * np.sqrt(sq)
         err = error(theta)
+        products += 1
         bt = 0
         while err > prev_error - float(step / f32(2)) * gnorm and bt < 500:
             step = step / f32(2)
@@ -530,6 +532,7 @@ def linreg_train(s: dict, label, step_size, lam, max_iterations, compute_varianc
             theta = newp
             theta[lab] = -1
             err = error(theta)
+            products += 1
             bt += 1
         if dparam < 1e-20 or np.sqrt(gnorm) / (first_norm + 0.001) < 1e-8:
             break
@@ -556,6 +559,7 @@ def linreg_train(s: dict, label, step_size, lam, max_iterations, compute_varianc
         out += [means[i] for i in range(1, p) if i != lab]
     if compute_variance:
         out.append(np.sqrt(variance))
+    linreg_train.last_products = products
     return np.asarray(out, np.float32), it
 
 
