@@ -59,6 +59,7 @@ SIGNATURES = {
     "cfb_ctx_finalize": (C.c_int, [_P, C.c_int, C.POINTER(Result)]),
     "cfb_result_free": (None, [C.POINTER(Result)]),
     "cfb_result_combine": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.c_int, C.c_int, C.POINTER(Result)]),
+    "cfb_result_impute_linear": (C.c_int, [C.POINTER(Result), _P, C.c_int, C.POINTER(Result)]),
     "cfb_result_multiply": (C.c_int, [C.POINTER(Result), C.POINTER(Result), C.POINTER(Result)]),
     "cfb_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "cfb_model_destroy": (None, [_P]),

@@ -153,6 +153,13 @@ class ResultHandle:
         nat.check(nat.lib().cfb_result_combine(C.byref(self.res), C.byref(other.res), sign, 1 if keep_zero_keys else 0, C.byref(out.res)))
         return out
 
+    def impute_linear(self, model, target: int) -> "ResultHandle":
+        """The cofactor of the same rows after numeric column `target` is overwritten by the linear model's
+        predictions (predict.LinearModel, n_out = 1) -- closed form, no scan (cfb_result_impute_linear)."""
+        out = ResultHandle()
+        nat.check(nat.lib().cfb_result_impute_linear(C.byref(self.res), C.byref(model.c), target, C.byref(out.res)))
+        return out
+
     def arrays(self) -> dict:
         return result_arrays(self.res)
 

@@ -2849,6 +2849,102 @@ int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int f
   return CFB_OK;
 }
 
+int cfb_result_impute_linear(const cfb_result *a, const cfb_linear_model *M, int target, cfb_result *out) {
+  if (!a || !M || !out) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (a->kind != CFB_TRIPLE) return fail(CFB_ERR_INVALID, "impute_linear needs the full ring (CFB_TRIPLE)");
+  const int n = a->n_num, m = a->n_cat;
+  if (target < 0 || target >= n) return fail(CFB_ERR_INVALID, "target %d is not a numeric column", target);
+  if (M->n_out != 1 || M->n_num != n - 1 || M->n_cat != m)
+    return fail(CFB_ERR_INVALID, "model shape (%d numeric, %d categorical, %d outputs) does not fit the cofactor without its target",
+                M->n_num, M->n_cat, M->n_out);
+  const int64_t tk = a->total_keys;
+  // theta over [1 | numeric (0 for the target) | result keys]: a key the model does not hold weighs 0 (as in predict)
+  const double b = M->bias[0];
+  std::vector<double> wn(n, 0.0), wk((size_t)tk, 0.0);
+  for (int i = 0, f = 0; i < n; i++)
+    if (i != target) wn[i] = M->w_num[f++];
+  for (int c = 0; c < m; c++) {
+    const int32_t *mk = M->cat_keys + M->cat_offsets[c], *me = M->cat_keys + M->cat_offsets[c + 1];
+    for (int64_t t = a->cat_offsets[c]; t < a->cat_offsets[c + 1]; t++) {
+      const int32_t *hit = std::lower_bound(mk, me, a->cat_keys[t]);
+      if (hit != me && *hit == a->cat_keys[t]) wk[(size_t)t] = M->w_cat[M->cat_offsets[c] + (hit - mk)];
+    }
+  }
+  auto quad_at = [&](int i, int j) -> double & {
+    if (i > j) std::swap(i, j);
+    return a->quad[(int64_t)i * n - (int64_t)i * (i + 1) / 2 + j];
+  };
+  // copy, then rewrite what involves the target
+  {  // a + 0 with the keys kept: a deep copy through the combine path
+    cfb_result z = *a;
+    std::vector<double> zl(n, 0.0), zq((size_t)a->n_quad, 0.0), zn((size_t)n * tk, 0.0);
+    std::vector<int64_t> zc((size_t)tk, 0), zp((size_t)(a->n_pair_lists ? a->pair_offsets[a->n_pair_lists] : 0), 0);
+    z.N = 0;
+    z.lin = zl.data();
+    z.quad = zq.data();
+    z.numcat_sums = zn.data();
+    z.cat_counts = zc.data();
+    z.pair_counts = zp.data();
+    int rc = cfb_result_combine(a, &z, +1, CFB_COMBINE_KEEP_ZERO_KEYS, out);
+    if (rc) return rc;
+  }
+  // SUM y
+  double sy = b * (double)a->N;
+  for (int k = 0; k < n; k++) sy += wn[k] * a->lin[k];
+  for (int64_t t = 0; t < tk; t++) sy += wk[(size_t)t] * (double)a->cat_counts[t];
+  // SUM y x_i
+  std::vector<double> syx(n, 0.0);
+  for (int i = 0; i < n; i++) {
+    if (i == target) continue;
+    double v = b * a->lin[i];
+    for (int k = 0; k < n; k++)
+      if (k != target) v += wn[k] * quad_at(k, i);
+    for (int64_t t = 0; t < tk; t++) v += wk[(size_t)t] * a->numcat_sums[(size_t)i * tk + t];
+    syx[i] = v;
+  }
+  // SUM y [key_d = kappa]
+  std::vector<double> syk((size_t)tk, 0.0);
+  for (int64_t t = 0; t < tk; t++) {
+    double v = b * (double)a->cat_counts[t];
+    for (int k = 0; k < n; k++)
+      if (k != target) v += wn[k] * a->numcat_sums[(size_t)k * tk + t];
+    v += wk[(size_t)t] * (double)a->cat_counts[t];  // the same column: the key meets only itself
+    syk[(size_t)t] = v;
+  }
+  auto entry_of = [&](int c, int32_t key) -> int64_t {
+    const int32_t *lo = a->cat_keys + a->cat_offsets[c], *hi = a->cat_keys + a->cat_offsets[c + 1];
+    const int32_t *hit = std::lower_bound(lo, hi, key);
+    return hit != hi && *hit == key ? a->cat_offsets[c] + (hit - lo) : -1;
+  };
+  int64_t list = 0;
+  for (int k = 0; k < m; k++)
+    for (int l = k; l < m; l++, list++) {
+      if (k == l) continue;
+      for (int64_t t = a->pair_offsets[list]; t < a->pair_offsets[list + 1]; t++) {
+        const int64_t ek = entry_of(k, a->pair_key1[t]), el = entry_of(l, a->pair_key2[t]);
+        if (ek < 0 || el < 0) {
+          cfb_result_free(out);
+          return fail(CFB_ERR_INVALID, "impute_linear: a key pair names a key its column's list does not hold");
+        }
+        const double cnt = (double)a->pair_counts[t];
+        syk[(size_t)el] += wk[(size_t)ek] * cnt;
+        syk[(size_t)ek] += wk[(size_t)el] * cnt;
+      }
+    }
+  // SUM y^2 = theta . (the new cross terms)
+  double syy = b * sy;
+  for (int k = 0; k < n; k++)
+    if (k != target) syy += wn[k] * syx[k];
+  for (int64_t t = 0; t < tk; t++) syy += wk[(size_t)t] * syk[(size_t)t];
+  out->lin[target] = sy;
+  for (int i = 0; i < n; i++) {
+    const int lo = std::min(i, target), hi = std::max(i, target);
+    out->quad[(int64_t)lo * n - (int64_t)lo * (lo + 1) / 2 + hi] = i == target ? syy : syx[i];
+  }
+  for (int64_t t = 0; t < tk; t++) out->numcat_sums[(size_t)target * tk + t] = syk[(size_t)t];
+  return CFB_OK;
+}
+
 void cfb_result_free(cfb_result *r) {
   if (!r) return;
   free(r->lin);

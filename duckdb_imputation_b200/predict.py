@@ -19,7 +19,7 @@ class _Model(C.Structure):
 class LinearModel:
     """score_o = bias[o] + w_num[o] . x + sum_c w_cat[o][position of key_c]  (include/cofactor_b200.h: cfb_linear_model)."""
 
-    def __init__(self, bias, w_num, cat_keys=(), w_cat=None, device: int = 0):
+    def __init__(self, bias, w_num, cat_keys=(), w_cat=None, device: int = 0, upload: bool = True):
         self.bias = np.ascontiguousarray(np.atleast_1d(bias), np.float64)
         K = len(self.bias)
         self.w_num = np.ascontiguousarray(np.asarray(w_num, np.float64).reshape(K, -1))
@@ -33,7 +33,8 @@ class LinearModel:
                         self.flat_keys.ctypes.data, self.w_cat.ctypes.data)
         self.device = device
         self._h = C.c_void_p()
-        nat.check(nat.lib().cfb_model_create(device, C.byref(self.c), C.byref(self._h)))  # upload once
+        if upload:  # (upload=False: only the host description, e.g. for cfb_result_impute_linear)
+            nat.check(nat.lib().cfb_model_create(device, C.byref(self.c), C.byref(self._h)))  # upload once
 
     def close(self):
         if self._h:

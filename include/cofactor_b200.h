@@ -219,6 +219,21 @@ int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *ou
 #define CFB_COMBINE_KEEP_ZERO_KEYS 1
 int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int flags, cfb_result *out);
 
+/* The write-back step as ring arithmetic ("predict -> delta-triple"): `rows` is the cofactor of some rows
+ * R; numeric column `target` of those rows is about to be overwritten by the linear model's prediction
+ *     y = bias + SUM_i w_num[i] * x_i + SUM_c w_cat[position of key_c]      (n_out = 1; the features are the other
+ * numeric columns in order -- model->n_num == n_num - 1 -- and every categorical column).  Every entry of the NEW
+ * cofactor that involves the target is a linear or quadratic function of entries that do not change:
+ *     SUM y          = theta . (first row of the sigma matrix of R)
+ *     SUM y x_i      = theta . (row i), SUM y [key_d = k] = theta . (row of that one-hot column)
+ *     SUM y^2        = theta . (the new cross terms)
+ * so `out` = the cofactor of R after the write-back, WITHOUT scanning the rows again (the reference recomputes the
+ * delta with a second scan, imputation_low.cpp:85-110).  Exact up to the FLOAT rounding of the stored predictions;
+ * not applicable to stochastic regression (noise = true) or to classifiers.  A host-side function on a small
+ * result; `out` is owned by the caller afterwards (cfb_result_free).                                           */
+struct cfb_linear_model;
+int cfb_result_impute_linear(const cfb_result *rows, const struct cfb_linear_model *model, int target, cfb_result *out);
+
 /* ------------------------------------------------- multi-GPU partial exchange */
 
 /* Dense partial layout for the NCCL reduce of SURVEY 8(e): the caller

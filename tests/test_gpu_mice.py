@@ -35,12 +35,13 @@ def test_device_loop_matches_host_loop():
     assert np.abs(d_num[0].cpu().numpy()[mn[0]] - truth[("n", 0)][mn[0]]).mean() < 0.6 * np.abs(num[0][mn[0]] - truth[("n", 0)][mn[0]]).mean()
 
 
-@pytest.mark.parametrize("per_pattern", [False, True])
-def test_delta_cofactor_loop_matches_the_filtered_scan_loop(per_pattern):
+@pytest.mark.parametrize("per_pattern,closed_form", [(False, False), (True, False), (True, True)])
+def test_delta_cofactor_loop_matches_the_filtered_scan_loop(per_pattern, closed_form):
     """with the table partitioned by NULL pattern, the cofactor over the rows where a column is
     observed is total - nulls (cfb_result_combine, the arithmetic of subtract_triple, imputation/triple/sub.cpp:71-219)
     and only the NULL rows (20 %) are scanned per step.  Same models, same imputations as the loop that rescans the
-    whole table behind a row filter.  per_pattern: one kept cofactor per NULL pattern, one scan per column."""
+    whole table behind a row filter.  per_pattern: one kept cofactor per NULL pattern, one scan per column; closed_form: the cofactor after a linear-regression
+    write-back from cfb_result_impute_linear, no scan."""
     rows = 60_001
     num, cat, mn, mc, _ = mice_loop.synthetic_table(rows, n=5, m=3, dom=5, null_num=(0, 3), null_cat=(2,), seed=21)
 
@@ -52,7 +53,7 @@ def test_delta_cofactor_loop_matches_the_filtered_scan_loop(per_pattern):
     a_num, a_cat, a_nn, a_nc = dev()
     mice_loop.mice_gpu(a_num, a_cat, a_nn, a_nc, 2, rows)
     b_num, b_cat, b_nn, b_nc = dev()
-    _, order, _ = mice_loop.mice_gpu_delta(b_num, b_cat, b_nn, b_nc, 2, rows, per_pattern=per_pattern)
+    _, order, _ = mice_loop.mice_gpu_delta(b_num, b_cat, b_nn, b_nc, 2, rows, per_pattern=per_pattern, closed_form=closed_form)
     order = order.cpu().numpy()
     for c in mn:
         want, got = a_num[c].cpu().numpy()[order], b_num[c].cpu().numpy()

@@ -64,3 +64,64 @@ def test_keep_zero_keys_leaves_the_emptied_keys_in_place():
     zero = [i for i, k in enumerate(kept["cat_keys"]) if k >= 4]
     assert zero and all(kept["cat_counts"][i] == 0 for i in zero)
     assert len(kept["pair_counts"]) == len(W["pair_counts"])
+
+
+# ------------------------------------------------------------ the write-back as ring arithmetic (no second scan)
+def _impute(a, model, target):
+    from duckdb_imputation_b200.predict import LinearModel
+    ra, ka = to_result(a)
+    lm = LinearModel(model["bias"], model["w_num"], model["keys"], model["w_cat"], upload=False)
+    out = nat.Result()
+    nat.check(nat.lib().cfb_result_impute_linear(C.byref(ra), C.byref(lm.c), target, C.byref(out)))
+    try:
+        return result_arrays(out)
+    finally:
+        nat.lib().cfb_result_free(C.byref(out))
+
+
+@pytest.mark.parametrize("n,m,target", [(4, 2, 1), (3, 0, 0), (2, 3, 1), (5, 1, 4)])
+def test_impute_linear_equals_the_cofactor_of_the_overwritten_rows(n, m, target):
+    """cfb_result_impute_linear(cofactor(R), model, j) == cofactor(R with x_j := model(R)): the delta triple of a
+    linear-regression write-back in closed form (the reference rescans, imputation_low.cpp:85-110)."""
+    rng = np.random.default_rng(100 * n + 10 * m + target)
+    rows = 3000
+    num = [rng.standard_normal(rows).astype(np.float32) for _ in range(n)]
+    cat = [rng.integers(-1, 4, rows).astype(np.int32) for _ in range(m)]
+    keys = [np.array([-1, 0, 1, 2, 3], np.int32) for _ in range(m)]
+    model = {"bias": np.array([0.3]), "w_num": rng.standard_normal((1, n - 1)), "keys": keys,
+             "w_cat": rng.standard_normal((1, 5 * m))}
+    before = oracle.aggregate_arrays(oracle.TRIPLE, num, cat)[0]
+    y = np.full(rows, 0.3)
+    for f, i in enumerate(i for i in range(n) if i != target):
+        y += model["w_num"][0, f] * num[i].astype(np.float64)
+    for c in range(m):
+        y += model["w_cat"][0, 5 * c + (cat[c] + 1)]
+    after_cols = list(num)
+    after_cols[target] = y.astype(np.float32)  # what the predict kernel stores
+    want = oracle.aggregate_arrays(oracle.TRIPLE, after_cols, cat)[0]
+    got = _impute(before, model, target)
+    assert got["N"] == want["N"] and np.array_equal(got["cat_counts"], want["cat_counts"])
+    assert np.array_equal(got["pair_counts"], want["pair_counts"])
+    scale = max(1.0, float(np.abs(want["quad"]).max()))
+    np.testing.assert_allclose(got["lin"], want["lin"], rtol=1e-6, atol=1e-6 * scale)
+    np.testing.assert_allclose(got["quad"], want["quad"], rtol=1e-6, atol=1e-6 * scale)
+    np.testing.assert_allclose(got["numcat"], want["numcat"], rtol=1e-6, atol=1e-6 * scale)
+    # and the entries that do not involve the target are untouched bit for bit
+    keep = [i for i in range(n) if i != target]
+    assert np.array_equal(got["lin"][keep], before["lin"][keep])
+    assert np.array_equal(got["numcat"][keep], before["numcat"][keep])
+
+
+def test_impute_linear_checks_the_model_shape():
+    rng = np.random.default_rng(2)
+    A = oracle.aggregate_arrays(oracle.TRIPLE, [rng.random(20).astype(np.float32)] * 3, [rng.integers(0, 3, 20).astype(np.int32)])[0]
+    bad = {"bias": np.array([0.0]), "w_num": np.zeros((1, 3)), "keys": [np.arange(3, dtype=np.int32)], "w_cat": np.zeros((1, 3))}
+    with pytest.raises(nat.CofactorError, match="does not fit"):
+        _impute(A, bad, 0)
+    ok = dict(bad, w_num=np.zeros((1, 2)))
+    with pytest.raises(nat.CofactorError, match="not a numeric column"):
+        _impute(A, ok, 3)
+    # an unknown key weighs 0, as in the predict kernels
+    short = dict(ok, keys=[np.array([0, 1], np.int32)], w_cat=np.ones((1, 2)))
+    got = _impute(A, short, 0)
+    assert got["lin"][0] == pytest.approx(float(A["cat_counts"][:2].sum()))

@@ -197,7 +197,7 @@ def _scan_ranges(ctx, d_num, d_cat, ranges):
             ctx.scan_device([t[w:a_lo] for t in d_num], [t[w:a_lo] for t in d_cat], 4, d_group=slot)
 
 
-def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None, per_pattern=True):
+def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=None, log=None, per_pattern=True, closed_form=False):
     """The loop with DELTA COFACTORS (the idea of imputation_low.cpp:85-110 and the Value-level subtract_triple /
     sum_triple helpers, imputation/triple/sub.cpp:71-219): the table is partitioned by NULL pattern once; the cofactor
     of the whole table is computed once and then maintained; per imputed column only its NULL rows (20 %) are scanned.
@@ -212,6 +212,11 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
     the two scans disappears because nulls = sum of the kept cofactors of the patterns that contain c; after the
     write-back each of those partitions is rescanned once and its cofactor replaced (ONE scan of the NULL rows per
     column, the rest is ring arithmetic on small results).
+
+    closed_form=True (with per_pattern): after a LINEAR-REGRESSION write-back not even that scan is needed -- every entry
+    of a partition's new cofactor that involves the imputed column is theta . (a row of the partition's old sigma
+    matrix), cfb_result_impute_linear; only classifier write-backs (LDA: the new keys are not linear in anything)
+    rescan their NULL rows.
 
     Returns (per-iteration timings, the permutation applied to the rows, setup ms)."""
     import torch
@@ -278,8 +283,9 @@ def mice_gpu_delta(d_num, d_cat, d_null_num, d_null_cat, iters, rows, domains=No
                 t3 = time.perf_counter()
                 if per_pattern:
                     for p in pats:
-                        by_pattern[p].close()
-                        by_pattern[p] = cofactor([ranges["patterns"][p]])
+                        old = by_pattern[p]
+                        by_pattern[p] = old.impute_linear(lm, c) if closed_form and kind == "n" else cofactor([ranges["patterns"][p]])
+                        old.close()
                     new_nulls, new_owned = ring_sum([by_pattern[p] for p in pats])
                 else:
                     new_nulls, new_owned = cofactor(rs), True
@@ -360,10 +366,12 @@ def main():
     tot = sum(sum(t.values()) for t in ts)
     scans = iters * (len(null_num) + len(null_cat))
     # the same loop with delta cofactors: one partition + one full scan up front, then only the NULL rows per step
-    for per_pattern in (False, True):
-        td, _, setup_ms = mice_gpu_delta(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m, per_pattern=per_pattern)
+    for per_pattern, closed_form in ((False, False), (True, False), (True, True)):
+        td, _, setup_ms = mice_gpu_delta(d_num, d_cat, d_nn, d_nc, iters, rows, domains=[(0, dom - 1)] * m, per_pattern=per_pattern,
+                                         closed_form=closed_form)
         totd = sum(sum(t.values()) for t in td)
-        what = ("one kept cofactor per NULL pattern, ONE scan of the NULL rows per column" if per_pattern
+        what = ("one kept cofactor per NULL pattern, linear write-backs in closed form: NO scan for the numeric columns" if closed_form
+                else "one kept cofactor per NULL pattern, ONE scan of the NULL rows per column" if per_pattern
                 else "total - nulls, two scans of the NULL rows per column")
         print(json.dumps({"summary": f"MICE loop with delta cofactors ({what})", "rows": rows,
                           "iterations": iters, "ms_per_iteration": round(totd / iters, 2), "setup_full_scan_ms": round(setup_ms, 2),
