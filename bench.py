@@ -192,6 +192,30 @@ CONFIGS = [
 ]
 
 
+def train_leg(ctx, n, m):
+    """linreg_train / lda_train on the device from a scanned context (cfb_sigma_*): wall ms of the second call of each
+    (the first loads the kernels), the gradient descent also per Sigma * theta product."""
+    from duckdb_imputation_b200.train import Sigma
+    out = {}
+    t0 = time.perf_counter()
+    with Sigma.from_context(ctx) as s:
+        out["p"] = s.p
+        out["sigma_from_state_ms"] = (time.perf_counter() - t0) * 1e3
+        s.linreg_train(0, 0.001, 0.01, 2)
+        t0 = time.perf_counter()
+        fit = s.linreg_train(0, 0.001, 0.01, 300)
+        dt = time.perf_counter() - t0
+        out.update({"linreg_train_ms": dt * 1e3, "linreg_iterations": fit["iterations"], "linreg_products": fit["products"],
+                    "linreg_us_per_product": dt * 1e6 / max(1, fit["products"])})
+    with Sigma.from_context(ctx, label_cat=m - 1) as s:
+        s.lda_train(0.01)
+        t0 = time.perf_counter()
+        s.lda_train(0.01)
+        out["lda_train_ms"] = (time.perf_counter() - t0) * 1e3
+        out["lda_classes"] = s.n_classes
+    return out
+
+
 def run_configs(lib, local, stream, peak, scale, e2e_rows):
     """Device-resident rows/s + roofline fraction, full-size integer / fp64 checks against torch (checker only), the
     same aggregate end to end through the DuckDB callbacks from host columns, and the reference's CPU callbacks
@@ -244,9 +268,12 @@ def run_configs(lib, local, stream, peak, scale, e2e_rows):
                     times.append(e0.elapsed_time(e1))
                 if rep == reps - 1:
                     res = [ctx.finalize_arrays(gg) for gg in range(G)]
+                    if tag == "C3":  # SURVEY 8 f4 on the state just scanned: sigma on the device, both trainers
+                        train_rec = train_leg(ctx, n, m)
         ms = sum(times) / len(times)
         bpr = 4 * (n + m + (1 if G > 1 else 0))
         rec = {"config": tag, "workload": name, "rows": rows, "ms_per_scan": ms, "rows_per_s": rows / ms * 1e3,
+               **({"train": train_rec} if tag == "C3" else {}),
                "bytes_per_row": bpr, "roofline": {"bound": "hbm", "achieved": rows * bpr / ms / 1e6, "peak": peak, "unit": "GB/s",
                                                     "frac": rows * bpr / ms / 1e6 / peak}}
         # ---- full-size checks of the scan just timed, against torch reductions (exact integers; fp64 sums)

@@ -1,7 +1,7 @@
 """Time the device trainers on one-hot expansions of growing width, next to the reference's own
 trainers (oracle/_ref, host, one core) on the same triple:
 
-    python tools/train_bench.py [rows] [max_iterations]
+    python tools/train_bench.py [rows] [max_iterations] [shape index]
 
 Per shape: p (sigma is p x p fp64), ms to assemble sigma from the device state, ms and iterations of the ridge
 gradient descent (cfb_sigma_linreg_train, one cooperative kernel), ms of the LDA solve (blocked Cholesky), and the
@@ -26,6 +26,8 @@ def main():
     rows = int(float(sys.argv[1])) if len(sys.argv) > 1 else 4_000_000
     max_it = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
     shapes = [(19, (10,) * 10), (10, (30,) * 10), (10, (100,) * 10), (10, (200,) * 16)]
+    if len(sys.argv) > 3:  # one shape only (profiling)
+        shapes = [shapes[int(sys.argv[3])]]
     from oracle import oracle
     rng = np.random.default_rng(3)
     for n, doms in shapes:
