@@ -44,4 +44,27 @@ lda = predict.LinearModel(rng.standard_normal(3), rng.standard_normal((3, 5)), [
 cls = predict.predict_host(lda, num[:5], cat, predict.ARGMAX)
 torch.cuda.synchronize()
 assert cls.min() >= 0 and cls.max() <= 2
+# trainers: sigma from the state / a result, gradient descent (one CTA and several), Cholesky with panels
+from duckdb_imputation_b200.struct_result import arrays_to_struct
+from duckdb_imputation_b200.train import Sigma
+wide = [rng.integers(0, 70, rows).astype(np.int32) for _ in range(3)]
+with CofactorContext(CFB_TRIPLE, 4, 3) as ctx:
+    ctx.set_cat_domain([0] * 3, [69] * 3)
+    ctx.append(num[:4], wide)
+    t = arrays_to_struct(oracle.aggregate_arrays(CFB_TRIPLE, num[:4], wide)[0], narrow=False)
+    with Sigma.from_context(ctx) as s:                              # p = 215: several CTAs + grid barrier
+        fit = s.linreg_train(1, 0.001, 0.01, 40)
+        np.testing.assert_allclose(s.matrix()[0], oracle.build_sigma(t)[0], rtol=1e-5, atol=1e-3)
+    with Sigma.from_context(ctx, label_cat=2) as s:                 # q = 144: three Cholesky panels
+        got = s.lda_params(s.lda_train(0.05))
+        want = oracle.lda_train(t, 2, 0.05, False)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()))
+    res = ctx.finalize_result()
+    with Sigma.from_result(res, label_cat=-1, drop_first=True) as s:
+        s.linreg_train(0, 0.001, 0.0, 5, normalize=True)
+    res.close()
+with CofactorContext(CFB_TRIPLE, 3, 1) as ctx:                      # p = 15: the single-CTA descent
+    ctx.append(num[:3], cat[:1])
+    with Sigma.from_context(ctx) as s:
+        s.linreg_train(2, 0.001, 0.0, 30)
 print("sanitize smoke ok")
