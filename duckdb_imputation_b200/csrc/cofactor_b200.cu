@@ -213,6 +213,10 @@ struct cfb_ctx {
   int cur = 0;
   bool uses_group = false;
   int st_lo[cfb::kMaxCat], st_hi[cfb::kMaxCat];  // min/max of the keys staged in the open tile
+  // A state without a dense partial (hashed pair counts, key dictionaries, a domain every rank discovered for
+  // itself) is all-reduced as results: per group the global result lives here, finalize hands out copies, and
+  // the context accepts no further input (its device state is still the local one).
+  std::vector<cfb_result> reduced;
 };
 
 namespace {
@@ -246,6 +250,37 @@ struct CtxPool {
   }
 };
 CtxPool g_ctx_pool;
+
+int check_open(const cfb_ctx *c) {
+  if (c && !c->reduced.empty())
+    return fail(CFB_ERR_STATE, "this context holds an all-reduced result (cfb_ctx_allreduce of a sparse state): finalize it, it takes no more input");
+  return CFB_OK;
+}
+// deep copy of a result (every array malloc'd, as cfb_result_free expects)
+int copy_result(const cfb_result *a, cfb_result *out) {
+  *out = *a;
+  auto dup = [](const void *p, size_t bytes) {
+    void *q = malloc(std::max<size_t>(8, bytes));
+    if (q && p && bytes) memcpy(q, p, bytes);
+    return q;
+  };
+  const size_t tk = (size_t)a->total_keys, np = (size_t)(a->n_pair_lists ? a->pair_offsets[a->n_pair_lists] : 0);
+  out->lin = (double *)dup(a->lin, (size_t)a->n_num * 8);
+  out->quad = (double *)dup(a->quad, (size_t)a->n_quad * 8);
+  out->cat_offsets = (int64_t *)dup(a->cat_offsets, ((size_t)a->n_cat + 1) * 8);
+  out->cat_keys = (int32_t *)dup(a->cat_keys, tk * 4);
+  out->cat_counts = (int64_t *)dup(a->cat_counts, tk * 8);
+  out->numcat_sums = a->numcat_sums ? (double *)dup(a->numcat_sums, (size_t)a->n_num * tk * 8) : nullptr;
+  out->pair_offsets = (int64_t *)dup(a->pair_offsets, ((size_t)a->n_pair_lists + 1) * 8);
+  out->pair_key1 = (int32_t *)dup(a->pair_key1, np * 4);
+  out->pair_key2 = (int32_t *)dup(a->pair_key2, np * 4);
+  out->pair_counts = (int64_t *)dup(a->pair_counts, np * 8);
+  return CFB_OK;
+}
+void drop_reduced(cfb_ctx *c) {
+  for (auto &r : c->reduced) cfb_result_free(&r);
+  c->reduced.clear();
+}
 
 // ------------------------------------------------------------------------- layout
 // Dense pair tables are used while they stay below this many bytes (all groups); above it the
@@ -1974,6 +2009,7 @@ int cfb_ctx_create(int device, int kind, int n_num, int n_cat, int n_groups, cfb
 
 int cfb_ctx_destroy(cfb_ctx *c) {
   if (!c) return CFB_OK;
+  drop_reduced(c);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->user_stream) cudaStreamSynchronize(c->user_stream);
@@ -2028,6 +2064,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
 
 int cfb_ctx_set_cat_domain(cfb_ctx *c, const int32_t *lo, const int32_t *hi) {
   if (!c || !lo || !hi) return fail(CFB_ERR_INVALID, "NULL argument");
+  if (int rc = check_open(c)) return rc;
   for (int k = 0; k < c->m; k++)
     if (hi[k] < lo[k]) return fail(CFB_ERR_INVALID, "empty domain for categorical column %d", k);
   CU(cudaSetDevice(c->device));
@@ -2041,6 +2078,7 @@ int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *con
                    const int32_t *const *cat_cols, const uint32_t *const *cat_sel, const uint32_t *group_slot,
                    size_t count) {
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (int rc = check_open(c)) return rc;
   if (count == 0) return CFB_OK;
   if ((c->n && !num_cols) || (c->m && !cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
   CU(cudaSetDevice(c->device));
@@ -2114,6 +2152,7 @@ int cfb_ctx_append_triples_slot(cfb_ctx *c, int slot, size_t count, const int32_
                                 const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
                                 const float *cc_val) {
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (int rc = check_open(c)) return rc;
   if (slot < 0 || slot >= c->G) return fail(CFB_ERR_INVALID, "slot %d out of range", slot);
   if (count == 0) return CFB_OK;
   const int n = c->n, m = c->m;
@@ -2243,6 +2282,7 @@ int cfb_ctx_append_triples_slot(cfb_ctx *c, int slot, size_t count, const int32_
 int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                       const int32_t *d_group_slot, size_t n_rows, void *stream) {
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (int rc = check_open(c)) return rc;
   if ((c->n && !d_num_cols) || (c->m && !d_cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -2342,6 +2382,8 @@ int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src_c, size_t n_pairs, co
                           const int32_t *src_slots) {
   cfb_ctx *src = const_cast<cfb_ctx *>(src_c);
   if (!dst || !src) return fail(CFB_ERR_INVALID, "ctx is NULL");
+  if (int rc = check_open(dst)) return rc;
+  if (int rc = check_open(src)) return rc;
   if (dst == src) return combine_within(dst, n_pairs, dst_slots, src_slots);
   if (dst->kind != src->kind || dst->n != src->n || dst->m != src->m) return fail(CFB_ERR_INVALID, "combine: shapes differ");
   // slot map: dst slot of every src slot (-1 = not combined); identity when no pairs are given
@@ -2493,6 +2535,7 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
   if (!c || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (group < 0 || group >= c->G) return fail(CFB_ERR_INVALID, "group %d out of range", group);
   memset(out, 0, sizeof(*out));
+  if (!c->reduced.empty()) return copy_result(&c->reduced[(size_t)group], out);
   int rc = cfb_ctx_sync(c);
   if (rc) return rc;
   // the aggregate is complete: hand the (drained) staging tiles back; a later append re-acquires them
@@ -3076,6 +3119,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   std::string error;
@@ -3107,6 +3151,7 @@ const NcclApi &nccl_api() {
     a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
     a.CommCount = (decltype(a.CommCount))sym("ncclCommCount");
     a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
     a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
   });
@@ -3191,13 +3236,143 @@ int cfb_nccl_agree_domain(void *comm, int device, int32_t *lo, int32_t *hi, int 
   return CFB_OK;
 }
 
+// A result as one flat byte string (and back): what ranks exchange when the state has no dense partial.
+static void pack_result(const cfb_result &r, std::vector<char> &out) {
+  auto put = [&](const void *p, size_t bytes) {
+    const char *b = (const char *)p;
+    out.insert(out.end(), b, b + bytes);
+  };
+  const int64_t np = r.n_pair_lists ? r.pair_offsets[r.n_pair_lists] : 0;
+  const int64_t head[8] = {r.kind, r.n_num, r.n_cat, r.N, r.n_quad, r.total_keys, r.n_pair_lists, np};
+  put(head, sizeof head);
+  put(r.lin, (size_t)r.n_num * 8);
+  put(r.quad, (size_t)r.n_quad * 8);
+  put(r.cat_offsets, ((size_t)r.n_cat + 1) * 8);
+  put(r.cat_counts, (size_t)r.total_keys * 8);
+  if (r.kind == CFB_TRIPLE) put(r.numcat_sums, (size_t)r.n_num * r.total_keys * 8);
+  put(r.pair_offsets, ((size_t)r.n_pair_lists + 1) * 8);
+  put(r.pair_counts, (size_t)np * 8);
+  put(r.cat_keys, (size_t)r.total_keys * 4);
+  put(r.pair_key1, (size_t)np * 4);
+  put(r.pair_key2, (size_t)np * 4);
+  while (out.size() % 8) out.push_back(0);
+}
+// a VIEW into the byte string (8-byte fields first, so every array is aligned); returns the bytes consumed
+static size_t view_result(const char *p, cfb_result *r) {
+  const char *p0 = p;
+  int64_t head[8];
+  memcpy(head, p, sizeof head);
+  p += sizeof head;
+  memset(r, 0, sizeof *r);
+  r->kind = (int32_t)head[0];
+  r->n_num = (int32_t)head[1];
+  r->n_cat = (int32_t)head[2];
+  r->N = head[3];
+  r->n_quad = head[4];
+  r->total_keys = head[5];
+  r->n_pair_lists = head[6];
+  const int64_t np = head[7];
+  auto take = [&](size_t bytes) {
+    const char *q = p;
+    p += bytes;
+    return (void *)q;
+  };
+  r->lin = (double *)take((size_t)r->n_num * 8);
+  r->quad = (double *)take((size_t)r->n_quad * 8);
+  r->cat_offsets = (int64_t *)take(((size_t)r->n_cat + 1) * 8);
+  r->cat_counts = (int64_t *)take((size_t)r->total_keys * 8);
+  if (r->kind == CFB_TRIPLE) r->numcat_sums = (double *)take((size_t)r->n_num * r->total_keys * 8);
+  r->pair_offsets = (int64_t *)take(((size_t)r->n_pair_lists + 1) * 8);
+  r->pair_counts = (int64_t *)take((size_t)np * 8);
+  r->cat_keys = (int32_t *)take((size_t)r->total_keys * 4);
+  r->pair_key1 = (int32_t *)take((size_t)np * 4);
+  r->pair_key2 = (int32_t *)take((size_t)np * 4);
+  size_t used = (size_t)(p - p0);
+  return (used + 7) & ~(size_t)7;
+}
+
+// The exchange for states without a dense partial ("sparse / large-domain fallback"): every rank finalizes
+// its groups, the canonical results are all-gathered as byte strings (sizes agreed by a MAX all-reduce) and merged by
+// key in rank order on every rank -- the same sums in the same order everywhere.  The merged results are kept in the
+// context; cfb_ctx_finalize hands them out.
+static int allreduce_results(cfb_ctx *c, ncclComm_t comm, cudaStream_t s) {
+  const NcclApi &a = nccl_api();
+  int world = 1;
+  if (a.CommCount(comm, &world) != ncclSuccess) return fail(CFB_ERR_CUDA, "ncclCommCount failed");
+  std::vector<char> mine(8, 0);  // [0..8): the length of this rank's string
+  for (int g = 0; g < c->G; g++) {
+    cfb_result r;
+    int rc = cfb_ctx_finalize(c, g, &r);
+    if (rc) return rc;
+    pack_result(r, mine);
+    cfb_result_free(&r);
+  }
+  const unsigned long long len = mine.size();
+  memcpy(mine.data(), &len, 8);
+  unsigned long long *d_len = nullptr;
+  CU(cudaMalloc(&d_len, 8));
+  CU(cudaMemcpyAsync(d_len, &len, 8, cudaMemcpyHostToDevice, s));
+  ncclResult_t r = a.AllReduce(d_len, d_len, 1, ncclUint64, ncclMax, comm, s);
+  unsigned long long padded = 0;
+  cudaError_t e = cudaMemcpyAsync(&padded, d_len, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_len);
+  if (r != ncclSuccess) return fail(CFB_ERR_CUDA, "NCCL all-reduce of the result sizes failed: %s", a.GetErrorString(r));
+  CU(e);
+  char *d_send = nullptr, *d_recv = nullptr;
+  CU(cudaMalloc(&d_send, padded));
+  e = cudaMalloc(&d_recv, padded * world);
+  if (e != cudaSuccess) {
+    cudaFree(d_send);
+    CU(e);
+  }
+  std::vector<char> all((size_t)padded * world);
+  e = cudaMemcpyAsync(d_send, mine.data(), mine.size(), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) r = a.AllGather(d_send, d_recv, padded, ncclChar, comm, s);
+  if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(all.data(), d_recv, all.size(), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  if (r != ncclSuccess) return fail(CFB_ERR_CUDA, "NCCL all-gather of the results failed: %s", a.GetErrorString(r));
+  CU(e);
+  std::vector<cfb_result> merged((size_t)c->G);
+  for (auto &m : merged) memset(&m, 0, sizeof m);
+  for (int rank = 0; rank < world; rank++) {
+    const char *p = all.data() + (size_t)rank * padded + 8;
+    for (int g = 0; g < c->G; g++) {
+      cfb_result v;
+      p += view_result(p, &v);
+      if (rank == 0) {
+        copy_result(&v, &merged[(size_t)g]);
+        continue;
+      }
+      cfb_result sum;
+      const int rc = cfb_result_combine(&merged[(size_t)g], &v, +1, 0, &sum);
+      if (rc) {
+        for (auto &m : merged) cfb_result_free(&m);
+        return rc;
+      }
+      cfb_result_free(&merged[(size_t)g]);
+      merged[(size_t)g] = sum;
+    }
+  }
+  drop_reduced(c);
+  c->reduced = std::move(merged);
+  return CFB_OK;
+}
+
 int cfb_ctx_allreduce(cfb_ctx *c, void *comm, void *stream) {
   if (!c || !comm) return fail(CFB_ERR_INVALID, "NULL argument");
-  if (c->lay.pairs_hashed || any_dict(c))
-    return fail(CFB_ERR_DOMAIN, "sparse state (hashed pair counts / key dictionaries) has no dense partial: combine with cfb_ctx_combine");
-  if (c->m > 0 && !c->user_domain)
-    return fail(CFB_ERR_STATE, "all-reduce needs the same categorical domain on every rank: agree on it (cfb_nccl_agree_domain) and "
-                               "declare it with cfb_ctx_set_cat_domain before the scan");
+  if (int rc0 = check_open(c)) return rc0;
+  if (c->lay.pairs_hashed || any_dict(c) || (c->m > 0 && !c->user_domain)) {
+    // no dense partial that means the same on every rank (hashed pair counts, key dictionaries, or a domain each
+    // rank discovered for itself): exchange canonical results instead.  Every rank must be in the same case --
+    // declare the domain on all ranks (cfb_nccl_agree_domain + cfb_ctx_set_cat_domain) or on none.
+    int rc = nccl_ready();
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    return allreduce_results(c, (ncclComm_t)comm, stream ? (cudaStream_t)stream : c->stream);
+  }
   int rc = nccl_ready();
   if (rc) return rc;
   CU(cudaSetDevice(c->device));

@@ -257,7 +257,12 @@ int cfb_ctx_import_partial(cfb_ctx *ctx, const void *d_f64, const void *d_u64, v
  * (cudaStream_t; NULL = the context's stream, then the call returns when done).  Every rank must have
  * declared the same categorical domain (cfb_nccl_agree_domain + cfb_ctx_set_cat_domain) and the same
  * n_groups.  NCCL is resolved from libnccl.so.2 at first use (CFB_NCCL_LIB overrides the name); the library
- * itself does not link it.  CFB_ERR_STATE when NCCL cannot be loaded.                                     */
+ * itself does not link it.  CFB_ERR_STATE when NCCL cannot be loaded.
+ * States WITHOUT a dense partial that means the same on every rank -- hashed pair counts (large domains), key
+ * dictionaries, or a domain every rank discovered for itself -- take SURVEY 8e's fallback instead: every rank
+ * finalizes, the canonical results are all-gathered and merged by key in rank order on every rank (host-mediated,
+ * synchronous); the context then HOLDS the global result: cfb_ctx_finalize returns it, further input is refused
+ * (CFB_ERR_STATE).  All ranks must be in the same case: declare the domain on every rank or on none.      */
 int cfb_ctx_allreduce(cfb_ctx *ctx, void *nccl_comm, void *stream);
 
 /* Communicator plumbing for hosts that do not link NCCL themselves (one process per GPU): rank 0 asks for an

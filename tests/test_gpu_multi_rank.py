@@ -2,8 +2,10 @@
 
 One process per GPU: every rank scans its row range of a `_10_10` table, the categorical domains are agreed with
 a MIN/MAX all-reduce (cfb_nccl_agree_domain), the dense states are summed in place by ONE fused NCCL group, and every
-rank must hold the oracle's result for the whole table (counts exact, sums <= 1e-5).  Needs >= 2 GPUs for the
-2-rank case; the world-size-1 case runs the same calls on one GPU."""
+rank must hold the oracle's result for the whole table (counts exact, sums <= 1e-5).  States without a dense partial
+(undeclared domains; wide key ranges with key dictionaries and hashed pair counts) take the fallback: canonical results
+all-gathered and merged by key.  Needs >= 2 GPUs for the 2-rank case; the world-size-1 case runs the same calls on one
+GPU."""
 import os
 import socket
 
@@ -54,16 +56,27 @@ def _worker(rank, world, port, q):
                 ctx.scan_device(dn, dc, hi - lo, stream=s.cuda_stream)
                 multi_gpu.allreduce_context(ctx, comm)  # default stream argument: torch's current stream
                 total = ctx.finalize_arrays()
-            # a state whose domain was never declared cannot be reduced: loud error, not a wrong sum
+            # a state whose domain was never declared has no dense partial that means the same on every rank: the
+            # ranks exchange canonical results instead (SURVEY 8e fallback); afterwards the context is sealed
             with CofactorContext(CFB_TRIPLE, 10, m, 1, rank) as ctx:
                 ctx.scan_device(dn, dc, hi - lo, stream=s.cuda_stream)
+                ctx.allreduce(comm.handle, stream=s.cuda_stream)
+                undeclared = ctx.finalize_arrays()
                 try:
-                    ctx.allreduce(comm.handle, stream=s.cuda_stream)
+                    ctx.scan_device(dn, dc, hi - lo, stream=s.cuda_stream)
                     refused = False
                 except nat.CofactorError as e:
                     refused = e.code == nat.CFB_ERR_STATE
+            # wide key ranges: key dictionaries + hashed pair counts, two GROUP BY slots
+            wide = [(c.astype(np.int64) * 40_000_003 % 2_000_000_011 - 1_000_000_000).astype(np.int32) for c in cat[:2]]
+            dw = [torch.from_numpy(c[lo:hi]).cuda() for c in wide]
+            slot = torch.from_numpy((np.arange(lo, hi) % 2).astype(np.int32)).cuda()
+            with CofactorContext(CFB_TRIPLE, 3, 2, 2, rank) as ctx:
+                ctx.scan_device(dn[:3], dw, hi - lo, d_group=slot, stream=s.cuda_stream)
+                ctx.allreduce(comm.handle, stream=s.cuda_stream)
+                sparse = [ctx.finalize_arrays(g) for g in range(2)]
         comm.close()
-        q.put((rank, g_lo, g_hi, total, refused))
+        q.put((rank, g_lo, g_hi, total, refused, undeclared, sparse))
     finally:
         dist.destroy_process_group()
 
@@ -94,7 +107,14 @@ def test_allreduce_inside_the_library_equals_the_oracle(world):
         assert p.exitcode == 0
     num, cat = _table()
     whole = oracle.aggregate_arrays(oracle.TRIPLE, num, cat)[0]
-    for rank, g_lo, g_hi, total, refused in results:
+    wide = [(c.astype(np.int64) * 40_000_003 % 2_000_000_011 - 1_000_000_000).astype(np.int32) for c in cat[:2]]
+    rows = len(num[0])
+    # the slot of a row is (its index inside the rank's shard + the shard's first row) % 2 = its global index % 2
+    by_slot = oracle.aggregate_arrays(oracle.TRIPLE, num[:3], wide, group=(np.arange(rows) % 2).astype(np.int32), n_groups=2)
+    for rank, g_lo, g_hi, total, refused, undeclared, sparse in results:
         assert g_lo == [int(c.min()) for c in cat] and g_hi == [int(c.max()) for c in cat]
         assert_parity(total, whole, what=f"rank {rank} of {world}")  # every rank holds the global triple
+        assert_parity(undeclared, whole, what=f"rank {rank} of {world}, undeclared domain (results exchanged)")
         assert refused
+        for g in range(2):
+            assert_parity(sparse[g], by_slot[g], what=f"rank {rank} of {world}, wide keys, slot {g}")
