@@ -22,6 +22,8 @@ cudaError_t chain_launch(const ChainLaunchParams &p) {
   a.tile_rows = p.tile_rows;
   a.fold_tiles = p.fold_tiles;
   a.sub_shift = p.sub_shift;
+  a.head_cap = p.head_cap;
+  a.skew_tile_rows = p.skew_tile_rows;
   for (int c = 0; c < kMaxCat; c++) {
     a.lo[c] = L.lo[c];
     a.dom[c] = L.dom[c];

@@ -21,6 +21,10 @@
 //      result goes to the CTA's fp32 slab in L2 as one 128-bit vector reduction per (list, quad) -- fire and
 //      forget, a few per row instead of 3 per (row, column);
 //   3. every `fold_tiles` tiles (<= ~32 K rows: bounds every fp32 run) the slab is folded into the fp64 / u64 state.
+// Skewed keys: a hot key's list would keep one team of lanes busy long after every other list has ended, so the
+// number of sub-lists of a bucket follows the bucket's length in the CTA's previous tile (~32 rows per sub-list, heads
+// handed out by a prefix sum); as long as no bucket needs more than twice the static plan the static plan (uniform
+// shift, no lookups) stays in force.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -45,6 +49,8 @@ struct ChainArgs {
   int tile_rows;   // multiple of 32, <= 65504
   int fold_tiles;  // fold the slab into the state every this many tiles of a CTA
   int sub_shift;   // S = 1 << sub_shift sub-lists per bucket (keeps all lanes busy when there are few buckets)
+  int head_cap;    // list heads in shared memory (>= D << sub_shift, <= kChainMaxHeads)
+  int skew_tile_rows;  // tile of a CTA that runs the skew plan (0: never -- CFB_CHAIN_NO_ADAPT, n = 0); multiple of 32
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];
   long long numcat_base;
   float *slab;         // [gridDim.x][D * 4Q] fp32 sums, all zero on entry and on exit
@@ -64,9 +70,17 @@ __host__ __device__ constexpr int chain_quads(int n) { return (n + 3) / 4; }
 __host__ __device__ constexpr int chain_quad_stride(int n) { return chain_quads(n) | 1; }  // odd: conflict-free payload stores
 
 // dynamic shared memory: payload tile, next pointers, list heads, column of every key
-__host__ __device__ inline size_t chain_smem_bytes(int n, int m, int heads, int total_dom, int tile_rows) {
-  return (size_t)tile_rows * (n ? chain_quad_stride(n) : 0) * 16 + (size_t)m * tile_rows * 2 + (size_t)heads * 4 +
-         (size_t)((total_dom + 15) & ~15);
+// (+ per bucket: its length in the current tile).  The skew plan (per bucket: head base / shift; per head: its bucket)
+// lives in the tail of the payload tile: a CTA that switches to it works on tiles of `skew_tile_rows` rows.
+__host__ __device__ inline size_t chain_fixed_smem_bytes(int head_cap, int total_dom, int buckets) {
+  return (size_t)head_cap * 4 + (size_t)((total_dom + 15) & ~15) + (size_t)buckets * 4 + 16;
+}
+__host__ __device__ inline size_t chain_plan_bytes(int head_cap, int buckets) {
+  return (size_t)((buckets + 7) & ~7) * 2 + (size_t)head_cap * 2;
+}
+__host__ __device__ inline size_t chain_smem_bytes(int n, int m, int head_cap, int total_dom, int buckets, int tile_rows) {
+  return (size_t)tile_rows * (n ? chain_quad_stride(n) : 0) * 16 + (size_t)m * tile_rows * 2 +
+         chain_fixed_smem_bytes(head_cap, total_dom, buckets);
 }
 
 template <int N>
@@ -74,23 +88,40 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
   extern __shared__ float4 chain_smem[];
   constexpr int Q = chain_quads(N), QS = N ? chain_quad_stride(N) : 0, QT = Q ? Q : 1;  // QT lanes per list
   const int T = a.tile_rows, m = a.m, D = a.n_groups * a.total_dom, tid = threadIdx.x;
-  const int S = 1 << a.sub_shift, heads = D << a.sub_shift;
+  const int cap = a.head_cap;
   float4 *pay = chain_smem;                                                               // [T][QS]
   unsigned short *nxt = reinterpret_cast<unsigned short *>(pay + (size_t)T * QS);          // [m][T]
-  unsigned *head = reinterpret_cast<unsigned *>(nxt + (size_t)m * T);                      // [heads]
-  unsigned char *col_of = reinterpret_cast<unsigned char *>(head + heads);                 // [total_dom]
+  unsigned *head = reinterpret_cast<unsigned *>(nxt + (size_t)m * T);                      // [cap]
+  unsigned char *col_of = reinterpret_cast<unsigned char *>(head + cap);                   // [total_dom]
+  unsigned *blen = reinterpret_cast<unsigned *>(col_of + ((a.total_dom + 15) & ~15));      // [D] bucket lengths of this tile
+  // skew plan, over the payload rows >= skew_tile_rows: [D] head base (12 bits) | shift << 12, [cap] bucket of every head
+  unsigned short *hplan = reinterpret_cast<unsigned short *>(pay + (size_t)a.skew_tile_rows * QS);
+  unsigned short *hbucket = hplan + ((D + 7) & ~7);
   float *slab = a.slab + (size_t)blockIdx.x * D * (4 * Q);
   unsigned *cslab = a.cnt_slab + (size_t)blockIdx.x * D;
+  __shared__ unsigned plan_scan[kChainThreads / 32 + 1];
+  // the static plan: the same shift for every bucket, head = (bucket << shift) + (row & (S - 1)), no lookups
+  bool uniform = true;
+  int ushift = a.sub_shift, heads = D << a.sub_shift;
 
   for (int c = 0; c < m; c++)
     for (int s = a.cat_off[c] + tid; s < a.cat_off[c + 1]; s += kChainThreads) col_of[s] = (unsigned char)c;
 
+  // Tiles of T rows, interleaved over the CTAs (neighbouring CTAs stream neighbouring pages).  While the skew plan is
+  // in force a tile is worked off in pieces of at most skew_tile_rows rows (the plan occupies the payload's tail).
   const unsigned long long n_tiles = (a.n_rows + T - 1) / T;
   int since_fold = 0;
   for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long lo = tile * T;
-    const int cnt = (int)min((unsigned long long)T, a.n_rows - lo);
+   const unsigned long long tile_lo = tile * T;
+   const int tile_cnt = (int)min((unsigned long long)T, a.n_rows - tile_lo);
+   for (int done = 0; done < tile_cnt;) {
+    const unsigned long long lo = tile_lo + done;
+    const int cnt = min(uniform ? T : a.skew_tile_rows, tile_cnt - done);
+    const bool first_piece = done == 0;
+    done += cnt;
+    const bool last_piece = done >= tile_cnt;
     for (int i = tid; i < heads; i += kChainThreads) head[i] = kChainEnd;
+    for (int i = tid; i < D; i += kChainThreads) blen[i] = 0;
     __syncthreads();
     // ---- 1. payload rows, list pushes, packed slots
     const bool grouped = a.cols.group != nullptr;
@@ -123,7 +154,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
           for (int q = 0; q < Q; q++) pay[(size_t)row * QS + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
-      const int gbase = g * a.total_dom, sub = row & (S - 1);
+      const int gbase = g * a.total_dom;
       bool bad = false;
       for (int c0 = 0; c0 < m; c0 += 4) {  // keys four columns at a time: the loads are independent
         unsigned s[4];
@@ -135,7 +166,15 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
             const int c = c0 + e;
             const bool ok = s[e] < (unsigned)a.dom[c];
             if (ok && live) {
-              const unsigned prev = atomicExch(&head[((gbase + a.cat_off[c] + (int)s[e]) << a.sub_shift) + sub], (unsigned)row);
+              const int bucket = gbase + a.cat_off[c] + (int)s[e];
+              int h;
+              if (uniform) {
+                h = (bucket << ushift) + (row & ((1 << ushift) - 1));
+              } else {
+                const unsigned pl = hplan[bucket];
+                h = (int)(pl & 0xFFFu) + (row & ((1 << (pl >> 12)) - 1));
+              }
+              const unsigned prev = atomicExch(&head[h], (unsigned)row);
               nxt[(size_t)c * T + row] = (unsigned short)prev;
             }
             // a filtered row keeps its real slots: its zero increments then spread over the pair tables like live rows
@@ -152,7 +191,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
     __syncthreads();
     // the next tile of this CTA is pulled into L2 while the lists are walked: pass 1 is bound by the latency of its
     // global loads (a few dependent batches per row), and an L2 hit costs a third of an HBM access
-    if (tile + gridDim.x < n_tiles) {
+    if (first_piece && tile + gridDim.x < n_tiles) {
       const unsigned long long nlo = (tile + gridDim.x) * T;
       const int ncnt = (int)min((unsigned long long)T, a.n_rows - nlo);
       const int lines = (ncnt + 31) / 32, n_cols = N + m + (a.cols.group ? 1 : 0);
@@ -174,7 +213,8 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       const int list_b = task_b < n_tasks ? task_b / QT : list_a, q_b = task_b - (task_b / QT) * QT;
       unsigned row_a = head[list_a], row_b = task_b < n_tasks ? head[list_b] : kChainEnd;
       if (row_a == kChainEnd && row_b == kChainEnd) continue;
-      const int b_a = list_a >> a.sub_shift, b_b = list_b >> a.sub_shift;  // bucket = (slot, column, key)
+      const int b_a = uniform ? list_a >> ushift : (int)hbucket[list_a];  // bucket = (slot, column, key)
+      const int b_b = uniform ? list_b >> ushift : (int)hbucket[list_b];
       const unsigned short *nx_a = nxt + (size_t)col_of[b_a % a.total_dom] * T;  // the column's next pointers
       const unsigned short *nx_b = nxt + (size_t)col_of[b_b % a.total_dom] * T;
       float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
@@ -209,15 +249,75 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       }
       if (n_a) {
         if constexpr (N > 0) red_v4(slab + (size_t)b_a * (4 * Q) + 4 * q_a, acc_a.x, acc_a.y, acc_a.z, acc_a.w);
-        if (q_a == 0) atomicAdd(cslab + b_a, n_a);
+        if (q_a == 0) atomicAdd(blen + b_a, n_a);
       }
       if (n_b) {
         if constexpr (N > 0) red_v4(slab + (size_t)b_b * (4 * Q) + 4 * q_b, acc_b.x, acc_b.y, acc_b.z, acc_b.w);
-        if (q_b == 0) atomicAdd(cslab + b_b, n_b);
+        if (q_b == 0) atomicAdd(blen + b_b, n_b);
+      }
+    }
+    __syncthreads();
+    // ---- 2b. key counts to the count slab; the sub-list plan of the next tile from this tile's bucket lengths
+    {
+      constexpr int kTargetLen = 32, kMaxShift = 8;
+      auto want = [&](unsigned len, int target) {
+        int sh = 0;
+        while (sh < kMaxShift && (len + target - 1) / target > (1u << sh)) sh++;
+        return sh;
+      };
+      int hot = 0;
+      for (int b = tid; b < D; b += kChainThreads) {
+        const unsigned len = blen[b];
+        if (len) atomicAdd(cslab + b, len);
+        hot |= want(len, kTargetLen) > a.sub_shift + 1;
+      }
+      // (a short piece -- the rest of a tile -- says nothing about the next full one: the plan in force stays)
+      const bool keep_plan = !uniform && 2 * cnt < a.skew_tile_rows;
+      const bool skewed = __syncthreads_or(hot) != 0 && a.skew_tile_rows > 0;
+      if (keep_plan) {
+      } else if (!skewed) {
+        uniform = true;
+        ushift = a.sub_shift;
+        heads = D << a.sub_shift;
+      } else {
+        // per bucket 2^shift sub-lists of ~target rows; the target doubles until the heads fit
+        const int per = (D + kChainThreads - 1) / kChainThreads, b0 = tid * per, b1 = min(D, b0 + per);
+        int target = kTargetLen;
+        unsigned mine = 0, total = 0, before = 0;
+        for (;; target *= 2) {
+          mine = 0;
+          for (int b = b0; b < b1; b++) mine += 1u << want(blen[b], target);
+          unsigned incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += t;
+          }
+          __syncthreads();
+          if ((tid & 31) == 31) plan_scan[tid >> 5] = incl;
+          __syncthreads();
+          before = incl - mine;
+          total = 0;
+          for (int w = 0; w < kChainThreads / 32; w++) {
+            const unsigned v = plan_scan[w];
+            if (w < (tid >> 5)) before += v;
+            total += v;
+          }
+          if ((int)total <= cap || target >= (1 << 20)) break;
+        }
+        unsigned base = before;
+        for (int b = b0; b < b1; b++) {
+          const int sh = want(blen[b], target);
+          hplan[b] = (unsigned short)(base | ((unsigned)sh << 12));
+          for (unsigned j = 0; j < (1u << sh); j++) hbucket[base + j] = (unsigned short)b;
+          base += 1u << sh;
+        }
+        uniform = false;
+        heads = (int)total;
       }
     }
     // ---- 3. fold the slab into the fp64 / u64 state
-    if (++since_fold >= a.fold_tiles || tile + gridDim.x >= n_tiles) {
+    if ((last_piece && ++since_fold >= a.fold_tiles) || (last_piece && tile + gridDim.x >= n_tiles)) {
       since_fold = 0;
       __threadfence();
       __syncthreads();
@@ -236,6 +336,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       }
     }
     __syncthreads();
+   }
   }
 }
 

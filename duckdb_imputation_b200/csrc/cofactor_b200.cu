@@ -856,15 +856,25 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   if (const char *e = getenv("CFB_CHAIN_SUB_SHIFT")) sub_shift = std::max(0, std::min(atoi(e), 12));
   while ((D << sub_shift) > cfb::kChainMaxHeads) sub_shift--;
   const int heads = (int)(D << sub_shift);
+  // the skew plan (per-bucket sub-list counts) wants room for at least 2048 heads; it lives in the payload tile's tail
+  const bool adaptive = !getenv("CFB_CHAIN_NO_ADAPT") && c->n > 0;
+  const int head_cap = adaptive ? std::min<int>(cfb::kChainMaxHeads, std::max(heads, 2048)) : heads;
   // kChainCtasPerSm CTAs share an SM: each gets its share of the SM's shared memory (1 KB per CTA is the system's)
   const long long cta_smem = std::min<long long>(dev_info(c->device).smem_optin - 1024,
                                                  (long long)dev_info(c->device).smem_sm / cfb::kChainCtasPerSm - 1024 - 512);
-  const long long budget = cta_smem - 4ll * heads - ((c->lay.total_dom + 15) & ~15ll);
+  const long long budget = cta_smem - (long long)cfb::chain_fixed_smem_bytes(head_cap, (int)c->lay.total_dom, (int)D);
   const int per_row = (c->n ? cfb::chain_quad_stride(c->n) * 16 : 0) + 2 * c->m;
   int tile = (int)std::min<long long>(budget / per_row, 32768);
   tile = tile >= 2 * cfb::kChainThreads ? tile / cfb::kChainThreads * cfb::kChainThreads : tile / 256 * 256;
   if (const char *e = getenv("CFB_CHAIN_TILE")) tile = std::min(tile, std::max(256, atoi(e) / 32 * 32));
   if (tile < 512) return 1;
+  int skew_tile = 0;
+  if (adaptive) {
+    const long long quad_bytes = (long long)cfb::chain_quad_stride(c->n) * 16;
+    const long long lost = ((long long)cfb::chain_plan_bytes(head_cap, (int)D) + quad_bytes - 1) / quad_bytes;
+    skew_tile = (int)((tile - lost) / 32 * 32);
+    if (skew_tile < 256) skew_tile = 0;
+  }
   const unsigned long long n_tiles = (rows + tile - 1) / tile;
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * cfb::kChainCtasPerSm, n_tiles);
   const long long slab_floats = std::max<long long>(4, D * 4 * cfb::chain_quads(c->n));
@@ -903,7 +913,9 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   p.sub_shift = sub_shift;
   p.grid = grid;
   p.smem_max = dev_info(c->device).smem_optin - 1024;
-  p.smem_bytes = cfb::chain_smem_bytes(c->n, c->m, heads, (int)c->lay.total_dom, tile);
+  p.smem_bytes = cfb::chain_smem_bytes(c->n, c->m, head_cap, (int)c->lay.total_dom, (int)D, tile);
+  p.head_cap = head_cap;
+  p.skew_tile_rows = skew_tile;
   p.slab = c->d_chain_slab;
   p.cnt_slab = c->d_cnt_slab;
   p.f64 = c->d_f64;
@@ -919,6 +931,49 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
 }
 
 // Room for `cols` packed one-byte columns of `rows` rows (column stride returned in *stride).
+// Large packed-slot scratch (hundreds of MB for a 32 M-row slice) is not kept by parked contexts; it waits here for
+// the next context instead of going back to the driver: a cudaMalloc of that size inside a scan costs milliseconds
+// and now and then far more.  Buffers arrive with their context's streams drained.
+struct PackedPool {
+  std::mutex mu;
+  struct Buf {
+    int device;
+    unsigned char *p;
+    size_t cap;
+  };
+  std::vector<Buf> idle;
+  static constexpr size_t kMaxIdle = 2;
+  unsigned char *take(int device, size_t need, size_t *cap) {
+    std::lock_guard<std::mutex> g(mu);
+    for (size_t i = 0; i < idle.size(); i++)
+      if (idle[i].device == device && idle[i].cap >= need) {
+        unsigned char *p = idle[i].p;
+        *cap = idle[i].cap;
+        idle[i] = idle.back();
+        idle.pop_back();
+        return p;
+      }
+    return nullptr;
+  }
+  void give(int device, unsigned char *p, size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
+    if (idle.size() >= kMaxIdle) {  // keep the larger ones
+      size_t smallest = 0;
+      for (size_t i = 1; i < idle.size(); i++)
+        if (idle[i].cap < idle[smallest].cap) smallest = i;
+      if (idle[smallest].cap >= cap) {
+        cudaFree(p);
+        return;
+      }
+      cudaFree(idle[smallest].p);
+      idle[smallest] = idle.back();
+      idle.pop_back();
+    }
+    idle.push_back({device, p, cap});
+  }
+};
+PackedPool g_packed_pool;
+
 int ensure_packed(cfb_ctx *c, int cols, unsigned long long rows, unsigned long long *stride) {
   *stride = (rows + 255) & ~255ull;
   const size_t need = (size_t)cols * *stride;
@@ -926,9 +981,15 @@ int ensure_packed(cfb_ctx *c, int cols, unsigned long long rows, unsigned long l
     if (c->d_packed) {
       CU(cudaStreamSynchronize(c->stream));
       if (c->user_stream) CU(cudaStreamSynchronize(c->user_stream));
-      cudaFree(c->d_packed);
+      g_packed_pool.give(c->device, c->d_packed, c->packed_cap);
       c->d_packed = nullptr;
       c->packed_cap = 0;
+    }
+    size_t cap = 0;
+    if (unsigned char *p = g_packed_pool.take(c->device, need, &cap)) {
+      c->d_packed = p;
+      c->packed_cap = cap;
+      return CFB_OK;
     }
     CU(cudaMalloc(&c->d_packed, need));
     c->packed_cap = need;
@@ -2020,7 +2081,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   c->uses_group = false;
   c->user_stream = nullptr;
   if (c->packed_cap > (160u << 20)) {  // a parked context keeps moderate scratch only (<= 13 M rows x 12 columns)
-    cudaFree(c->d_packed);
+    g_packed_pool.give(c->device, c->d_packed, c->packed_cap);  // (the streams are drained: nothing reads it)
     c->d_packed = nullptr;
     c->packed_cap = 0;
   }
