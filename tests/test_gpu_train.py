@@ -155,3 +155,36 @@ def test_training_errors_are_reported():
             s.linreg_train(0, 0.001, 0.0, 10)
         with Sigma.from_context(ctx) as s, pytest.raises(CofactorError, match="no categorical label"):
             s.lda_train(0.1)
+
+
+def test_sigma_of_one_group_slot_numeric_only_and_empty():
+    """cfb_sigma_from_ctx on a GROUP BY context (every slot has its own state), on a table without categorical columns,
+    and on a context that has seen no rows."""
+    rng = np.random.default_rng(61)
+    rows = 5_000
+    x = [rng.standard_normal(rows).astype(np.float32) for _ in range(3)]
+    c = [rng.integers(0, 4, rows).astype(np.int32)]
+    g = rng.integers(0, 3, rows).astype(np.int32)
+    with CofactorContext(CFB_TRIPLE, 3, 1, n_groups=3) as ctx:
+        ctx.set_cat_domain([0], [3])
+        ctx.append(x, c, group=g.astype(np.uint32))
+        for slot in range(3):
+            sel = g == slot
+            want, cat_array, _ = oracle.build_sigma(arrays_to_struct(
+                oracle.aggregate_arrays(oracle.TRIPLE, [v[sel] for v in x], [v[sel] for v in c])[0], narrow=False))
+            with Sigma.from_context(ctx, group=slot) as s:
+                assert list(s.cat_array) == cat_array
+                np.testing.assert_allclose(s.matrix()[0], want, rtol=1e-5, atol=1e-3)
+    with CofactorContext(CFB_TRIPLE, 3, 0) as ctx:
+        ctx.append(x, [])
+        want, _, _ = oracle.build_sigma(arrays_to_struct(oracle.aggregate_arrays(oracle.TRIPLE, x, [])[0], narrow=False))
+        with Sigma.from_context(ctx) as s:
+            assert s.p == 4 and len(s.cat_array) == 0
+            np.testing.assert_allclose(s.matrix()[0], want, rtol=1e-5, atol=1e-3)
+            fit = s.linreg_train(2, 0.01, 0.0, 500)
+            assert fit["coeff"][3] == -1.0 and np.all(np.isfinite(fit["coeff"]))
+    with CofactorContext(CFB_TRIPLE, 2, 1) as ctx:
+        with Sigma.from_context(ctx) as s:  # no rows: N = 0, no keys
+            assert s.p == 3 and s.matrix()[0].sum() == 0.0
+            fit = s.linreg_train(0, 0.01, 0.0, 10)
+            assert list(fit["coeff"]) == [0.0, -1.0, 0.0]
