@@ -317,3 +317,31 @@ def test_cross_device_combine():
             a.combine(b)
             got = a.finalize_arrays()
         assert_parity(got, oracle.aggregate_arrays(CFB_TRIPLE, num, cat)[0], what=f"cross-device dom={dom}")
+
+
+@pytest.mark.parametrize("n,m,G", [(10, 10, 1), (20, 10, 2), (3, 4, 1)])
+def test_skewed_keys_switch_the_list_plan(n, m, G, monkeypatch):
+    """Zipf-distributed keys over a domain of 100: a hot key's bucket is far longer than the static sub-lists expect,
+    so chain_sum_kernel hands that bucket more sub-lists for the CTA's NEXT tile (and works tiles off in two pieces
+    while that plan is in force).  Small tiles (CFB_CHAIN_TILE) give every CTA several tiles at test size, so the
+    switch to the plan, its use, the short rest-of-tile pieces and the way back all run.  Counts exact, sums <= 1e-5."""
+    import torch
+    monkeypatch.setenv("CFB_CHAIN_TILE", "512")
+    rng = np.random.default_rng(77 + n)
+    rows = 420_013
+    num = [rng.random(rows).astype(np.float32) for _ in range(n)]
+    cat = [np.minimum(rng.zipf(1.2, rows) - 1, 99).astype(np.int32) for _ in range(m)]
+    # the second half of the table is uniform again in two columns: the plan must fall back to the static one
+    for c in cat[:2]:
+        c[rows // 2:] = rng.integers(0, 100, rows - rows // 2)
+    group = (rng.random(rows) < 0.2).astype(np.int32) if G > 1 else None
+    dn = [torch.from_numpy(c).cuda() for c in num]
+    dc = [torch.from_numpy(c).cuda() for c in cat]
+    dg = torch.from_numpy(group).cuda() if G > 1 else None
+    with CofactorContext(CFB_TRIPLE, n, m, G) as ctx:
+        ctx.set_cat_domain([0] * m, [99] * m)
+        ctx.scan_device(dn, dc, rows, d_group=dg)
+        got = [ctx.finalize_arrays(g) for g in range(G)]
+    want = oracle.aggregate_arrays(oracle.TRIPLE, num, cat, group=group, n_groups=G)
+    for g in range(G):
+        assert_parity(got[g], want[g], what=f"skewed keys, slot {g}")
