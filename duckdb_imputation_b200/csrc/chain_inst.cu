@@ -23,7 +23,7 @@ cudaError_t chain_launch(const ChainLaunchParams &p) {
   a.fold_tiles = p.fold_tiles;
   a.sub_shift = p.sub_shift;
   a.head_cap = p.head_cap;
-  a.skew_tile_rows = p.skew_tile_rows;
+  a.adaptive = p.adaptive;
   for (int c = 0; c < kMaxCat; c++) {
     a.lo[c] = L.lo[c];
     a.dom[c] = L.dom[c];

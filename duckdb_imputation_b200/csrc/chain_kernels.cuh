@@ -23,8 +23,8 @@
 //   3. every `fold_tiles` tiles (<= ~32 K rows: bounds every fp32 run) the slab is folded into the fp64 / u64 state.
 // Skewed keys: a hot key's list would keep one team of lanes busy long after every other list has ended, so the
 // number of sub-lists of a bucket follows the bucket's length in the CTA's previous tile (~32 rows per sub-list, heads
-// handed out by a prefix sum); as long as no bucket needs more than twice the static plan the static plan (uniform
-// shift, no lookups) stays in force.
+// handed out by a prefix sum; a head's upper half-word names its bucket); as long as no bucket needs more than twice the
+// static plan the static plan (uniform shift, no lookups) stays in force.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -50,7 +50,7 @@ struct ChainArgs {
   int fold_tiles;  // fold the slab into the state every this many tiles of a CTA
   int sub_shift;   // S = 1 << sub_shift sub-lists per bucket (keeps all lanes busy when there are few buckets)
   int head_cap;    // list heads in shared memory (>= D << sub_shift, <= kChainMaxHeads)
-  int skew_tile_rows;  // tile of a CTA that runs the skew plan (0: never -- CFB_CHAIN_NO_ADAPT, n = 0); multiple of 32
+  int adaptive;    // 0: always the static plan (CFB_CHAIN_NO_ADAPT: measurements)
   int lo[kMaxCat], dom[kMaxCat], cat_off[kMaxCat + 1];
   long long numcat_base;
   float *slab;         // [gridDim.x][D * 4Q] fp32 sums, all zero on entry and on exit
@@ -70,13 +70,9 @@ __host__ __device__ constexpr int chain_quads(int n) { return (n + 3) / 4; }
 __host__ __device__ constexpr int chain_quad_stride(int n) { return chain_quads(n) | 1; }  // odd: conflict-free payload stores
 
 // dynamic shared memory: payload tile, next pointers, list heads, column of every key
-// (+ per bucket: its length in the current tile).  The skew plan (per bucket: head base / shift; per head: its bucket)
-// lives in the tail of the payload tile: a CTA that switches to it works on tiles of `skew_tile_rows` rows.
+// (+ per bucket: its length in the current tile and its entry of the skew plan)
 __host__ __device__ inline size_t chain_fixed_smem_bytes(int head_cap, int total_dom, int buckets) {
-  return (size_t)head_cap * 4 + (size_t)((total_dom + 15) & ~15) + (size_t)buckets * 4 + 16;
-}
-__host__ __device__ inline size_t chain_plan_bytes(int head_cap, int buckets) {
-  return (size_t)((buckets + 7) & ~7) * 2 + (size_t)head_cap * 2;
+  return (size_t)head_cap * 4 + (size_t)((total_dom + 15) & ~15) + (size_t)buckets * 4 + (size_t)((buckets + 7) & ~7) * 2 + 16;
 }
 __host__ __device__ inline size_t chain_smem_bytes(int n, int m, int head_cap, int total_dom, int buckets, int tile_rows) {
   return (size_t)tile_rows * (n ? chain_quad_stride(n) : 0) * 16 + (size_t)m * tile_rows * 2 +
@@ -94,9 +90,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
   unsigned *head = reinterpret_cast<unsigned *>(nxt + (size_t)m * T);                      // [cap]
   unsigned char *col_of = reinterpret_cast<unsigned char *>(head + cap);                   // [total_dom]
   unsigned *blen = reinterpret_cast<unsigned *>(col_of + ((a.total_dom + 15) & ~15));      // [D] bucket lengths of this tile
-  // skew plan, over the payload rows >= skew_tile_rows: [D] head base (12 bits) | shift << 12, [cap] bucket of every head
-  unsigned short *hplan = reinterpret_cast<unsigned short *>(pay + (size_t)a.skew_tile_rows * QS);
-  unsigned short *hbucket = hplan + ((D + 7) & ~7);
+  unsigned short *hplan = reinterpret_cast<unsigned short *>(blen + D);  // [D] skew plan: head base (12 bits) | shift << 12
   float *slab = a.slab + (size_t)blockIdx.x * D * (4 * Q);
   unsigned *cslab = a.cnt_slab + (size_t)blockIdx.x * D;
   __shared__ unsigned plan_scan[kChainThreads / 32 + 1];
@@ -107,20 +101,13 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
   for (int c = 0; c < m; c++)
     for (int s = a.cat_off[c] + tid; s < a.cat_off[c + 1]; s += kChainThreads) col_of[s] = (unsigned char)c;
 
-  // Tiles of T rows, interleaved over the CTAs (neighbouring CTAs stream neighbouring pages).  While the skew plan is
-  // in force a tile is worked off in pieces of at most skew_tile_rows rows (the plan occupies the payload's tail).
   const unsigned long long n_tiles = (a.n_rows + T - 1) / T;
   int since_fold = 0;
   for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-   const unsigned long long tile_lo = tile * T;
-   const int tile_cnt = (int)min((unsigned long long)T, a.n_rows - tile_lo);
-   for (int done = 0; done < tile_cnt;) {
-    const unsigned long long lo = tile_lo + done;
-    const int cnt = min(uniform ? T : a.skew_tile_rows, tile_cnt - done);
-    const bool first_piece = done == 0;
-    done += cnt;
-    const bool last_piece = done >= tile_cnt;
-    for (int i = tid; i < heads; i += kChainThreads) head[i] = kChainEnd;
+    const unsigned long long lo = tile * T;
+    const int cnt = (int)min((unsigned long long)T, a.n_rows - lo);
+    // (skew plan: a head's upper half-word is its bucket, written when the plan is made)
+    for (int i = tid; i < heads; i += kChainThreads) head[i] = uniform ? kChainEnd : ((head[i] & 0xFFFF0000u) | kChainEnd);
     for (int i = tid; i < D; i += kChainThreads) blen[i] = 0;
     __syncthreads();
     // ---- 1. payload rows, list pushes, packed slots
@@ -168,13 +155,15 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
             if (ok && live) {
               const int bucket = gbase + a.cat_off[c] + (int)s[e];
               int h;
+              unsigned tag = (unsigned)row;
               if (uniform) {
                 h = (bucket << ushift) + (row & ((1 << ushift) - 1));
               } else {
                 const unsigned pl = hplan[bucket];
                 h = (int)(pl & 0xFFFu) + (row & ((1 << (pl >> 12)) - 1));
+                tag |= (unsigned)bucket << 16;
               }
-              const unsigned prev = atomicExch(&head[h], (unsigned)row);
+              const unsigned prev = atomicExch(&head[h], tag);
               nxt[(size_t)c * T + row] = (unsigned short)prev;
             }
             // a filtered row keeps its real slots: its zero increments then spread over the pair tables like live rows
@@ -191,7 +180,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
     __syncthreads();
     // the next tile of this CTA is pulled into L2 while the lists are walked: pass 1 is bound by the latency of its
     // global loads (a few dependent batches per row), and an L2 hit costs a third of an HBM access
-    if (first_piece && tile + gridDim.x < n_tiles) {
+    if (tile + gridDim.x < n_tiles) {
       const unsigned long long nlo = (tile + gridDim.x) * T;
       const int ncnt = (int)min((unsigned long long)T, a.n_rows - nlo);
       const int lines = (ncnt + 31) / 32, n_cols = N + m + (a.cols.group ? 1 : 0);
@@ -211,10 +200,11 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       const int task_b = task + kChainThreads;
       const int list_a = task / QT, q_a = task - list_a * QT;
       const int list_b = task_b < n_tasks ? task_b / QT : list_a, q_b = task_b - (task_b / QT) * QT;
-      unsigned row_a = head[list_a], row_b = task_b < n_tasks ? head[list_b] : kChainEnd;
+      const unsigned head_a = head[list_a], head_b = task_b < n_tasks ? head[list_b] : kChainEnd;
+      unsigned row_a = head_a & 0xFFFFu, row_b = head_b & 0xFFFFu;
       if (row_a == kChainEnd && row_b == kChainEnd) continue;
-      const int b_a = uniform ? list_a >> ushift : (int)hbucket[list_a];  // bucket = (slot, column, key)
-      const int b_b = uniform ? list_b >> ushift : (int)hbucket[list_b];
+      const int b_a = uniform ? list_a >> ushift : (int)(head_a >> 16);  // bucket = (slot, column, key)
+      const int b_b = uniform ? list_b >> ushift : (int)(head_b >> 16);
       const unsigned short *nx_a = nxt + (size_t)col_of[b_a % a.total_dom] * T;  // the column's next pointers
       const unsigned short *nx_b = nxt + (size_t)col_of[b_b % a.total_dom] * T;
       float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
@@ -265,17 +255,17 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
         while (sh < kMaxShift && (len + target - 1) / target > (1u << sh)) sh++;
         return sh;
       };
+      // the static plan is good enough while its longest sub-list stays within a few times the average work of a
+      // lane slot (two lists per lane in flight): imbalance only costs when one walk outlasts everything else
+      const unsigned slot_work = (unsigned)((long long)cnt * m * QT / (2 * kChainThreads)) + 1;
       int hot = 0;
       for (int b = tid; b < D; b += kChainThreads) {
         const unsigned len = blen[b];
         if (len) atomicAdd(cslab + b, len);
-        hot |= want(len, kTargetLen) > a.sub_shift + 1;
+        hot |= (len >> a.sub_shift) > 4 * slot_work;
       }
-      // (a short piece -- the rest of a tile -- says nothing about the next full one: the plan in force stays)
-      const bool keep_plan = !uniform && 2 * cnt < a.skew_tile_rows;
-      const bool skewed = __syncthreads_or(hot) != 0 && a.skew_tile_rows > 0;
-      if (keep_plan) {
-      } else if (!skewed) {
+      const bool skewed = __syncthreads_or(hot) != 0 && a.adaptive;
+      if (!skewed) {
         uniform = true;
         ushift = a.sub_shift;
         heads = D << a.sub_shift;
@@ -309,7 +299,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
         for (int b = b0; b < b1; b++) {
           const int sh = want(blen[b], target);
           hplan[b] = (unsigned short)(base | ((unsigned)sh << 12));
-          for (unsigned j = 0; j < (1u << sh); j++) hbucket[base + j] = (unsigned short)b;
+          for (unsigned j = 0; j < (1u << sh); j++) head[base + j] = ((unsigned)b << 16) | kChainEnd;
           base += 1u << sh;
         }
         uniform = false;
@@ -317,7 +307,7 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       }
     }
     // ---- 3. fold the slab into the fp64 / u64 state
-    if ((last_piece && ++since_fold >= a.fold_tiles) || (last_piece && tile + gridDim.x >= n_tiles)) {
+    if (++since_fold >= a.fold_tiles || tile + gridDim.x >= n_tiles) {
       since_fold = 0;
       __threadfence();
       __syncthreads();
@@ -336,7 +326,6 @@ __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) chain_sum_kern
       }
     }
     __syncthreads();
-   }
   }
 }
 

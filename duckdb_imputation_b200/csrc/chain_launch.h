@@ -11,7 +11,7 @@ struct ChainLaunchParams {
   ScanCols cols;
   const Layout *lay;  // host copy
   unsigned long long rows;
-  int tile_rows, skew_tile_rows, fold_tiles, sub_shift, head_cap, grid;
+  int tile_rows, fold_tiles, sub_shift, head_cap, adaptive, grid;
   int smem_max;  // cudaDevAttrMaxSharedMemoryPerBlockOptin - 1 KB
   size_t smem_bytes;
   float *slab;

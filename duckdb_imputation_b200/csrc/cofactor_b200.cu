@@ -856,7 +856,7 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   if (const char *e = getenv("CFB_CHAIN_SUB_SHIFT")) sub_shift = std::max(0, std::min(atoi(e), 12));
   while ((D << sub_shift) > cfb::kChainMaxHeads) sub_shift--;
   const int heads = (int)(D << sub_shift);
-  // the skew plan (per-bucket sub-list counts) wants room for at least 2048 heads; it lives in the payload tile's tail
+  // the skew plan (per-bucket sub-list counts) wants room for at least 2048 heads
   const bool adaptive = !getenv("CFB_CHAIN_NO_ADAPT") && c->n > 0;
   const int head_cap = adaptive ? std::min<int>(cfb::kChainMaxHeads, std::max(heads, 2048)) : heads;
   // kChainCtasPerSm CTAs share an SM: each gets its share of the SM's shared memory (1 KB per CTA is the system's)
@@ -868,13 +868,6 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   tile = tile >= 2 * cfb::kChainThreads ? tile / cfb::kChainThreads * cfb::kChainThreads : tile / 256 * 256;
   if (const char *e = getenv("CFB_CHAIN_TILE")) tile = std::min(tile, std::max(256, atoi(e) / 32 * 32));
   if (tile < 512) return 1;
-  int skew_tile = 0;
-  if (adaptive) {
-    const long long quad_bytes = (long long)cfb::chain_quad_stride(c->n) * 16;
-    const long long lost = ((long long)cfb::chain_plan_bytes(head_cap, (int)D) + quad_bytes - 1) / quad_bytes;
-    skew_tile = (int)((tile - lost) / 32 * 32);
-    if (skew_tile < 256) skew_tile = 0;
-  }
   const unsigned long long n_tiles = (rows + tile - 1) / tile;
   const int grid = (int)std::min<unsigned long long>((unsigned long long)dev_info(c->device).sms * cfb::kChainCtasPerSm, n_tiles);
   const long long slab_floats = std::max<long long>(4, D * 4 * cfb::chain_quads(c->n));
@@ -915,7 +908,7 @@ int launch_chain(cfb_ctx *c, const cfb::ScanCols &sc, unsigned long long rows, u
   p.smem_max = dev_info(c->device).smem_optin - 1024;
   p.smem_bytes = cfb::chain_smem_bytes(c->n, c->m, head_cap, (int)c->lay.total_dom, (int)D, tile);
   p.head_cap = head_cap;
-  p.skew_tile_rows = skew_tile;
+  p.adaptive = adaptive ? 1 : 0;
   p.slab = c->d_chain_slab;
   p.cnt_slab = c->d_cnt_slab;
   p.f64 = c->d_f64;
@@ -1661,12 +1654,19 @@ int predict_launch(cfb_model *M, const float *const *num, const int32_t *const *
   }
   a.vec4 = single && aligned;
   const size_t units = a.vec4 ? std::max<size_t>(1, rows / 4) : rows;
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(single ? 4 : 2, (size_t)smem_max / std::max<size_t>(M->smem, 1)));
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)dev_info(device).sms * per_sm, (units + cfb::kPredictThreads - 1) / cfb::kPredictThreads));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(single ? 4 : 2, (size_t)smem_max / std::max<size_t>(M->smem, 1)));
+  // a model that leaves room for at most two CTAs per SM: one CTA of 1024 threads shares it among 32 warps
+  int threads = cfb::kPredictThreads;
+  if (!single && cfb::predict_multi_max_threads(a.kb) >= 1024 && (size_t)dev_info(device).smem_sm / std::max<size_t>(M->smem + 1024, 1) <= 3 &&
+      !getenv("CFB_PREDICT_SMALL_CTAS")) {
+    threads = 1024;
+    per_sm = 1;
+  }
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)dev_info(device).sms * per_sm, (units + threads - 1) / threads));
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return e;
-    kern<<<grid, cfb::kPredictThreads, M->smem, s>>>(a);
+    kern<<<grid, threads, M->smem, s>>>(a);
     return cudaGetLastError();
   };
   cudaError_t e;

@@ -69,9 +69,9 @@ __host__ __device__ inline size_t predict_smem_bytes(int n, int kb, int total, i
 // model -> shared memory (every CTA; persistent grid, so once per CTA)
 __device__ __forceinline__ void predict_load_model(const PredictArgs &a, double *smem) {
   const int words = a.kb * (1 + a.n + a.total);
-  for (int i = threadIdx.x; i < words; i += kPredictThreads) smem[i] = a.d_model[i];
+  for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = a.d_model[i];
   int *map = reinterpret_cast<int *>(smem + words);
-  for (int i = threadIdx.x; i < a.map_total; i += kPredictThreads) map[i] = a.d_map[i];
+  for (int i = threadIdx.x; i < a.map_total; i += blockDim.x) map[i] = a.d_map[i];
   __syncthreads();
 }
 
@@ -150,15 +150,18 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_score_kernel(const
 // class-minor ([feature][KB], padded with zeros), so the KB weights of a feature are consecutive: a uniform
 // LDS.128 per two classes for a numeric feature, and one contiguous run per thread for a (column, key).
 // Result = first index of the largest score (lda.cpp:566-573), or score_0 when mode = SCORE.
+// A wide model leaves room for one or two CTAs per SM only; up to 12 outputs (<= 64 registers per thread) the CTA may
+// then have 1024 threads, so that one copy of the model serves 32 warps (the kernel waits on its column loads).
+constexpr int predict_multi_max_threads(int kb) { return kb <= 12 ? 1024 : kPredictThreads; }
 template <int KB>
-__global__ void __launch_bounds__(kPredictThreads) predict_multi_kernel(const __grid_constant__ PredictArgs a) {
+__global__ void __launch_bounds__(predict_multi_max_threads(KB)) predict_multi_kernel(const __grid_constant__ PredictArgs a) {
   extern __shared__ double predict_smem[];
   predict_load_model(a, predict_smem);
   const int n = a.n, m = a.m;
   const double *bias = predict_smem, *w_num = bias + KB, *w_cat = w_num + (size_t)n * KB;
   const int *map = reinterpret_cast<const int *>(w_cat + (size_t)a.total * KB);
-  for (unsigned long long r = (unsigned long long)blockIdx.x * kPredictThreads + threadIdx.x; r < a.n_rows;
-       r += (unsigned long long)gridDim.x * kPredictThreads) {
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rows;
+       r += (unsigned long long)gridDim.x * blockDim.x) {
     if (a.cols.group && a.cols.group[r] == 0) continue;  // not a cell to fill
     double acc[KB];
 #pragma unroll
