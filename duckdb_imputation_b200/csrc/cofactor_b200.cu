@@ -344,9 +344,57 @@ int alloc_state(const Layout &L, double **f, unsigned long long **u, cudaStream_
 // ---- sparse pair counts ------------------------------------------------------------
 constexpr unsigned long long kMinHashCapacity = 1ull << 16, kMaxHashCapacity = 1ull << 30;
 
-void hash_free(cfb::PairHash &h) {
-  cudaFree(h.keys);
-  cudaFree(h.counts);
+// Large hash tables (hundreds of MB to GB) wait here for the next context / the next doubling instead of going back
+// to the driver: cudaMalloc + cudaFree of that size inside a scan cost tens to hundreds of milliseconds.  A pooled
+// pair is handed out only after the stream that last used it was drained (callers synchronise before hash_free).
+struct HashPool {
+  std::mutex mu;
+  struct Buf {
+    int device;
+    size_t bytes;
+    unsigned long long *keys, *counts;
+  };
+  std::vector<Buf> idle;
+  static constexpr size_t kMaxIdle = 3, kMinBytes = 32u << 20;
+  bool take(int device, size_t bytes, unsigned long long **keys, unsigned long long **counts) {
+    std::lock_guard<std::mutex> g(mu);
+    for (size_t i = 0; i < idle.size(); i++)
+      if (idle[i].device == device && idle[i].bytes == bytes) {
+        *keys = idle[i].keys;
+        *counts = idle[i].counts;
+        idle[i] = idle.back();
+        idle.pop_back();
+        return true;
+      }
+    return false;
+  }
+  bool give(int device, size_t bytes, unsigned long long *keys, unsigned long long *counts) {
+    if (bytes < kMinBytes) return false;
+    std::lock_guard<std::mutex> g(mu);
+    if (idle.size() >= kMaxIdle) {  // drop the smallest
+      size_t smallest = 0;
+      for (size_t i = 1; i < idle.size(); i++)
+        if (idle[i].bytes < idle[smallest].bytes) smallest = i;
+      if (idle[smallest].bytes >= bytes) return false;
+      cudaFree(idle[smallest].keys);
+      cudaFree(idle[smallest].counts);
+      idle[smallest] = idle.back();
+      idle.pop_back();
+    }
+    idle.push_back({device, bytes, keys, counts});
+    return true;
+  }
+};
+HashPool g_hash_pool;
+
+void hash_free(cfb::PairHash &h, int G = 0) {
+  int device = 0;
+  cudaGetDevice(&device);
+  const size_t bytes = (size_t)h.capacity * (size_t)std::max(G, 0) * 8;
+  if (!(G > 0 && h.keys && h.counts && g_hash_pool.give(device, bytes, h.keys, h.counts))) {
+    cudaFree(h.keys);
+    cudaFree(h.counts);
+  }
   cudaFree(h.n_entries);
   h = cfb::PairHash{};
 }
@@ -356,8 +404,13 @@ int hash_alloc(cfb::PairHash *h, unsigned long long capacity, int G, cudaStream_
   if (capacity > kMaxHashCapacity) return fail(CFB_ERR_DOMAIN, "pair hash table would need %llu slots per group", capacity);
   h->capacity = capacity;
   const size_t bytes = (size_t)capacity * G * 8;
-  cudaError_t e = cudaMalloc(&h->keys, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&h->counts, bytes);
+  int device = 0;
+  cudaGetDevice(&device);
+  cudaError_t e = cudaSuccess;
+  if (!g_hash_pool.take(device, bytes, &h->keys, &h->counts)) {
+    e = cudaMalloc(&h->keys, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->counts, bytes);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->n_entries, 8);
   if (e != cudaSuccess) {
     hash_free(*h);
@@ -394,7 +447,7 @@ int hash_reserve(cfb_ctx *c, unsigned long long add) {
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    hash_free(c->hash);
+    hash_free(c->hash, c->G);
     c->hash = nh;
   }
   c->hash_upper += add;
@@ -480,7 +533,7 @@ int ensure_domain(cfb_ctx *c, const int *lo, const int *hi, bool exact = false, 
   cudaFree(c->d_f64);
   cudaFree(c->d_u64);
   cudaFree(c->d_lay);
-  if (c->hash.capacity) hash_free(c->hash);
+  if (c->hash.capacity) hash_free(c->hash, c->G);
   c->d_f64 = nf;
   c->d_u64 = nu;
   c->d_lay = d_nl;
@@ -2111,7 +2164,7 @@ int cfb_ctx_destroy(cfb_ctx *c) {
   cudaFree(c->d_cnt_slab);
   cudaFree(c->d_packed);
   delete c->role_plan;
-  if (c->hash.capacity) hash_free(c->hash);
+  if (c->hash.capacity) hash_free(c->hash, c->G);
   for (auto &cd : c->dict)
     if (cd.on || cd.d.table) dict_free(cd);
   cudaFree(c->d_remap);
