@@ -356,8 +356,9 @@ def qda_params(labels, quad, lin, intercept, cat_keys, means=None):
 def qda_predict(params, normalize, num_cols, cat_cols):
     """Restatement of ML::qda_impute (ML/qda.cpp:338-498): score_k = intercept_k + f^T Q_k f + l_k . f over the
     features f = [numeric | one-hot] (centred when normalize; a key the model does not hold leaves its one-hot
-    block zero); the LABEL of the first class with the largest score.  PARITY UNPINNED: ML/qda.cpp does not compile
-    with g++ (qda.cpp:209), so this restatement could not be run against the reference."""
+    block zero); the LABEL of the first class with the largest score.  Pinned to the reference's own ML::qda_impute
+    (tests/test_predict_ref_cpu.py; oracle/Makefile compiles ML/qda.cpp through a one-cast sed stream because g++
+    rejects qda.cpp:209 as written)."""
     p = np.asarray(params, np.float32)
     n, m = len(num_cols), len(cat_cols)
     rows = len(num_cols[0]) if n else len(cat_cols[0])

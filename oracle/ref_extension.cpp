@@ -11,6 +11,7 @@
 
 #include <ML/lda.h>
 #include <ML/naive_bayes.h>
+#include <ML/qda.h>
 #include <ML/regression.h>
 
 namespace {
@@ -30,8 +31,7 @@ const char *Implementation() { return "reference"; }
 void Load(duckdb::DatabaseInstance &db) {
   using namespace duckdb;
   // the predict side of the write-back step, as load_ml registers it (duckdb_imputation_extension.cpp:193-249); the
-  // QDA trainer is not registered, qda_predict neither (ML/qda.cpp does not compile with g++:
-  // `new double[wkopt]` with a double, qda.cpp:209)
+  // QDA trainer is not registered
   {
     ScalarFunction lda_predict("lda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, LDA_impute, LDA_impute_bind, nullptr, LDA_impute_stats);
     lda_predict.varargs = LogicalType::ANY;
@@ -52,6 +52,11 @@ void Load(duckdb::DatabaseInstance &db) {
     linreg_train_func.varargs = LogicalType::ANY;
     linreg_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
     ExtensionUtil::RegisterFunction(db, linreg_train_func);
+    // qda_predict (duckdb_imputation_extension.cpp:234-240); ML/qda.cpp through the build copy of oracle/Makefile
+    ScalarFunction qda_predict("qda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::qda_impute, ML::qda_impute_bind, nullptr);
+    qda_predict.varargs = LogicalType::ANY;
+    qda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, qda_predict);
     ScalarFunction nb_predict("nb_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::nb_impute, ML::nb_impute_bind, nullptr);
     nb_predict.varargs = LogicalType::ANY;
     nb_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;

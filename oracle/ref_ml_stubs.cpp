@@ -53,3 +53,13 @@ extern "C" void dgemm(char *ta, char *tb, int *m, int *n, int *k, double *alpha,
   static fn f = (fn)lapack_symbol("scipy_dgemm_");
   f(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
+// qda_train (ML/qda.cpp:27-330) additionally calls dgesvd and dscal
+extern "C" void dgesvd(char *jobu, char *jobvt, int *m, int *n, double *a, int *lda, double *s, double *u, int *ldu, double *vt,
+                       int *ldvt, double *work, int *lwork, int *info) {
+  using fn = void (*)(char *, char *, int *, int *, double *, int *, double *, double *, int *, double *, int *, double *, int *, int *);
+  static fn f = (fn)lapack_symbol("scipy_dgesvd_");
+  f(jobu, jobvt, m, n, a, lda, s, u, ldu, vt, ldvt, work, lwork, info);
+}
+extern "C" void dscal(int *n, double *da, double *dx, int *incx) {
+  for (int i = 0; i < *n; i++) dx[(long)i * *incx] *= *da;
+}

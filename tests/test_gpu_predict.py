@@ -239,8 +239,9 @@ def test_nb_predict_equals_the_references_own_function(n, doms, K):
 
 @pytest.mark.parametrize("n,doms,K,normalize", [(4, [3, 5], 3, False), (4, [3, 5], 3, True), (6, [], 4, True), (0, [4, 4], 2, False)])
 def test_qda_predict_matches_the_restatement(n, doms, K, normalize):
-    """qda_predict against the numpy restatement of ML::qda_impute (parity unpinned: ML/qda.cpp does not compile with
-    g++, so the reference's own function cannot run here)."""
+    """qda_predict against the numpy restatement of ML::qda_impute (pinned to the reference in
+    tests/test_predict_ref_cpu.py) and, where oracle/_ref is present and the keys are non-negative (the reference reads
+    the parameter list's keys as FLOAT -> int), against the reference's own function."""
     rng = np.random.default_rng(11 * n + K + normalize)
     keys = [np.sort(rng.choice(np.arange(-4, 3 * d), d, replace=False)).astype(np.int32) for d in doms]
     P = n + int(sum(doms))
@@ -255,3 +256,6 @@ def test_qda_predict_matches_the_restatement(n, doms, K, normalize):
     top2 = np.sort(scores, axis=1)[:, -2:]
     clear = (top2[:, 1] - top2[:, 0]) > 1e-9 * np.abs(top2).max(axis=1)
     assert clear.mean() > 0.999 and (got[clear] == want[clear]).all()
+    if ref_replay.available() and all((k >= 0).all() for k in keys):
+        ref = ref_replay.predict("qda_predict", p, [normalize], num, cat)
+        assert (got[clear] == ref[clear]).all()

@@ -75,3 +75,28 @@ def test_reference_noise_is_gaussian_with_the_models_sigma():
     noisy = ref_replay.predict("linreg_predict", p, [True, False], num, cat)
     res = (noisy - clean).astype(np.float64)
     assert abs(res.mean()) < 0.05 and abs(res.std() - 2.5) < 0.05
+
+
+@pytest.mark.parametrize("n,m,K", [(4, 3, 3), (3, 0, 4), (0, 2, 2), (2, 1, 2)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_qda_predict_is_identical_to_the_reference(n, m, K, normalize):
+    """ML::qda_impute (ML/qda.cpp:338-498) -- compiled from the build-directory copy of qda.cpp that oracle/Makefile
+    makes (one cast at qda.cpp:209, which g++ rejects as written)."""
+    rng, num, cat, keys = _table(300 + 10 * n + m)
+    num, cat, keys = num[:n], cat[:m], keys[:m]
+    # the reference reads the keys of the parameter list as FLOAT -> int: keep them non-negative (a negative key is
+    # emitted as 2^64 + key by the trainers and never found again)
+    cat = [np.abs(c) for c in cat]
+    keys = [sorted({abs(k) for k in ks}) for ks in keys]
+    P = n + sum(len(k) for k in keys)
+    labels = [7, 3, 9, 1][:K]
+    quad = rng.normal(size=(K, P, P)) * 0.3
+    p = oracle.qda_params(labels, quad, rng.normal(size=(K, P)), rng.normal(size=K), keys,
+                          means=rng.normal(size=P) * 0.2 if normalize else None)
+    ref = ref_replay.predict("qda_predict", p, [normalize], num, cat)
+    got, scores = oracle.qda_predict(p, normalize, num, cat)
+    # rows whose two best scores are closer than fp64 summation-order noise may legitimately differ
+    top2 = np.sort(scores, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-9 * np.abs(top2).max()
+    assert clear.mean() > 0.999
+    assert np.array_equal(ref[clear], got[clear])
