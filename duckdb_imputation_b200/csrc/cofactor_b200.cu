@@ -1618,6 +1618,7 @@ int flush_tile(cfb_ctx *c) {
 }  // namespace
 extern "C" void cfb_stage_copy(void *dst, const void *src, size_t bytes);
 extern "C" void cfb_stage_gather32(void *dst, const void *src, const uint32_t *sel, size_t count);
+extern "C" void cfb_stage_minmax32(const int32_t *src, size_t count, int32_t *lo, int32_t *hi);
 namespace {
 
 template <class T>
@@ -2217,19 +2218,10 @@ int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *con
       const uint32_t *ks = cat_sel ? cat_sel[k] : nullptr;
       gather(dst, cat_cols[k], ks, done, take);
       if (!c->user_domain) {
-        // key range of the tile, read from the source (in cache) -- not from the tile, which was written around the cache
+        // key range of the tile: a contiguous vector is read from the source (in cache after the copy -- the tile itself
+        // was written around the cache), a gathered one from the tile (written with plain stores)
         int lo = c->st_lo[k], hi = c->st_hi[k];
-        const int32_t *src = cat_cols[k];
-        if (!ks)
-          for (size_t i = 0; i < take; i++) {
-            lo = std::min(lo, src[done + i]);
-            hi = std::max(hi, src[done + i]);
-          }
-        else
-          for (size_t i = 0; i < take; i++) {
-            lo = std::min(lo, src[ks[done + i]]);
-            hi = std::max(hi, src[ks[done + i]]);
-          }
+        cfb_stage_minmax32(ks ? dst : cat_cols[k] + done, take, &lo, &hi);
         c->st_lo[k] = lo;
         c->st_hi[k] = hi;
       }

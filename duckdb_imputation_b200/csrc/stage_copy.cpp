@@ -76,9 +76,54 @@ __attribute__((target("avx2"))) void gather_avx2(uint32_t *d, const uint32_t *s,
   for (; i < n; i++) d[i] = s[sel[i]];
 }
 
+// ---- key range of a staged categorical vector (domain discovery): the data is in cache, the loop must not be scalar
+using minmax_fn = void (*)(const int32_t *, size_t, int32_t *, int32_t *);
+void minmax_scalar(const int32_t *s, size_t n, int32_t *lo, int32_t *hi) {
+  int32_t a = *lo, b = *hi;
+  for (size_t i = 0; i < n; i++) {
+    a = s[i] < a ? s[i] : a;
+    b = s[i] > b ? s[i] : b;
+  }
+  *lo = a;
+  *hi = b;
+}
+__attribute__((target("avx2"))) void minmax_avx2(const int32_t *s, size_t n, int32_t *lo, int32_t *hi) {
+  size_t i = 0;
+  if (n >= 16) {
+    __m256i a0 = _mm256_loadu_si256((const __m256i *)s), a1 = _mm256_loadu_si256((const __m256i *)(s + 8)), b0 = a0, b1 = a1;
+    for (i = 16; i + 16 <= n; i += 16) {
+      const __m256i x = _mm256_loadu_si256((const __m256i *)(s + i)), y = _mm256_loadu_si256((const __m256i *)(s + i + 8));
+      a0 = _mm256_min_epi32(a0, x), b0 = _mm256_max_epi32(b0, x);
+      a1 = _mm256_min_epi32(a1, y), b1 = _mm256_max_epi32(b1, y);
+    }
+    alignas(32) int32_t va[8], vb[8];
+    _mm256_store_si256((__m256i *)va, _mm256_min_epi32(a0, a1));
+    _mm256_store_si256((__m256i *)vb, _mm256_max_epi32(b0, b1));
+    minmax_scalar(va, 8, lo, hi);
+    minmax_scalar(vb, 8, lo, hi);
+  }
+  minmax_scalar(s + i, n - i, lo, hi);
+}
+__attribute__((target("avx512f"))) void minmax_avx512(const int32_t *s, size_t n, int32_t *lo, int32_t *hi) {
+  size_t i = 0;
+  if (n >= 32) {
+    __m512i a0 = _mm512_loadu_si512(s), a1 = _mm512_loadu_si512(s + 16), b0 = a0, b1 = a1;
+    for (i = 32; i + 32 <= n; i += 32) {
+      const __m512i x = _mm512_loadu_si512(s + i), y = _mm512_loadu_si512(s + i + 16);
+      a0 = _mm512_min_epi32(a0, x), b0 = _mm512_max_epi32(b0, x);
+      a1 = _mm512_min_epi32(a1, y), b1 = _mm512_max_epi32(b1, y);
+    }
+    const int32_t mn = _mm512_reduce_min_epi32(_mm512_min_epi32(a0, a1)), mx = _mm512_reduce_max_epi32(_mm512_max_epi32(b0, b1));
+    *lo = mn < *lo ? mn : *lo;
+    *hi = mx > *hi ? mx : *hi;
+  }
+  minmax_scalar(s + i, n - i, lo, hi);
+}
+
 struct Dispatch {
   copy_fn lines = copy_lines_sse2;
   gather_fn gather = gather_scalar;
+  minmax_fn minmax = minmax_scalar;
   const char *isa = "sse2";
   Dispatch() {
     __builtin_cpu_init();
@@ -87,10 +132,12 @@ struct Dispatch {
     if (want2 && __builtin_cpu_supports("avx2")) {
       lines = copy_lines_avx2;
       gather = gather_avx2;
+      minmax = minmax_avx2;
       isa = "avx2";
     }
     if (want512 && __builtin_cpu_supports("avx512f")) {
       lines = copy_lines_avx512;
+      minmax = minmax_avx512;
       isa = "avx512";
     }
   }
@@ -126,6 +173,9 @@ void cfb_stage_copy(void *dst, const void *src, size_t bytes) {
 void cfb_stage_gather32(void *dst, const void *src, const uint32_t *sel, size_t count) {
   g_dispatch.gather((uint32_t *)dst, (const uint32_t *)src, sel, count);
 }
+
+// *lo = min(*lo, src[0..count)), *hi = max(*hi, src[0..count)): the key range of a staged categorical vector.
+void cfb_stage_minmax32(const int32_t *src, size_t count, int32_t *lo, int32_t *hi) { g_dispatch.minmax(src, count, lo, hi); }
 
 const char *cfb_stage_isa(void) { return g_dispatch.isa; }
 
