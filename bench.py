@@ -673,10 +673,11 @@ def main():
             dist.destroy_process_group()
         return 0
     achieved = rows * BYTES_PER_ROW / (kernel_ms * 1e-3) / 1e9
-    # DRAM traffic per launch: ncu --set full on this kernel (profiles/r01_gram_final_ncu_summary.txt) measured
-    # dram__bytes_read + dram__bytes_write = 20.0052 GB for 20.0000 GB of algorithmic bytes (250 M rows);
-    # the kernel has no size-dependent re-reads, so the ratio is applied to this launch's algorithmic bytes.
-    NCU_TRAFFIC_RATIO = (20.000506e9 + 4.665088e6) / 20.0e9
+    # DRAM traffic per launch: ncu --set full on this kernel (profiles/r02_gram_ncu_summary.txt; the same in round 1,
+    # profiles/r01_gram_final_ncu_summary.txt) measured dram__bytes_read + dram__bytes_write = 20.0004 GB + 4.4 MB for
+    # 20.0000 GB of algorithmic bytes (250 M rows); the kernel has no size-dependent re-reads, so the ratio is applied
+    # to this launch's algorithmic bytes.
+    NCU_TRAFFIC_RATIO = (20.000386e9 + 4.380928e6) / 20.0e9
     line = {
         "metric": "sum_to_triple rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -687,7 +688,7 @@ def main():
                    "accumulate": "fp32x2 FMA over bounded runs, folded into fp64"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": rows * BYTES_PER_ROW * NCU_TRAFFIC_RATIO, "algorithmic_bytes": rows * BYTES_PER_ROW,
-                     "traffic_source": "ncu --set full, profiles/r01_gram_final_ncu_summary.txt (bytes per launch, scaled by rows)", "kernel": "cfb::gram_scan_kernel<20,false,768>", "kernel_ms": kernel_ms,
+                     "traffic_source": "ncu --set full, profiles/r02_gram_ncu_summary.txt (bytes per launch, scaled by rows)", "kernel": "cfb::gram_scan_kernel<20,false,768>", "kernel_ms": kernel_ms,
                      "peak_source": peak_src, "hbm_gbs_whole_step": world * rows * BYTES_PER_ROW / (ms_per_step * 1e-3) / 1e9},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "check": check,
     }
