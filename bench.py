@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--rows", type=int, default=FULL_ROWS, help="rows per GPU (default: the 1 B of BASELINE.json)")
     ap.add_argument("--e2e-rows", type=int, default=64_000_000)
     ap.add_argument("--config-scale", type=float, default=1.0, help="row-count scale of the extra configs (C3..C5)")
-    ap.add_argument("--config-e2e-rows", type=int, default=8_000_000)
+    ap.add_argument("--config-e2e-rows", type=int, default=24_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
