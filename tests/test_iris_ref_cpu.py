@@ -1,0 +1,66 @@
+"""CPU suite: the reference's own ML tests (duckdb_extension/test/python/test_regression.py, test_LDA.py) replayed on
+the checkers -- (a) the REFERENCE's trainers and predict functions compiled into oracle/_ref, (b) the numpy
+restatements (oracle.linreg_train / lda_train / linreg_predict / lda_predict) -- with the reference's own criteria:
+R^2 / accuracy equal to scikit-learn's to 3 decimals.  tests/test_gpu_iris.py runs the same cases through the GPU
+build."""
+import numpy as np
+import pytest
+
+pd = pytest.importorskip("pandas")
+pytest.importorskip("sklearn")
+
+from duckdb_imputation_b200.struct_result import arrays_to_struct
+from oracle import oracle, ref_replay
+from tests.test_gpu_iris import _cols, _iris
+
+needs_ref = pytest.mark.skipif(not (ref_replay.available() and ref_replay.lapack_available()), reason="oracle/_ref cannot run the trainers here")
+NUM = ["s_length", "s_width", "p_length", "p_width"]
+
+
+def _struct(df, num, cat):
+    return arrays_to_struct(oracle.aggregate_arrays(oracle.TRIPLE, *_cols(df, num, cat))[0])
+
+
+def _sklearn_linreg(tr, te):
+    from sklearn.linear_model import LinearRegression
+    trd, ted = pd.get_dummies(tr, columns=["target"]), pd.get_dummies(te, columns=["target"])
+    reg = LinearRegression().fit(trd.drop(["s_length"], axis=1), trd["s_length"])
+    return reg.score(ted.drop(["s_length"], axis=1), ted["s_length"])
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("who", ["reference", "restatement"])
+def test_linreg_iris(who, normalize):
+    from sklearn.metrics import r2_score
+    if who == "reference" and not (ref_replay.available()):
+        pytest.skip("oracle/_ref not built")
+    tr, te, _, _ = _iris([])
+    t = _struct(tr, NUM, ["target"])
+    feats = _cols(te, ["s_width", "p_length", "p_width"], ["target"])
+    if who == "reference":
+        p = ref_replay.train("linreg_train", t, 0, 0.001, 0.0, 10000, False, normalize)
+        pred = ref_replay.predict("linreg_predict", p, [False, normalize], *feats)
+    else:
+        p, _ = oracle.linreg_train(t, 0, 0.001, 0.0, 10000, False, normalize)
+        pred = oracle.linreg_predict(np.concatenate([p, [0.0]]).astype(np.float32), normalize, *feats)  # (+ the sigma slot)
+    assert round(r2_score(te["s_length"], pred), 3) == round(_sklearn_linreg(tr, te), 3)
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("who", ["reference", "restatement"])
+def test_lda_iris(who, normalize):
+    from sklearn.discriminant_analysis import LinearDiscriminantAnalysis
+    if who == "reference" and not (ref_replay.available() and ref_replay.lapack_available()):
+        pytest.skip("oracle/_ref cannot run lda_train here")
+    tr, te, _, _ = _iris([])
+    t = _struct(tr, NUM, ["target"])
+    feats = _cols(te, NUM, [])
+    if who == "reference":
+        p = ref_replay.train("lda_train", t, 0, 0.0, normalize)
+        pred = ref_replay.predict("lda_predict", p, [normalize], *feats)
+    else:
+        p = oracle.lda_train(t, 0, 0.0, normalize)
+        idx, _ = oracle.lda_predict(p, normalize, *feats)
+        pred = idx
+    clf = LinearDiscriminantAnalysis(solver="lsqr", shrinkage=0).fit(tr[NUM], tr["target"])
+    assert round(float(np.mean(np.asarray(pred) == te["target"].to_numpy())), 3) == round(clf.score(te[NUM], te["target"]), 3)
