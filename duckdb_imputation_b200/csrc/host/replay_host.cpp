@@ -408,6 +408,70 @@ int replay_train(const char *scalar, const char *json_triple, int n_consts, cons
   }
 }
 
+int replay_train_list(const char *scalar, int nb, const char *json_triples, const int32_t *labels, size_t n_labels,
+                      int n_consts, const double *consts, const char *const_types, float **params_out, size_t *n_params_out) {
+  using namespace duckdb;
+  try {
+    if (!scalar || !json_triples || !params_out || !n_params_out || (n_labels && !labels) || (n_consts && (!consts || !const_types)))
+      throw InvalidInputException("bad arguments");
+    *params_out = nullptr;
+    *n_params_out = 0;
+    auto it = Catalog().scalars.find(scalar);
+    if (it == Catalog().scalars.end())
+      throw InvalidInputException(std::string("Catalog Error: scalar function ") + scalar + " does not exist");
+    ScalarFunction fun = it->second;
+    const LogicalType list_type = LogicalType::LIST(RingType(nb != 0));
+    ClientContext context;
+    vector<unique_ptr<Expression>> args;
+    args.push_back(make_uniq<Expression>());
+    args.back()->return_type = list_type;
+    unique_ptr<FunctionData> bind_data;
+    if (fun.bind) bind_data = fun.bind(context, fun, args);
+    // SELECT <scalar>(list(agg), list(label), <constants>): one row
+    DataChunk chunk;
+    chunk.data.emplace_back(list_type, 1);
+    const char *p = json_triples;
+    ParseValue(p, chunk.data[0], 0);
+    chunk.data.emplace_back(LogicalType::LIST(LogicalType::INTEGER), 1);
+    ListVector::Reserve(chunk.data[1], n_labels);
+    ListVector::SetListSize(chunk.data[1], n_labels);
+    if (n_labels) memcpy(FlatVector::GetData<int32_t>(ListVector::GetEntry(chunk.data[1])), labels, n_labels * sizeof(int32_t));
+    ListVector::GetData(chunk.data[1])[0] = {0, n_labels};
+    for (int i = 0; i < n_consts; i++) {
+      switch (const_types[i]) {
+        case 'i':
+          chunk.data.emplace_back(LogicalType::INTEGER, 1);
+          FlatVector::GetData<int32_t>(chunk.data.back())[0] = (int32_t)consts[i];
+          break;
+        case 'f':
+          chunk.data.emplace_back(LogicalType::FLOAT, 1);
+          FlatVector::GetData<float>(chunk.data.back())[0] = (float)consts[i];
+          break;
+        case 'b':
+          chunk.data.emplace_back(LogicalType::BOOLEAN, 1);
+          FlatVector::GetData<uint8_t>(chunk.data.back())[0] = consts[i] != 0.0;
+          break;
+        default:
+          throw InvalidInputException("replay_train_list: constant types are 'i', 'f' or 'b'");
+      }
+      chunk.data.back().SetVectorType(VectorType::CONSTANT_VECTOR);
+    }
+    chunk.SetCardinality(1);
+    ExpressionState state;
+    Vector result(LogicalType::LIST(LogicalType::FLOAT), 1);
+    fun.function(chunk, state, result);
+    const list_entry_t e = ListVector::GetData(result)[0];
+    float *out = (float *)malloc(std::max<size_t>(1, e.length) * sizeof(float));
+    memcpy(out, FlatVector::GetData<float>(ListVector::GetEntry(result)) + e.offset, e.length * sizeof(float));
+    *params_out = out;
+    *n_params_out = e.length;
+    return 0;
+  } catch (std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 int replay_scalar_structs(const char *scalar, int nb, int n_args, const char *const *json_args, size_t rows, char **json_out) {
   using namespace duckdb;
   try {

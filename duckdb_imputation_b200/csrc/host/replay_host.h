@@ -54,6 +54,10 @@ int replay_predict(const char *scalar, const float *params, size_t n_params, con
  * function returns (malloc'd, free with replay_free).                                                       */
 int replay_train(const char *scalar, const char *json_triple, int n_consts, const double *consts, const char *const_types,
                  float **params_out, size_t *n_params_out);
+/* Run  SELECT <scalar>(list(agg), list(label), c1, ...)  -- the per-class trainers (qda_train: normalize BOOLEAN;
+ * nb_train: no constants) over a LIST of ring STRUCTs (nb != 0: the four-field ring) and an INTEGER[] of labels.  */
+int replay_train_list(const char *scalar, int nb, const char *json_triples, const int32_t *labels, size_t n_labels,
+                      int n_consts, const double *consts, const char *const_types, float **params_out, size_t *n_params_out);
 /* Shapes of DuckDB's protocol that a plain table scan does not produce (process-wide; "reset" restores all):
  *   no_simple = 1          never plan an ungrouped aggregate: use update() with per-row state pointers
  *   lift_shape = 1|2|3     the lifted STRUCT reaches the aggregate as a DICTIONARY vector (1), as a flat vector with

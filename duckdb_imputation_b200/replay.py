@@ -51,6 +51,9 @@ class Replay:
         l.replay_train.restype = C.c_int
         l.replay_train.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_char_p, C.POINTER(P),
                                    C.POINTER(C.c_size_t)]
+        l.replay_train_list.restype = C.c_int
+        l.replay_train_list.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_size_t, C.c_int,
+                                        C.POINTER(C.c_double), C.c_char_p, C.POINTER(P), C.POINTER(C.c_size_t)]
         l.replay_value_ring.restype = C.c_int
         l.replay_value_ring.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.POINTER(P)]
         l.replay_value_error.restype = C.c_char_p
@@ -178,6 +181,23 @@ class Replay:
         out, n = C.c_void_p(), C.c_size_t()
         rc = self.lib.replay_train(function.encode(), json.dumps(triple).encode(), len(consts), vals, types.encode(),
                                    C.byref(out), C.byref(n))
+        if rc:
+            raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
+        try:
+            return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_float)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
+        finally:
+            self.lib.replay_free(out)
+
+    def train_list(self, function: str, triples: list, labels, *consts):
+        """SELECT function(list(agg), list(label), consts...): qda_train(triples, labels, normalize) / nb_train(triples,
+        labels) over per-class ring STRUCTs -> the FLOAT[] parameter list."""
+        nb = 0 if (triples and "quad_cat" in triples[0]) else 1
+        types = "".join("b" if isinstance(c, bool) else "i" if isinstance(c, (int, np.integer)) else "f" for c in consts)
+        vals = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
+        lab = (C.c_int32 * max(1, len(labels)))(*[int(v) for v in labels])
+        out, n = C.c_void_p(), C.c_size_t()
+        rc = self.lib.replay_train_list(function.encode(), nb, json.dumps(triples).encode(), lab, len(labels), len(consts), vals,
+                                        types.encode(), C.byref(out), C.byref(n))
         if rc:
             raise ReplayError(self.lib.replay_last_error().decode("utf-8", "replace"))
         try:

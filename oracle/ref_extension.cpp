@@ -31,7 +31,6 @@ const char *Implementation() { return "reference"; }
 void Load(duckdb::DatabaseInstance &db) {
   using namespace duckdb;
   // the predict side of the write-back step, as load_ml registers it (duckdb_imputation_extension.cpp:193-249); the
-  // QDA trainer is not registered
   {
     ScalarFunction lda_predict("lda_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, LDA_impute, LDA_impute_bind, nullptr, LDA_impute_stats);
     lda_predict.varargs = LogicalType::ANY;
@@ -57,6 +56,16 @@ void Load(duckdb::DatabaseInstance &db) {
     qda_predict.varargs = LogicalType::ANY;
     qda_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
     ExtensionUtil::RegisterFunction(db, qda_predict);
+    // the per-class trainers (duckdb_imputation_extension.cpp:219-224, :236-241): they make the parameter lists the
+    // reference's own QDA / naive-Bayes tests feed to qda_predict / nb_predict
+    ScalarFunction qda_train_func("qda_train", {LogicalType::ANY}, LogicalTypeId::LIST, ML::qda_train, ML::qda_train_bind, nullptr);
+    qda_train_func.varargs = LogicalType::ANY;
+    qda_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, qda_train_func);
+    ScalarFunction nb_train_func("nb_train", {LogicalType::ANY}, LogicalTypeId::LIST, ML::nb_train, ML::nb_train_bind, nullptr);
+    nb_train_func.varargs = LogicalType::ANY;
+    nb_train_func.null_handling = FunctionNullHandling::SPECIAL_HANDLING;
+    ExtensionUtil::RegisterFunction(db, nb_train_func);
     ScalarFunction nb_predict("nb_predict", {LogicalType::ANY}, LogicalTypeId::INTEGER, ML::nb_impute, ML::nb_impute_bind, nullptr);
     nb_predict.varargs = LogicalType::ANY;
     nb_predict.null_handling = FunctionNullHandling::SPECIAL_HANDLING;

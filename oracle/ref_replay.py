@@ -94,3 +94,12 @@ def train(function: str, triple: dict, *consts):
         os.environ.setdefault("CFB_REF_LAPACK", path)
     with _quiet_stdout():
         return ref().train(function, triple, *consts)
+
+
+def train_list(function: str, triples: list, labels, *consts):
+    """The reference's own qda_train / nb_train on per-class ring STRUCTs (GROUP BY label) -> FLOAT[] parameter list."""
+    path = _lapack_path()
+    if path:
+        os.environ.setdefault("CFB_REF_LAPACK", path)
+    with _quiet_stdout():
+        return ref().train_list(function, triples, labels, *consts)

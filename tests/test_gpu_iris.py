@@ -102,3 +102,41 @@ def test_lda_with_categorical_features_like_test_lda_cat(normalize):
     clf = LinearDiscriminantAnalysis(solver="lsqr", shrinkage=0).fit(etr.drop(["target"], axis=1), etr["target"])
     acc_py = clf.score(ete.drop(["target"], axis=1), ete["target"])
     assert round(acc_ours, 3) == round(acc_py, 3)
+
+
+def _per_class_params(kind_fn, tr, num, *consts):
+    """list(agg), list(target) FROM (SELECT agg(...) GROUP BY target) -> the REFERENCE's own per-class trainer (this
+    build has no qda_train / nb_train: out of scope) -> the FLOAT[] our predict functions must understand."""
+    from oracle import ref_replay
+    if not (ref_replay.available() and ref_replay.lapack_available()):
+        pytest.skip("oracle/_ref cannot run the reference's trainers here")
+    g = replay.glue()
+    labels = sorted(int(v) for v in tr["target"].unique())
+    agg = "sum_to_triple_%d_0" if kind_fn == "qda_train" else "sum_to_nb_agg_%d_0"
+    triples = [g.aggregate(agg % len(num), *_cols(tr[tr.target == l], num, []))[0] for l in labels]  # GPU aggregates
+    return ref_replay.train_list(kind_fn, triples, labels, *consts)
+
+
+def test_qda_predict_like_test_qda_py():
+    """test_qda_no_norm (test_QDA.py:46-68): per-class triples from the GPU aggregate, the reference's qda_train, OUR
+    qda_predict, accuracy equal to scikit-learn's QDA.  (test_qda_norm is not mirrored: the reference's qda_train with
+    normalize = true returns different parameters from call to call in one process -- uninitialised memory.)"""
+    from sklearn.discriminant_analysis import QuadraticDiscriminantAnalysis
+    tr, te, _, _ = _iris([])
+    num = ["s_length", "s_width", "p_length", "p_width"]
+    params = _per_class_params("qda_train", tr, num, False)
+    pred = replay.glue().predict("qda_predict", params, [False], *_cols(te, num, []))
+    clf = QuadraticDiscriminantAnalysis(store_covariance=True).fit(tr[num], tr["target"])
+    assert round(float(np.mean(pred == te["target"].to_numpy())), 3) == round(clf.score(te[num], te["target"]), 3)
+
+
+def test_nb_predict_like_test_nb_py():
+    """test_nb_no_norm (test_NB.py:46-72): per-class NB aggregates from the GPU, the reference's nb_train, OUR nb_predict,
+    accuracy equal to scikit-learn's GaussianNB."""
+    from sklearn.naive_bayes import GaussianNB
+    tr, te, _, _ = _iris([])
+    num = ["s_length", "s_width", "p_length", "p_width"]
+    params = _per_class_params("nb_train", tr, num)
+    pred = replay.glue().predict("nb_predict", params, [False], *_cols(te, num, []))
+    clf = GaussianNB().fit(tr[num], tr["target"])
+    assert round(float(np.mean(pred == te["target"].to_numpy())), 3) == round(clf.score(te[num], te["target"]), 3)

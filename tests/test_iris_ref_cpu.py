@@ -64,3 +64,23 @@ def test_lda_iris(who, normalize):
         pred = idx
     clf = LinearDiscriminantAnalysis(solver="lsqr", shrinkage=0).fit(tr[NUM], tr["target"])
     assert round(float(np.mean(np.asarray(pred) == te["target"].to_numpy())), 3) == round(clf.score(te[NUM], te["target"]), 3)
+
+
+@needs_ref
+@pytest.mark.parametrize("fn,pfn,kind", [("qda_train", "qda_predict", 0), ("nb_train", "nb_predict", 1)])
+def test_per_class_models_iris(fn, pfn, kind):
+    """test_QDA.py:46-68 / test_NB.py:46-72 on the reference build, and the restated predict functions on the same
+    parameter lists (class by class identical)."""
+    from sklearn.discriminant_analysis import QuadraticDiscriminantAnalysis
+    from sklearn.naive_bayes import GaussianNB
+    tr, te, _, _ = _iris([])
+    labels = sorted(int(v) for v in tr["target"].unique())
+    triples = [arrays_to_struct(oracle.aggregate_arrays(oracle.TRIPLE if kind == 0 else oracle.NB, *_cols(tr[tr.target == l], NUM, []))[0])
+               for l in labels]
+    params = ref_replay.train_list(fn, triples, labels, *((False,) if kind == 0 else ()))
+    feats = _cols(te, NUM, [])
+    ref = ref_replay.predict(pfn, params, [False], *feats)
+    mine = oracle.qda_predict(params, False, *feats)[0] if kind == 0 else oracle.nb_predict(params, *feats)[0]
+    assert np.array_equal(ref, mine)
+    clf = (QuadraticDiscriminantAnalysis(store_covariance=True) if kind == 0 else GaussianNB()).fit(tr[NUM], tr["target"])
+    assert round(float(np.mean(ref == te["target"].to_numpy())), 3) == round(clf.score(te[NUM], te["target"]), 3)
