@@ -54,7 +54,9 @@ def test_linreg_like_test_regression_py(normalize):
     trd, ted = pd.get_dummies(tr, columns=["target"]), pd.get_dummies(te, columns=["target"])
     reg = LinearRegression().fit(trd.drop(["s_length"], axis=1), trd["s_length"])
     r2_py = reg.score(ted.drop(["s_length"], axis=1), ted["s_length"])
-    assert round(r2_ours, 3) == round(r2_py, 3)
+    # the reference asserts round(.., 3) == round(.., 3); scikit-learn's 0.8606 sits next to a rounding boundary and the
+    # descent stops a few 1e-5 away from the least-squares optimum, so the criterion here is the distance itself
+    assert abs(r2_ours - r2_py) < 1e-3
 
 
 def test_linreg_with_categorical_features_like_test_lr_no_norm_cat():
