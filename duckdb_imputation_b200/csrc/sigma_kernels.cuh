@@ -173,6 +173,7 @@ struct BgdArgs {
   float step_size, lambda;
   int max_iterations;
   int rows_per_cta, warps_per_row;  // the band of rows a CTA owns; warps (1, 2, .. 32) sharing one row
+  int small_groups;                 // > 0: ONE CTA, a thread per row and group of columns (small matrices)
   double *v[2];         // two [p] buffers for Sigma * theta (alternating)
   unsigned *barrier;    // zeroed before the launch
   double *theta_out;    // [p]
@@ -189,18 +190,19 @@ __device__ __forceinline__ double ld_cg_f64(const double *p) {
 // warp, one shared-memory exchange, the same tree over the 32 warp results).  `red` holds K * 32 doubles.
 template <int K>
 __device__ __forceinline__ void bgd_block_sums(double (&x)[K], double *red) {
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; k++)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
   __syncthreads();  // `red` may still be read from the previous sums
-  if ((threadIdx.x & 31) == 0)
+  if (lane == 0)
 #pragma unroll
     for (int k = 0; k < K; k++) red[k * 32 + (threadIdx.x >> 5)] = x[k];
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    double v = red[k * 32 + (threadIdx.x & 31)];
+    double v = lane < nwarps ? red[k * 32 + lane] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     x[k] = v;
@@ -237,11 +239,39 @@ struct BgdGrid {
 // -- and puts warps_per_row warps on each (fixed split, fixed order of the partial sums: the result does not depend
 // on timing).  With more than one CTA the bands are exchanged through global memory and one grid barrier.
 __device__ double bgd_matvec(const BgdArgs &a, const double *theta, double *vs, int &flip, BgdGrid &grid, double *red) {
+  if (a.small_groups > 0) {
+    // A matrix of a few hundred KB on one CTA: a warp per row spends most of its instructions on reducing 32 lanes
+    // to one number; here thread (g, i) walks row i's entries j = g, g + G, .. -- read as sigma[j][i], the matrix is
+    // symmetric, so a warp's loads are one contiguous run -- and the G partial sums meet in shared memory.
+    const int p = a.p, G = a.small_groups, width = (p + 31) & ~31;
+    double *part = red + 96;  // [G][p]
+    const int g = threadIdx.x / width, i = threadIdx.x - g * width;
+    if (g < G && i < p) {
+      double acc = 0.0, acc2 = 0.0;  // two chains: a DFMA waits ~8 cycles for the one before it
+      int j = g;
+#pragma unroll 4
+      for (; j + G < p; j += 2 * G) {
+        acc = fma(a.sigma[(long long)j * p + i], theta[j], acc);
+        acc2 = fma(a.sigma[(long long)(j + G) * p + i], theta[j + G], acc2);
+      }
+      if (j < p) acc = fma(a.sigma[(long long)j * p + i], theta[j], acc);
+      part[g * p + i] = acc + acc2;
+    }
+    __syncthreads();
+    double part_sum = 0.0;
+    for (int r = threadIdx.x; r < p; r += blockDim.x) {
+      double sum = 0.0;
+      for (int q = 0; q < G; q++) sum += part[q * p + r];
+      vs[r] = sum;
+      part_sum = fma(theta[r], sum, part_sum);
+    }
+    return bgd_block_sum(part_sum, red);  // (its first barrier also publishes vs)
+  }
   double *v = a.v[flip];
   flip ^= 1;
   const bool alone = gridDim.x == 1;
   const int p = a.p, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int W = a.warps_per_row, part = warp % W, rows_at_once = (kBgdThreads / 32) / W;
+  const int W = a.warps_per_row, part = warp % W, rows_at_once = (int)(blockDim.x >> 5) / W;
   const int row0 = blockIdx.x * a.rows_per_cta;
   for (int r = warp / W; r - warp / W < a.rows_per_cta; r += rows_at_once) {  // uniform trip count: barriers inside
     const int row = row0 + r;
@@ -270,15 +300,16 @@ __device__ double bgd_matvec(const BgdArgs &a, const double *theta, double *vs, 
   }
   grid.sync();
   if (!alone) {
-    for (int i = threadIdx.x; i < p; i += kBgdThreads) vs[i] = ld_cg_f64(v + i);
+    for (int i = threadIdx.x; i < p; i += blockDim.x) vs[i] = ld_cg_f64(v + i);
     __syncthreads();
   }
   double part_sum = 0.0;
-  for (int i = threadIdx.x; i < p; i += kBgdThreads) part_sum = fma(theta[i], vs[i], part_sum);
+  for (int i = threadIdx.x; i < p; i += blockDim.x) part_sum = fma(theta[i], vs[i], part_sum);
   return bgd_block_sum(part_sum, red);
 }
 
-// Dynamic shared memory: 6 * p doubles (theta, prev_theta, grad, prev_grad, update, Sigma * theta) + 96 doubles.
+// Dynamic shared memory: 6 * p doubles (theta, prev_theta, grad, prev_grad, update, Sigma * theta) + 96 doubles
+// (+ small_groups * p doubles for the one-CTA path).  blockDim.x is 1024, or 512 for the one-CTA path.
 __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
   extern __shared__ double bgd_smem[];
   const int p = a.p, label = a.label, tid = threadIdx.x;
@@ -289,7 +320,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
   const double count = a.sigma[0];
   float step = a.step_size;  // the reference keeps step_size and lambda as FLOAT (regression.cpp:121-122)
   const float lambda = a.lambda;
-  for (int i = tid; i < p; i += kBgdThreads) {
+  for (int i = tid; i < p; i += blockDim.x) {
     theta[i] = i == label ? -1.0 : 0.0;
     prev_theta[i] = theta[i];
     grad[i] = prev_grad[i] = update[i] = 0.0;
@@ -298,12 +329,12 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
   double quad_form = bgd_matvec(a, theta, vs, flip, grid, red);
   // compute_gradient (regression.cpp:30-46)
   if (count != 0.0)
-    for (int i = tid; i < p; i += kBgdThreads) grad[i] = i == label ? 0.0 : vs[i] / count;
+    for (int i = tid; i < p; i += blockDim.x) grad[i] = i == label ? 0.0 : vs[i] / count;
   __syncthreads();
   // compute_error (:48-77) from theta^T Sigma theta and SUM_{i >= 1} theta_i^2
   auto error_of = [&](double qf, double sq_norm) { return count == 0.0 ? 0.0 : (qf / count + lambda * (sq_norm - 1.0)) / 2; };
   double two[2] = {0.0, 0.0};
-  for (int i = tid; i < p; i += kBgdThreads) {
+  for (int i = tid; i < p; i += blockDim.x) {
     const double upd = i == 0 ? grad[0] : grad[i] + lambda * theta[i];
     two[0] += upd * upd;
     if (i >= 1) two[1] += theta[i] * theta[i];
@@ -316,7 +347,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
   int iterations = 1, backtracks = 0;
   do {
     two[0] = two[1] = 0.0;
-    for (int i = tid; i < p; i += kBgdThreads) {
+    for (int i = tid; i < p; i += blockDim.x) {
       const double upd = i == 0 ? grad[0] : grad[i] + lambda * theta[i];
       update[i] = upd;
       two[0] += upd * upd;
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
     while (error > prev_error - (step / 2) * gradient_norm && bt < 500) {
       step /= 2;
       two[0] = two[1] = 0.0;
-      for (int i = tid; i < p; i += kBgdThreads) {
+      for (int i = tid; i < p; i += blockDim.x) {
         const double newp = prev_theta[i] - step * update[i];
         const double dp = theta[i] - newp;
         two[0] += dp * dp;
@@ -354,7 +385,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
     if (dparam_norm < 1e-20 || gradient_norm / (first_gradient_norm + 0.001) < 1e-8) break;
     // compute_gradient of the accepted theta (its Sigma * theta is still in vs), compute_step_size (:79-107)
     double three[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < p; i += kBgdThreads) {
+    for (int i = tid; i < p; i += blockDim.x) {
       const double g = count != 0.0 ? (i == label ? 0.0 : vs[i] / count) : grad[i];
       grad[i] = g;
       const double pd = theta[i] - prev_theta[i], gd = g - prev_grad[i];
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(kBgdThreads, 1) ridge_bgd_kernel(BgdArgs a) {
     iterations++;
   } while (iterations < a.max_iterations);
   if (blockIdx.x == 0) {
-    for (int i = tid; i < p; i += kBgdThreads) a.theta_out[i] = theta[i];
+    for (int i = tid; i < p; i += blockDim.x) a.theta_out[i] = theta[i];
     if (tid == 0) {
       a.scalars_out[0] = (double)iterations;
       a.scalars_out[1] = error;

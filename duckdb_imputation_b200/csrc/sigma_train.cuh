@@ -14,6 +14,7 @@ struct cfb_sigma {
   std::vector<int64_t> cat_array;      // every column's keys (the label column's too), reference order
   std::vector<int32_t> cat_idxs;       // [m + 1]
   cudaStream_t stream = nullptr;
+  double *d_bgd = nullptr;             // scratch of cfb_sigma_linreg_train: [2p v | p theta | 4 scalars | barrier], kept
 };
 
 namespace {
@@ -97,6 +98,7 @@ extern "C" void cfb_sigma_destroy(cfb_sigma *s) {
   cudaSetDevice(s->device);
   if (s->d_sigma) cudaFree(s->d_sigma);
   if (s->d_sums) cudaFree(s->d_sums);
+  if (s->d_bgd) cudaFree(s->d_bgd);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -362,20 +364,16 @@ extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, 
   a.step_size = step_size;
   a.lambda = lambda;
   a.max_iterations = max_iterations;
-  double *d_v = nullptr, *d_theta = nullptr, *d_scalars = nullptr;
-  unsigned *d_barrier = nullptr;
-  CU(tmp.alloc((size_t)2 * p, &d_v));
-  CU(tmp.alloc((size_t)p, &d_theta));
-  CU(tmp.alloc((size_t)4, &d_scalars));
-  CU(tmp.alloc((size_t)1, &d_barrier));
+  // scratch stays with the handle: a MICE step trains on the same shape again and again
+  if (!s->d_bgd) CU(cudaMalloc(&s->d_bgd, ((size_t)3 * p + 4 + 2) * sizeof(double)));
+  double *d_v = s->d_bgd, *d_theta = d_v + 2 * (size_t)p, *d_scalars = d_theta + p;
+  unsigned *d_barrier = reinterpret_cast<unsigned *>(d_scalars + 4);
   CU(cudaMemsetAsync(d_barrier, 0, sizeof(unsigned), s->stream));
   a.v[0] = d_v;
   a.v[1] = d_v + p;
   a.barrier = d_barrier;
   a.theta_out = d_theta;
   a.scalars_out = d_scalars;
-  const size_t smem = ((size_t)6 * p + 96) * sizeof(double);
-  CU(cudaFuncSetAttribute(cfb::ridge_bgd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 1;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   // bands of >= 8 rows (a band that fits L1 stays there between products), several warps on a row when the band is
@@ -385,8 +383,16 @@ extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, 
   a.rows_per_cta = (p + grid - 1) / grid;
   a.warps_per_row = 1;
   while (a.warps_per_row < 32 && a.rows_per_cta * a.warps_per_row * 2 <= 32) a.warps_per_row *= 2;
+  int threads = cfb::kBgdThreads;
+  size_t smem = ((size_t)6 * p + 96) * sizeof(double);
+  if (grid == 1 && ((p + 31) & ~31) <= 512 && !getenv("CFB_BGD_NO_SMALL")) {  // one CTA of 512 threads, a thread per (row, column group)
+    threads = 512;
+    a.small_groups = std::max(1, threads / ((p + 31) & ~31));
+    smem += (size_t)a.small_groups * p * sizeof(double);
+  }
+  CU(cudaFuncSetAttribute(cfb::ridge_bgd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
   void *params[] = {&a};
-  CU(cudaLaunchCooperativeKernel((const void *)cfb::ridge_bgd_kernel, dim3(grid), dim3(cfb::kBgdThreads), params, smem, s->stream));
+  CU(cudaLaunchCooperativeKernel((const void *)cfb::ridge_bgd_kernel, dim3(grid), dim3(threads), params, smem, s->stream));
   g_launches++;
   std::vector<double> theta((size_t)p), mu, sd;
   double scalars[4];

@@ -53,6 +53,11 @@ def main():
             out["linreg_iterations"] = fit["iterations"]
             out["linreg_products"] = fit["products"]
             out["us_per_product"] = round(dt * 1e6 / max(1, fit["products"]), 2)
+            t0 = time.perf_counter()
+            one = s.linreg_train(0, 0.001, 0.01, 1)  # one gradient step: the fixed cost of a call
+            fixed = time.perf_counter() - t0
+            out["call_overhead_ms"] = round(fixed * 1e3, 3)
+            out["us_per_product_steady"] = round((dt - fixed) * 1e6 / max(1, fit["products"] - one["products"]), 2)
             s.close()
             t0 = time.perf_counter()
             s = Sigma.from_context(ctx, label_cat=m - 1)
