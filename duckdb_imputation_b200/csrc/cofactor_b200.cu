@@ -27,6 +27,7 @@
 #include <dlfcn.h>
 #include <emmintrin.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects itself
 
 #include "gram_launch.h"
 #include "group_kernel.cuh"
@@ -54,6 +55,15 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_timing{0};
+
+// One NVTX range per C-ABI call (tracing): nsys / ncu --nvtx show the callbacks' appends, combines and
+// finalizes over the kernels they launch.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -1474,13 +1484,26 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
     if (hashed) slice = std::max<unsigned long long>(1ull << 18, ((1ull << 24) / npairs) & ~1023ull);
     else if (c->kind == CFB_TRIPLE && c->m >= 2)  // bounds the packed-slot scratch of the pair kernel ((m+1) bytes per row)
       slice = std::max<unsigned long long>(1ull << 20, (unsigned long long)env_int("CFB_CAT_SLICE_ROWS", 32 << 20) & ~16383ull);
+    // When the table for the WHOLE call fits the budget it is reserved once, here: growing slice by slice costs a
+    // cudaMalloc, a rehash of everything seen so far and a stream synchronisation per doubling.
+    bool reserved_whole = false;
+    if (hashed && rows > slice) {
+      const unsigned long long budget = (unsigned long long)std::max(0, env_int("CFB_HASH_RESERVE_MB", 8192)) << 20;
+      const unsigned long long whole = std::min<unsigned long long>(rows * npairs, (unsigned long long)dense_pair_entries(c->lay));
+      if (pow2_at_least((c->hash_upper + whole) * 2) * (unsigned long long)c->G * 16 <= budget) {
+        if (s != c->stream) CU(cudaStreamSynchronize(s));
+        int rc = hash_reserve(c, whole);
+        if (rc) return rc;
+        reserved_whole = true;
+      }
+    }
     for (unsigned long long r0 = 0; r0 < rows; r0 += slice) {
       const unsigned long long cnt = std::min(slice, rows - r0);
       cfb::ScanCols part = sc;
       for (int k = 0; k < c->n; k++) part.num[k] = num[k] + r0;
       for (int k = 0; k < c->m; k++) part.cat[k] = cat[k] + r0;
       if (group) part.group = group + r0;
-      if (hashed) {
+      if (hashed && !reserved_whole) {
         if (s != c->stream) CU(cudaStreamSynchronize(s));
         const unsigned long long worst = std::min<unsigned long long>(cnt * npairs, (unsigned long long)dense_pair_entries(c->lay));
         int rc = hash_reserve(c, worst);
@@ -2002,6 +2025,7 @@ extern "C" int cfb_model_create_qda(int device, const cfb_qda_model *M, cfb_mode
 
 extern "C" int cfb_predict_device(cfb_model *M, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                                   const int32_t *d_row_mask, size_t n_rows, int mode, void *d_out, void *stream) {
+  NvtxRange nvtx_range("cfb_predict_device");
   if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
   if (n_rows == 0) return CFB_OK;
   const int mn = M->type == 0 ? M->args.n : (M->type == 1 ? M->nb.n : M->qda.n), mm = M->type == 0 ? M->args.m : (M->type == 1 ? M->nb.m : M->qda.m);
@@ -2013,6 +2037,7 @@ extern "C" int cfb_predict_device(cfb_model *M, const float *const *d_num_cols, 
 extern "C" int cfb_predict_host(cfb_model *M, const float *const *num_cols, const uint32_t *const *num_sel,
                                 const int32_t *const *cat_cols, const uint32_t *const *cat_sel, size_t count, int mode,
                                 void *out) {
+  NvtxRange nvtx_range("cfb_predict_host");
   if (!M) return fail(CFB_ERR_INVALID, "model is NULL");
   if (count == 0) return CFB_OK;
   const int n = M->type == 0 ? M->args.n : (M->type == 1 ? M->nb.n : M->qda.n), m = M->type == 0 ? M->args.m : (M->type == 1 ? M->nb.m : M->qda.m);
@@ -2192,6 +2217,7 @@ int cfb_ctx_set_cat_domain(cfb_ctx *c, const int32_t *lo, const int32_t *hi) {
 int cfb_ctx_append(cfb_ctx *c, const float *const *num_cols, const uint32_t *const *num_sel,
                    const int32_t *const *cat_cols, const uint32_t *const *cat_sel, const uint32_t *group_slot,
                    size_t count) {
+  NvtxRange nvtx_range("cfb_ctx_append");
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
   if (int rc = check_open(c)) return rc;
   if (count == 0) return CFB_OK;
@@ -2257,6 +2283,7 @@ int cfb_ctx_append_triples_slot(cfb_ctx *c, int slot, size_t count, const int32_
                                 const cfb_list_entry *num_cat_lists, const int32_t *nc_key, const float *nc_val,
                                 const cfb_list_entry *cat_cat_lists, const int32_t *cc_key1, const int32_t *cc_key2,
                                 const float *cc_val) {
+  NvtxRange nvtx_range("cfb_ctx_append_triples_slot");
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
   if (int rc = check_open(c)) return rc;
   if (slot < 0 || slot >= c->G) return fail(CFB_ERR_INVALID, "slot %d out of range", slot);
@@ -2387,6 +2414,7 @@ int cfb_ctx_append_triples_slot(cfb_ctx *c, int slot, size_t count, const int32_
 
 int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t *const *d_cat_cols,
                       const int32_t *d_group_slot, size_t n_rows, void *stream) {
+  NvtxRange nvtx_range("cfb_triple_device");
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
   if (int rc = check_open(c)) return rc;
   if ((c->n && !d_num_cols) || (c->m && !d_cat_cols)) return fail(CFB_ERR_INVALID, "column array is NULL");
@@ -2415,6 +2443,7 @@ int cfb_triple_device(cfb_ctx *c, const float *const *d_num_cols, const int32_t 
 }
 
 int cfb_ctx_sync(cfb_ctx *c) {
+  NvtxRange nvtx_range("cfb_ctx_sync");
   if (!c) return fail(CFB_ERR_INVALID, "ctx is NULL");
   CU(cudaSetDevice(c->device));
   int rc = flush_tile(c);
@@ -2486,6 +2515,7 @@ int cfb_ctx_combine(cfb_ctx *dst, const cfb_ctx *src) {
 
 int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src_c, size_t n_pairs, const int32_t *dst_slots,
                           const int32_t *src_slots) {
+  NvtxRange nvtx_range("cfb_ctx_combine_slots");
   cfb_ctx *src = const_cast<cfb_ctx *>(src_c);
   if (!dst || !src) return fail(CFB_ERR_INVALID, "ctx is NULL");
   if (int rc = check_open(dst)) return rc;
@@ -2638,6 +2668,7 @@ int cfb_ctx_combine_slots(cfb_ctx *dst, const cfb_ctx *src_c, size_t n_pairs, co
 }
 
 int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
+  NvtxRange nvtx_range("cfb_ctx_finalize");
   if (!c || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (group < 0 || group >= c->G) return fail(CFB_ERR_INVALID, "group %d out of range", group);
   memset(out, 0, sizeof(*out));
@@ -2789,6 +2820,7 @@ int cfb_ctx_finalize(cfb_ctx *c, int group, cfb_result *out) {
 }
 
 int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *out) {
+  NvtxRange nvtx_range("cfb_result_multiply");
   if (!a || !b || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (a->kind != b->kind) return fail(CFB_ERR_INVALID, "multiply: a triple and an NB aggregate do not mix");
   const bool nb = a->kind == CFB_NB;
@@ -2902,6 +2934,7 @@ int cfb_result_multiply(const cfb_result *a, const cfb_result *b, cfb_result *ou
 }
 
 int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int flags, cfb_result *out) {
+  NvtxRange nvtx_range("cfb_result_combine");
   if (!a || !b || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (sign != 1 && sign != -1) return fail(CFB_ERR_INVALID, "sign must be +1 or -1");
   if (flags & ~CFB_COMBINE_KEEP_ZERO_KEYS) return fail(CFB_ERR_INVALID, "combine: unknown flag");
@@ -2999,6 +3032,7 @@ int cfb_result_combine(const cfb_result *a, const cfb_result *b, int sign, int f
 }
 
 int cfb_result_impute_linear(const cfb_result *a, const cfb_linear_model *M, int target, cfb_result *out) {
+  NvtxRange nvtx_range("cfb_result_impute_linear");
   if (!a || !M || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   if (a->kind != CFB_TRIPLE) return fail(CFB_ERR_INVALID, "impute_linear needs the full ring (CFB_TRIPLE)");
   const int n = a->n_num, m = a->n_cat;
@@ -3468,6 +3502,7 @@ static int allreduce_results(cfb_ctx *c, ncclComm_t comm, cudaStream_t s) {
 }
 
 int cfb_ctx_allreduce(cfb_ctx *c, void *comm, void *stream) {
+  NvtxRange nvtx_range("cfb_ctx_allreduce");
   if (!c || !comm) return fail(CFB_ERR_INVALID, "NULL argument");
   if (int rc0 = check_open(c)) return rc0;
   if (c->lay.pairs_hashed || any_dict(c) || (c->m > 0 && !c->user_domain)) {

@@ -104,6 +104,7 @@ extern "C" void cfb_sigma_destroy(cfb_sigma *s) {
 }
 
 extern "C" int cfb_sigma_from_result(int device, const cfb_result *res, int label_cat, int drop_first, cfb_sigma **out) {
+  NvtxRange nvtx_range("cfb_sigma_from_result");
   if (!res || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (res->kind != CFB_TRIPLE) return fail(CFB_ERR_INVALID, "the sigma matrix needs the full ring (CFB_TRIPLE)");
@@ -200,6 +201,7 @@ extern "C" int cfb_sigma_from_result(int device, const cfb_result *res, int labe
 }
 
 extern "C" int cfb_sigma_from_ctx(cfb_ctx *c, int group, int label_cat, int drop_first, cfb_sigma **out) {
+  NvtxRange nvtx_range("cfb_sigma_from_ctx");
   if (!c || !out) return fail(CFB_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (c->kind != CFB_TRIPLE) return fail(CFB_ERR_INVALID, "the sigma matrix needs the full ring (CFB_TRIPLE)");
@@ -346,6 +348,7 @@ int sigma_standardized_copy(const cfb_sigma *s, SigmaScratch &tmp, double **work
 
 extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, float lambda, int max_iterations, int normalize,
                                       double *coeff, double *means, double *variance, int32_t *iterations, int32_t *products) {
+  NvtxRange nvtx_range("cfb_sigma_linreg_train");
   if (!s || !coeff) return fail(CFB_ERR_INVALID, "NULL argument");
   if (s->label_cat >= 0) return fail(CFB_ERR_STATE, "this sigma matrix leaves a categorical label out (LDA): build one with label_cat = -1");
   if (label < 0 || label >= s->n) return fail(CFB_ERR_INVALID, "label %d is not a numeric column (0..%d)", label, s->n - 1);
@@ -419,6 +422,7 @@ extern "C" int cfb_sigma_linreg_train(cfb_sigma *s, int label, float step_size, 
 }
 
 extern "C" int cfb_sigma_lda_train(cfb_sigma *s, float shrinkage, int normalize, double *coef, double *intercept, double *means) {
+  NvtxRange nvtx_range("cfb_sigma_lda_train");
   if (!s || !coef || !intercept) return fail(CFB_ERR_INVALID, "NULL argument");
   if (s->label_cat < 0 || s->n_classes == 0) return fail(CFB_ERR_STATE, "this sigma matrix has no categorical label: build one with label_cat >= 0");
   CU(cudaSetDevice(s->device));
