@@ -802,6 +802,7 @@ int launch_gram(cfb_ctx *c, const float *const *cols, unsigned long long rows, c
   p.partials = c->d_partials;
   p.state = c->d_f64;  // ungrouped: slot 0, [lin | quad] leads the f64 array
   p.ticket = c->d_ticket;
+  p.count = c->d_u64;  // ungrouped: N of slot 0
   p.stream = s;
   p.device = c->device;
   const cudaError_t e = (c->kind == CFB_NB ? kGramNb : kGramTriple)[c->n - 1](p);
@@ -1462,11 +1463,12 @@ int scan_device(cfb_ctx *c, const float *const *num, const int32_t *const *cat, 
   if (c->timed) CU(cudaEventRecord(c->ev0, s));
   if (!grouped) {
     if (c->n > 0) {
-      int rc = launch_gram(c, num, rows, s);
+      int rc = launch_gram(c, num, rows, s);  // (N += rows goes along)
       if (rc) return rc;
+    } else {
+      cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
+      g_launches++;
     }
-    cfb::add_rows_kernel<<<1, 32, 0, s>>>(c->d_u64, rows);
-    g_launches++;
   }
   int slab_numeric = grouped ? 1 : 0;
   bool keys_done = false;  // the Naive-Bayes key counts went along with the numeric part

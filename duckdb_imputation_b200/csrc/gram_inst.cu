@@ -37,6 +37,7 @@ cudaError_t gram_launch(const GramLaunchParams &p) {
   a.partials = p.partials;
   a.state = p.state;
   a.ticket = p.ticket;
+  a.count = p.count;
   const unsigned long long tiles = ((p.rows & ~3ull) + TR - 1) / TR;
   const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(p.max_grid, tiles));
   kern<<<grid, S::kThreads, smem, p.stream>>>(a);

@@ -142,6 +142,7 @@ struct GramArgs {
   double *partials;           // [gridDim.x][kOut]
   double *state;              // [kOut] context totals (lin | quad), += at the end
   unsigned int *ticket;       // zero-initialised; reset by the last CTA
+  unsigned long long *count;  // N of the context: += n_rows by the last CTA (nullptr: not wanted)
 };
 
 // Rows per ring stage.  A tile is consumed in 128-row warp iterations split over kGroups row
@@ -409,7 +410,10 @@ __global__ void __launch_bounds__(GramShape<N, DIAG>::kThreads, 1)
       }
       a.state[t] += s;
     }
-    if (threadIdx.x == 0) *a.ticket = 0u;
+    if (threadIdx.x == 0) {
+      *a.ticket = 0u;
+      if (a.count) *a.count += a.n_rows;  // (a launch of its own for one add cost C1 a tenth of its time)
+    }
   }
 }
 

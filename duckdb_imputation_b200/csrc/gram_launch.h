@@ -17,6 +17,7 @@ struct GramLaunchParams {
   double *partials;
   double *state;
   unsigned int *ticket;
+  unsigned long long *count;  // N += rows along with the sums (nullptr: not wanted)
   cudaStream_t stream;
   int device;
 };
